@@ -1,0 +1,668 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY ("parity unpinned").
+
+CPU restatement (numpy + the plain-C iteration in oracle/oem_oracle.c) of the five C++
+entry points of jaredhuling/oem 2.0.12 that make up the hot path:
+
+    oem_fit_dense            src/oem_dense.cpp:30-309,   src/oem_dense.h, src/DataStd.h
+    oem_xtx                  src/oem_xtx.cpp:29-219,     src/oem_xtx.h
+    oem_xval_dense           src/oem_xval_dense.cpp:31-477, src/oem_xval_dense.h
+    oem_fit_logistic_dense   src/oem_logistic_dense.cpp:29-313, src/oem_logistic_dense.h
+    oem_fit_big              src/oem_big.cpp:30-258,     src/oem_big.h
+
+Each function keeps the reference's argument order and returns the reference's named list
+as a dict (beta / lambda / niter / loss / d [/ cvm / cvsd]).  Only tests/, smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module; the product never does.
+
+The reference cannot be built here (no R / Rcpp / Eigen / Spectra) and ships no tests or
+golden vectors, so this oracle is pinned only by the identities the reference's own examples
+print (oem == oem.xtx, KKT conditions, ...; tests/test_oracle.py) -- "parity unpinned".
+
+Third-party arithmetic restated (not vendored under /root/reference):
+  * Eigen (RcppEigen, unpinned): SYRK/GEMV = numpy/OpenBLAS here; LinSpaced = linspace_eigen().
+  * Spectra::SymEigsSolver (RSpectra >= 0.16-2), nev=1, tol 1e-10: the oracle defines the top
+    eigenvalue as the converged one (numpy.linalg.eigvalsh).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+PENALTIES = ["lasso", "ols", "elastic.net", "scad", "scad.net", "mcp", "mcp.net", "grp.lasso",
+             "grp.lasso.net", "grp.mcp", "grp.scad", "grp.mcp.net", "grp.scad.net", "sparse.grp.lasso"]
+PEN_ID = {name: i for i, name in enumerate(PENALTIES)}
+
+
+class _Pen(ctypes.Structure):
+    _fields_ = [("q", ctypes.c_int), ("penalty", ctypes.c_int),
+                ("alpha", ctypes.c_double), ("gamma", ctypes.c_double), ("tau", ctypes.c_double),
+                ("pen_fact", ctypes.c_void_p), ("ngroups", ctypes.c_int),
+                ("unique_groups", ctypes.c_void_p), ("grp_ptr", ctypes.c_void_p),
+                ("grp_idx", ctypes.c_void_p), ("group_weights", ctypes.c_void_p)]
+
+
+def build(force=False):
+    """Compile oracle/oem_oracle.c into oracle/_build/liboem_oracle.so (gcc, OpenMP)."""
+    out_dir = os.path.join(_HERE, "_build")
+    so = os.path.join(out_dir, "liboem_oracle.so")
+    src = os.path.join(_HERE, "oem_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-march=x86-64-v2", "-fopenmp", "-fPIC", "-shared", "-o", so, src, "-lm"])
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.oracle_solve.restype = ctypes.c_int
+        _LIB.oracle_solve.argtypes = [ctypes.POINTER(_Pen), ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double,
+                                      ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]
+        _LIB.oracle_stop_rule.restype = ctypes.c_int
+        _LIB.oracle_stop_rule.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double]
+        _LIB.oracle_xtx.restype = None
+        _LIB.oracle_xtx.argtypes = [ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    return _LIB
+
+
+def stop_rule(cur, prev, tol):
+    """src/utils.cpp:537-549."""
+    cur = np.ascontiguousarray(cur, dtype=np.float64)
+    prev = np.ascontiguousarray(prev, dtype=np.float64)
+    return bool(_lib().oracle_stop_rule(cur.size, cur.ctypes.data, prev.ctypes.data, float(tol)))
+
+
+def xtx_port(X, ncores=1):
+    """Row-sliced lower SYRK restated in plain C (src/oem_dense.h:318-361)."""
+    X = np.asfortranarray(X, dtype=np.float64)
+    n, p = X.shape
+    G = np.zeros((p, p), order="F")
+    _lib().oracle_xtx(n, p, X.ctypes.data, G.ctypes.data, int(ncores))
+    return G
+
+
+def linspace_eigen(N, lo, hi):
+    """Eigen >= 3.3 LinSpaced (linspaced_op_impl, not vendored): see SURVEY.md A.1."""
+    N = int(N)
+    if N == 1:
+        return np.array([lo], dtype=np.float64)
+    step = (hi - lo) / float(N - 1)
+    v = np.empty(N, dtype=np.float64)
+    if abs(hi) < abs(lo):
+        for i in range(N):
+            v[i] = hi - float(N - 1 - i) * step
+        v[0] = lo
+    else:
+        for i in range(N):
+            v[i] = lo + float(i) * step
+        v[N - 1] = hi
+    return v
+
+
+def lambda_base(lmax, nl, lmin_ratio):
+    """src/oem_dense.cpp:179-186: exp(LinSpaced(nl, log(lmax), log(lmin_ratio*lmax)))."""
+    import math
+    lmin = lmin_ratio * lmax
+    v = linspace_eigen(nl, math.log(lmax), math.log(lmin))
+    return np.array([math.exp(t) for t in v], dtype=np.float64)
+
+
+def top_eig(XX):
+    """Converged largest algebraic eigenvalue (stands in for Spectra)."""
+    return float(np.linalg.eigvalsh(XX)[-1])
+
+
+class _Groups:
+    """get_group_indexes (src/oem_dense.h:421-456): members of each unique group among the first
+    `scan` entries of `groups`, default weights sqrt(|g|); logistic sets w=0 for group 0
+    (src/oem_logistic_dense.h:421-437)."""
+
+    def __init__(self, groups, unique_groups, group_weights, scan, zero_weight_for_group0=False):
+        groups = np.asarray(groups, dtype=np.int32).ravel()
+        self.unique = np.ascontiguousarray(np.asarray(unique_groups, dtype=np.int32).ravel())
+        ptr, idx = [0], []
+        for g in self.unique:
+            members = [v for v in range(min(scan, groups.size)) if groups[v] == g]
+            idx.extend(members)
+            ptr.append(len(idx))
+        self.ptr = np.ascontiguousarray(np.array(ptr, dtype=np.int32))
+        self.idx = np.ascontiguousarray(np.array(idx if idx else [0], dtype=np.int32))
+        gw = np.asarray(group_weights, dtype=np.float64).ravel()
+        if gw.size < 1:
+            gw = np.sqrt(np.diff(self.ptr).astype(np.float64))
+            if zero_weight_for_group0:
+                gw = np.where(self.unique == 0, 0.0, gw)
+        self.weights = np.ascontiguousarray(gw)
+
+
+class _Solver:
+    """State shared by the five solvers: beta (warm start), Nesterov ak, penalty descriptor."""
+
+    def __init__(self, q, pen_fact, grp, maxit, tol, accelerate=False):
+        self.q = q
+        self.pf = np.ascontiguousarray(pen_fact, dtype=np.float64)
+        self.grp = grp
+        self.maxit, self.tol, self.accelerate = int(maxit), float(tol), bool(accelerate)
+        self.beta = np.zeros(q)
+        self.ak = ctypes.c_double(1.0)
+
+    def init(self, penalty, alpha, gamma, tau):
+        # init(): src/oem_dense.h:723-746 -- beta = 0, ak = 1
+        self.beta = np.zeros(self.q)
+        self.ak = ctypes.c_double(1.0)
+        g = self.grp
+        self.pen = _Pen(self.q, PEN_ID[penalty], float(alpha), float(gamma), float(tau),
+                        self.pf.ctypes.data, int(g.unique.size), g.unique.ctypes.data,
+                        g.ptr.ctypes.data, g.idx.ctypes.data, g.weights.ctypes.data)
+
+    def solve(self, A, XY, d, lam):
+        A = np.asfortranarray(A)
+        XY = np.ascontiguousarray(XY)
+        return _lib().oracle_solve(ctypes.byref(self.pen), A.ctypes.data, XY.ctypes.data, float(d),
+                                   float(lam), self.maxit, self.tol, int(self.accelerate),
+                                   ctypes.byref(self.ak), self.beta.ctypes.data)
+
+
+def _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha, logistic_fudge=None, gamma=None):
+    """Per-penalty lambda vectors: src/oem_dense.cpp:179-227 (logistic .net mcp/scad fudge:
+    src/oem_logistic_dense.cpp:210-225)."""
+    provided = len(lambda_) > 0 and np.asarray(lambda_[0]).size >= 1
+    base = None if provided else lambda_base(lmax, nlambda, lmin_ratio)
+    out = []
+    for pp, pen in enumerate(penalty):
+        if provided:
+            lam = np.asarray(lambda_[pp], dtype=np.float64).copy()
+        elif ".net" in pen:
+            lam = base / alpha
+            if logistic_fudge and ("mcp" in pen or "scad" in pen):
+                fact = 3.5 - min(3.5, gamma) * 5.71425 / 8.0
+                lam = fact * base / (alpha ** 0.8)
+        else:
+            lam = base.copy()
+        out.append(lam)
+    return out
+
+
+def _as_opts(opts):
+    o = dict(maxit=500, tol=1e-7, irls_maxit=100, irls_tol=1e-3, ncores=1,
+             hessian_type="upper.bound", accelerate=False, gigs=4.0)
+    for k, v in (opts or {}).items():
+        o[k.replace(".", "_")] = v
+    return o
+
+
+def _gamma_for(gamma, pp):
+    """API extension shared with the product: gamma may be one value per penalty."""
+    g = np.atleast_1d(np.asarray(gamma, dtype=np.float64))
+    return float(g[pp] if g.size > 1 else g[0])
+
+
+# ------------------------------------------------------------------------------------------
+# oem_fit_dense
+# ------------------------------------------------------------------------------------------
+def standardize(X, Y, standardize_, intercept):
+    """DataStd::standardize, no-weights branch (src/DataStd.h:94-267).  Returns
+    (Xs, Ys, meanX, scaleX, meanY, scaleY); quirk: flag 2 falls through into flag 3 for y."""
+    flag = int(bool(standardize_)) + 2 * int(bool(intercept))
+    n, p = X.shape
+    X = np.array(X, dtype=np.float64, order="F", copy=True)
+    Y = np.array(Y, dtype=np.float64, copy=True)
+    meanY, scaleY = 0.0, 1.0
+    meanX, scaleX = np.zeros(p), np.ones(p)
+    n_invsqrt = 1.0 / np.sqrt(float(n))
+    if flag == 1:
+        scaleY = float(np.linalg.norm(Y - Y.mean()) / np.sqrt(float(n)))
+        Y /= scaleY
+    elif flag in (2, 3):
+        meanY = float(Y.mean())
+        Y -= meanY
+        scaleY = float(np.linalg.norm(Y) * n_invsqrt)
+        Y /= scaleY
+    for i in range(p):
+        if flag == 1:
+            col = X[:, i]
+            s = float(np.linalg.norm(col - col.mean()) / np.sqrt(float(n)))
+            scaleX[i] = 1.0 if s == 0.0 else s
+            X[:, i] *= (1.0 / scaleX[i])
+        elif flag == 2:
+            meanX[i] = X[:, i].mean()
+            X[:, i] -= meanX[i]
+        elif flag == 3:
+            meanX[i] = X[:, i].mean()
+            X[:, i] -= meanX[i]
+            s = float(np.linalg.norm(X[:, i]) * n_invsqrt)
+            scaleX[i] = 1.0 if s == 0.0 else s
+            X[:, i] /= scaleX[i]
+    return X, Y, meanX, scaleX, meanY, scaleY, flag
+
+
+def recover(flag, coef, meanX, scaleX, meanY, scaleY):
+    """DataStd::recover (src/DataStd.h:269-293)."""
+    coef = coef.copy()
+    beta0 = 0.0
+    if flag == 1:
+        coef /= scaleX
+        coef *= scaleY
+    elif flag == 2:
+        coef *= scaleY
+        beta0 = meanY - float((coef * meanX).sum())
+    elif flag == 3:
+        coef /= scaleX
+        coef *= scaleY
+        beta0 = meanY - float((coef * meanX).sum())
+    return beta0, coef
+
+
+def oem_fit_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_,
+                  nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize_, intercept,
+                  compute_loss, opts, xtx_fn=None):
+    """src/oem_dense.cpp:30-309."""
+    o = _as_opts(opts)
+    if family != "gaussian":
+        raise ValueError("binomial not available for oem_fit_dense, use oem_fit_logistic_dense")
+    if np.asarray(weights).size:
+        raise ValueError("weights not implemented yet.")   # R/oem.R:244
+    x = np.asarray(x, dtype=np.float64)
+    n, p = x.shape
+    X, Y, meanX, scaleX, meanY, scaleY, flag = standardize(x, y, standardize_, intercept)
+    # init_oem: src/oem_dense.h:693-712, compute_XtX_d_update_A :458-506
+    XY = X.T @ Y / n
+    XX = (xtx_fn(X) if xtx_fn else X.T @ X) / n
+    d = top_eig(XX) * 1.005
+    A = -XX
+    A[np.diag_indices(p)] += d
+    lmax = float(np.abs(XY).max()) * scaleY
+    lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha)
+    grp = _Groups(groups, unique_groups, group_weights, scan=p)
+    s = _Solver(p, penalty_factor, grp, o["maxit"], o["tol"], o["accelerate"])
+    out = dict(beta=[], lambda_=[], niter=[], loss=[], d=d)
+    for pp, pen in enumerate(penalty):
+        lam = lams[pp]
+        L = 1 if pen == "ols" else lam.size
+        beta = np.zeros((p + 1, L), order="F")
+        niter = np.zeros(L, dtype=np.int32)
+        loss = np.full(L, 1e99)
+        s.init(pen, alpha, _gamma_for(gamma, pp), tau)
+        for i in range(L):
+            niter[i] = s.solve(A, XY, d, lam[i] / scaleY)
+            b0, res = recover(flag, s.beta, meanX, scaleX, meanY, scaleY)
+            beta[0, i] = b0
+            beta[1:, i] = res
+            if compute_loss:
+                loss[i] = float(((Y - X @ s.beta) ** 2).sum())
+        out["beta"].append(beta)
+        out["lambda_"].append(lam)
+        out["niter"].append(niter)
+        out["loss"].append(loss)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# oem_xtx
+# ------------------------------------------------------------------------------------------
+def oem_xtx(xtx, xty, family, penalty, groups, unique_groups, group_weights, lambda_, nlambda,
+            lmin_ratio, alpha, gamma, tau, scale_factor, penalty_factor, opts):
+    """src/oem_xtx.cpp:29-219, src/oem_xtx.h:347-381,520-581."""
+    o = _as_opts(opts)
+    if family != "gaussian":
+        raise ValueError("binomial not available for oem_fit_dense, use oem_fit_logistic_dense")
+    XX = np.array(xtx, dtype=np.float64, order="F")
+    p = XX.shape[1]
+    XY = np.array(xty, dtype=np.float64).ravel().copy()
+    sf = np.asarray(scale_factor, dtype=np.float64).ravel()
+    sinv = None
+    if sf.size:
+        sinv = 1.0 / sf
+        XY = XY * sinv
+        XX = sinv[:, None] * XX * sinv[None, :]
+    d = top_eig(XX) * 1.005
+    A = -XX
+    A[np.diag_indices(p)] += d
+    lmax = float(np.abs(XY).max())
+    lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha)
+    grp = _Groups(groups, unique_groups, group_weights, scan=p)
+    s = _Solver(p, penalty_factor, grp, o["maxit"], o["tol"])
+    out = dict(beta=[], lambda_=[], niter=[], loss=[], d=d)
+    for pp, pen in enumerate(penalty):
+        lam = lams[pp]
+        L = 1 if pen == "ols" else lam.size
+        beta = np.zeros((p, L), order="F")
+        niter = np.zeros(L, dtype=np.int32)
+        s.init(pen, alpha, _gamma_for(gamma, pp), tau)
+        for i in range(L):
+            niter[i] = s.solve(A, XY, d, lam[i])
+            if sinv is not None:
+                s.beta *= sinv          # get_beta() mutates the iterate (src/oem_xtx.h:576-581)
+            beta[:, i] = s.beta
+        out["beta"].append(beta)
+        out["lambda_"].append(lam)
+        out["niter"].append(niter)
+        out["loss"].append(np.full(L, 1e99))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# oem_xval_dense
+# ------------------------------------------------------------------------------------------
+def fold_parts(X, Y, foldid, nfolds, intercept):
+    """XtX_xval / XtX_xval_int (src/oem_xval_dense.h:358-484): per-fold Gram pieces."""
+    p = X.shape[1]
+    parts = []
+    for k in range(1, nfolds + 1):
+        idx = np.nonzero(foldid == k)[0]
+        sub, sub_y = X[idx, :], Y[idx]
+        G = sub.T @ sub
+        b = sub.T @ sub_y
+        if intercept:
+            cs = sub.sum(axis=0)
+            Gi = np.zeros((p + 1, p + 1))
+            Gi[1:, 1:] = G
+            Gi[0, 1:] = cs
+            Gi[1:, 0] = cs
+            Gi[0, 0] = idx.size
+            G = Gi
+            b = np.concatenate([[sub_y.sum()], b])
+        parts.append(dict(xtx=G, xty=b, nobs=idx.size, colsq=(sub ** 2).sum(axis=0)))
+    return parts
+
+
+def assemble(parts, skip_fold, p, standardize_, intercept):
+    """compute_/update_XtX_d_update_A (src/oem_xval_dense.h:731-788, 791-853): sum the parts
+    except fold `skip_fold` (1-based; 0 = none), uncentred scaling, /n, top eigenvalue."""
+    q = p + int(intercept)
+    XX, XY, colsq, nobs = np.zeros((q, q)), np.zeros(q), np.zeros(p), 0
+    for k, part in enumerate(parts, start=1):
+        if k != skip_fold:
+            XX += part["xtx"]
+            XY += part["xty"]
+            nobs += part["nobs"]
+            colsq += part["colsq"]
+    colsq = colsq / (float(nobs) - 1.0)
+    colsq = np.where(colsq == 0.0, 1.0, colsq)
+    colsq_inv = 1.0 / np.sqrt(colsq)
+    if standardize_:
+        if intercept:
+            XX[1:, 1:] = colsq_inv[:, None] * XX[1:, 1:] * colsq_inv[None, :]
+            XX[0, 1:] *= colsq_inv
+            XX[1:, 0] *= colsq_inv
+            XY[1:] *= colsq_inv
+        else:
+            XX = colsq_inv[:, None] * XX * colsq_inv[None, :]
+            XY *= colsq_inv
+    XX /= nobs
+    XY /= nobs
+    d = top_eig(XX) * 1.005
+    if not nobs > p:
+        raise ValueError("dimension of x larger than number of observations")
+    A = -XX
+    A[np.diag_indices(q)] += d
+    return A, XY, d, colsq_inv, nobs
+
+
+def oem_xval_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_,
+                   nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize_, intercept,
+                   nfolds, foldid, compute_loss, type_measure, opts):
+    """src/oem_xval_dense.cpp:31-477; unweighted branch, ncores=1 semantics."""
+    o = _as_opts(opts)
+    if family != "gaussian":
+        raise ValueError("binomial not available for oem_xval_dense, use oem_xval_logistic_dense")
+    if np.asarray(weights).size:
+        raise NotImplementedError("xval weights: out of scope (SURVEY.md 8a a9)")
+    X = np.asarray(x, dtype=np.float64)
+    Y = np.asarray(y, dtype=np.float64).ravel()
+    n, p = X.shape
+    foldid = np.asarray(foldid, dtype=np.int32).ravel()
+    q = p + int(intercept)
+    pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
+    if intercept:
+        pf = np.concatenate([[0.0], pf])
+    if not n > p:
+        raise ValueError("dimension of x larger than number of observations")
+    parts = fold_parts(X, Y, foldid, nfolds, intercept)
+    grp = _Groups(groups, unique_groups, group_weights, scan=q)
+    s = _Solver(q, pf, grp, o["maxit"], o["tol"])
+    out = dict(beta=[None] * len(penalty), lambda_=[None] * len(penalty), niter=[None] * len(penalty),
+               loss=[None] * len(penalty), cvm=[], cvsd=[], d=None)
+    beta_folds = [[None] * nfolds for _ in penalty]
+    lams = None
+    for ff in range(nfolds + 1):
+        A, XY, d, colsq_inv, nobs = assemble(parts, ff, p, standardize_, intercept)
+        if ff == 0:
+            out["d"] = d
+            lmax = float(np.abs(XY[1:] if intercept else XY).max())
+            lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha)
+        for pp, pen in enumerate(penalty):
+            lam = lams[pp]
+            L = 1 if pen == "ols" else lam.size
+            beta = np.zeros((p + 1, L), order="F")
+            niter = np.zeros(L, dtype=np.int32)
+            loss = np.full(L, 1e99)
+            s.init(pen, alpha, _gamma_for(gamma, pp), tau)
+            for i in range(L):
+                niter[i] = s.solve(A, XY, d, lam[i])
+                res = s.beta.copy()               # get_beta(): src/oem_xval_dense.h:1102-1120
+                if standardize_:
+                    if intercept:
+                        res[1:] *= colsq_inv
+                    else:
+                        res *= colsq_inv
+                if intercept:
+                    beta[:, i] = res
+                else:
+                    beta[1:, i] = res
+                if compute_loss and ff == 0:
+                    loss[i] = float(((Y - X @ beta[1:, i] - beta[0, i]) ** 2).sum())
+            if ff == 0:
+                out["beta"][pp], out["lambda_"][pp] = beta, lam
+                out["niter"][pp], out["loss"][pp] = niter, loss
+            else:
+                beta_folds[pp][ff - 1] = beta
+    # CV scoring: src/oem_xval_dense.cpp:345-464.  Welford over rows in original order gives the
+    # mean and M2 = sum (t - mean)^2; evaluated here per fold block with the same definitions.
+    for pp, pen in enumerate(penalty):
+        L = beta_folds[pp][0].shape[1]
+        T = np.empty((n, L))
+        for k in range(1, nfolds + 1):
+            idx = np.nonzero(foldid == k)[0]
+            B = beta_folds[pp][k - 1]
+            r = Y[idx, None] - (X[idx, :] @ B[1:, :] + B[0:1, :])
+            T[idx, :] = r ** 2 if type_measure == "mse" else np.abs(r)
+        m = T.mean(axis=0)
+        M2 = ((T - m[None, :]) ** 2).sum(axis=0)
+        out["cvm"].append(m)
+        out["cvsd"].append(np.sqrt(M2 / float(n - 1)) / np.sqrt(float(n)))
+    return out
+
+
+def welford_rows(T):
+    """Literal row-order Welford of src/oem_xval_dense.cpp:407-412 (small n only; used by tests
+    to pin the blocked evaluation above)."""
+    n, L = T.shape
+    m, ss = np.zeros(L), np.zeros(L)
+    for i in range(n):
+        delta = T[i] - m
+        m = m + delta / (i + 1)
+        ss = ss + delta * (T[i] - m)
+    return m, ss
+
+
+# ------------------------------------------------------------------------------------------
+# oem_fit_big
+# ------------------------------------------------------------------------------------------
+def oem_fit_big(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_,
+                nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize_, intercept,
+                compute_loss, opts, xtx_fn=None):
+    """src/oem_big.cpp:30-258, src/oem_big.h:469-566,731-842; unweighted."""
+    o = _as_opts(opts)
+    if family != "gaussian":
+        raise ValueError("binomial not available for oem_fit_dense, use oem_fit_logistic_dense")
+    if np.asarray(weights).size:
+        raise ValueError("weights not implemented yet.")   # R/big_oem.R:178
+    X = np.asarray(x, dtype=np.float64)
+    Y = np.asarray(y, dtype=np.float64).ravel()
+    n, p = X.shape
+    q = p + int(intercept)
+    pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
+    if intercept:
+        pf = np.concatenate([[0.0], pf])
+    colsq_inv = np.ones(p)
+    if standardize_:
+        colsq = (X ** 2).sum(axis=0) / (float(n) - 1.0)
+        colsq = np.where(colsq == 0.0, 1.0, colsq)
+        colsq_inv = 1.0 / np.sqrt(colsq)
+    XY = np.zeros(q)
+    XY[q - p:] = X.T @ Y
+    if intercept:
+        XY[0] = Y.sum()
+    if standardize_:
+        XY[q - p:] *= colsq_inv
+    XY /= n
+    G = xtx_fn(X) if xtx_fn else X.T @ X
+    if standardize_:
+        G = colsq_inv[:, None] * G * colsq_inv[None, :]
+    XX = np.zeros((q, q))
+    XX[q - p:, q - p:] = G
+    if intercept:
+        colsums = X.sum(axis=0)
+        if standardize_:
+            colsums = colsums * colsq_inv
+        XX[0, 1:] = colsums
+        XX[1:, 0] = colsums
+        XX[0, 0] = n
+    XX /= n
+    d = top_eig(XX) * 1.005
+    A = -XX
+    A[np.diag_indices(q)] += d
+    lmax = float(np.abs(XY).max())          # includes the intercept entry (src/oem_big.h:844-848)
+    lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha)
+    grp = _Groups(groups, unique_groups, group_weights, scan=p)   # v < nvars quirk (src/oem_big.h:445)
+    s = _Solver(q, pf, grp, o["maxit"], o["tol"])
+    out = dict(beta=[], lambda_=[], niter=[], loss=[], d=d)
+    for pp, pen in enumerate(penalty):
+        lam = lams[pp]
+        L = 1 if pen == "ols" else lam.size
+        beta = np.zeros((p + 1, L), order="F")
+        niter = np.zeros(L, dtype=np.int32)
+        s.init(pen, alpha, _gamma_for(gamma, pp), tau)
+        for i in range(L):
+            niter[i] = s.solve(A, XY, d, lam[i])
+            res = s.beta.copy()
+            res[q - p:] *= colsq_inv if standardize_ else 1.0
+            beta[1 - int(intercept):, i] = res
+        out["beta"].append(beta)
+        out["lambda_"].append(lam)
+        out["niter"].append(niter)
+        out["loss"].append(np.full(L, 1e99))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# oem_fit_logistic_dense
+# ------------------------------------------------------------------------------------------
+def oem_fit_logistic_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights,
+                           lambda_, nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor,
+                           standardize_, intercept, compute_loss, opts):
+    """src/oem_logistic_dense.cpp:29-313, src/oem_logistic_dense.h:721-1036,
+    n > p branch, unweighted, ncores=1, including the quirks of Appendix B item 5."""
+    o = _as_opts(opts)
+    if np.asarray(weights).size:
+        raise ValueError("weights not implemented yet.")
+    X = np.asarray(x, dtype=np.float64)
+    Y = np.asarray(y, dtype=np.float64).ravel()
+    n, p = X.shape
+    q = p + int(intercept)
+    if not n > q:
+        raise NotImplementedError("n <= p logistic branch is out of scope (SURVEY.md 8f row 4)")
+    pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
+    if intercept:
+        pf = np.concatenate([[0.0], pf])
+    colsq_inv = np.ones(p)
+    if standardize_:
+        colsq = (X ** 2).sum(axis=0) / (float(n) - 1.0)
+        colsq = np.where(colsq == 0.0, 1.0, colsq)
+        colsq_inv = 1.0 / np.sqrt(colsq)
+    XY = np.zeros(q)
+    XY[q - p:] = X.T @ Y
+    if intercept:
+        XY[0] = Y.sum()
+    if standardize_:
+        XY[q - p:] *= colsq_inv
+    XY /= n
+    lmax = float(np.abs(XY[q - p:]).max())
+    lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha,
+                         logistic_fudge=True, gamma=_gamma_for(gamma, 0))
+    grp = _Groups(groups, unique_groups, group_weights, scan=q, zero_weight_for_group0=True)
+    s = _Solver(q, pf, grp, o["maxit"], o["tol"])
+    full_hessian = o["hessian_type"] == "full"
+    XX, A, d = None, None, None
+    prob = np.zeros(n)
+    out = dict(beta=[], lambda_=[], niter=[], loss=[], d=None)
+    for pp, pen in enumerate(penalty):
+        lam = lams[pp]
+        L = 1 if pen == "ols" else lam.size
+        beta = np.zeros((p + 1, L), order="F")
+        niter = np.zeros(L, dtype=np.int32)
+        loss = np.full(L, 1e99)
+        s.init(pen, alpha, _gamma_for(gamma, pp), tau)
+        for i in range(L):
+            on_lam_1 = (i == 0)
+            it = 0
+            for it in range(o["irls_maxit"]):
+                beta_prev_irls = s.beta.copy()
+                if not (it == 0 and not on_lam_1):
+                    bx = s.beta[q - p:] * colsq_inv if standardize_ else s.beta[q - p:]
+                    eta = X @ bx + (s.beta[0] if intercept else 0.0)
+                    prob = 1.0 / (1.0 + np.exp(-eta))
+                    W = prob * (1.0 - prob)
+                    if W[it] < 1e-5:                    # sic: indexed by the IRLS counter
+                        W[it] = 1e-5
+                    if (it == 0 and on_lam_1) or full_hessian:
+                        XtWX = (X * W[:, None]).T @ X
+                        XX = np.zeros((q, q))
+                        if standardize_:
+                            XtWX = colsq_inv[:, None] * XtWX * colsq_inv[None, :]
+                        XX[q - p:, q - p:] = XtWX
+                        if intercept:
+                            cs = W @ X
+                            if standardize_:
+                                cs = cs * colsq_inv
+                            XX[0, 1:] = cs
+                            XX[1:, 0] = cs
+                            XX[0, 0] = W.sum()
+                        XX /= n
+                        d = top_eig(XX) * 1.0005
+                        A = -XX
+                        A[np.diag_indices(q)] += d
+                    presid = Y - prob
+                    grad = np.zeros(q)
+                    grad[q - p:] = (X.T @ presid) / float(n)
+                    if intercept:
+                        grad[0] = presid.sum() / float(n)
+                    if standardize_:
+                        grad[q - p:] *= colsq_inv
+                    XY = XX @ s.beta + grad
+                s.solve(A, XY, d, lam[i])
+                if stop_rule(s.beta, beta_prev_irls, o["irls_tol"]):
+                    break
+            else:
+                it = o["irls_maxit"]
+            niter[i] = it + 1
+            res = s.beta.copy()
+            if standardize_:
+                res[q - p:] *= colsq_inv
+            beta[1 - int(intercept):, i] = res
+            if compute_loss:        # get_loss(): src/oem_logistic_dense.h:1057-1088 (stale prob)
+                ok = np.where(Y == 1, prob > 1e-5, prob <= 1.0 - 1e-5)
+                pr = np.where(Y == 1, prob, 1.0 - prob)
+                loss[i] = float(np.where(ok, np.log(1.0 / np.where(ok, pr, 1.0)), np.log(1.0 / 1e-5)).sum())
+        out["beta"].append(beta)
+        out["lambda_"].append(lam)
+        out["niter"].append(niter)
+        out["loss"].append(loss)
+    out["d"] = d
+    return out
