@@ -1,0 +1,348 @@
+"""Host-side mirror of the reference's five C++ entry points, bound to liboem_b200.so through ctypes.
+
+Same names, argument order and return layout as the reference's .Call interface
+(R/oem.R:556-575, R/oem_xtx.R:389-420, R/oem_xval.R:525-548, R/big_oem.R:449-490, and the
+RcppExport functions src/oem_dense.cpp:30, oem_xtx.cpp:29, oem_xval_dense.cpp:31,
+oem_logistic_dense.cpp:29, oem_big.cpp:30):
+
+    oem_fit_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_,
+                  nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept,
+                  compute_loss, opts)  ->  dict(beta=[...], lambda_=[...], niter=[...], loss=[...], d=...)
+
+`x` / `y` may be numpy arrays (host; copied to the GPU inside the call) or torch CUDA tensors
+(device; used in place - x must be column-major, i.e. x.stride() == (1, ld)).  There is no CPU
+implementation behind these functions: without the CUDA library / a GPU they raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "liboem_b200.so")
+_lib = None
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p)
+
+
+class OemB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[oem_b200 error {code}] {msg}")
+        self.code = code
+
+
+class Opts(ctypes.Structure):
+    _fields_ = [("maxit", ctypes.c_int), ("tol", ctypes.c_double), ("irls_maxit", ctypes.c_int),
+                ("irls_tol", ctypes.c_double), ("ncores", ctypes.c_int), ("hessian_full", ctypes.c_int),
+                ("accelerate", ctypes.c_int), ("gigs", ctypes.c_double), ("device", ctypes.c_int),
+                ("stream", ctypes.c_void_p), ("allreduce", ALLREDUCE_FN), ("allreduce_ctx", ctypes.c_void_p),
+                ("rank", ctypes.c_int), ("world", ctypes.c_int)]
+
+
+class Spec(ctypes.Structure):
+    _fields_ = [("family", ctypes.c_char_p), ("n_penalty", ctypes.c_int),
+                ("penalty", ctypes.POINTER(ctypes.c_char_p)),
+                ("weights", ctypes.c_void_p), ("n_weights", ctypes.c_int64),
+                ("groups", ctypes.c_void_p), ("n_groups", ctypes.c_int),
+                ("unique_groups", ctypes.c_void_p), ("n_unique_groups", ctypes.c_int),
+                ("group_weights", ctypes.c_void_p), ("n_group_weights", ctypes.c_int),
+                ("lambda_", ctypes.POINTER(ctypes.c_void_p)), ("n_lambda", ctypes.c_void_p),
+                ("nlambda", ctypes.c_int), ("lambda_min_ratio", ctypes.c_double), ("alpha", ctypes.c_double),
+                ("gamma", ctypes.c_void_p), ("n_gamma", ctypes.c_int), ("tau", ctypes.c_double),
+                ("penalty_factor", ctypes.c_void_p), ("standardize", ctypes.c_int), ("intercept", ctypes.c_int),
+                ("compute_loss", ctypes.c_int)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_double) for k in
+                ("ms_h2d", "ms_colstats", "ms_gram", "ms_gram_reduce", "ms_allreduce", "ms_assemble", "ms_path",
+                 "ms_cvscore", "ms_irls_xb", "ms_irls_xtr", "ms_total", "gram_flops", "gemv_bytes")] + \
+               [(k, ctypes.c_int64) for k in
+                ("kernel_launches", "gram_launches", "xb_launches", "xtr_launches", "total_oem_iters",
+                 "lanczos_steps", "h2d_bytes", "d2h_bytes")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("beta", ctypes.c_void_p), ("lambda_", ctypes.c_void_p), ("niter", ctypes.c_void_p),
+                ("loss", ctypes.c_void_p), ("d", ctypes.c_void_p), ("cvm", ctypes.c_void_p),
+                ("cvsd", ctypes.c_void_p), ("nlam_out", ctypes.c_void_p), ("stats", ctypes.POINTER(Stats))]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load liboem_b200.so; fails loudly when the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise OemB200Error(-1, f"{_LIB_PATH} is missing: run `python -m oem_b200.build` "
+                               "(the CUDA extension is the only implementation; there is no CPU fallback)")
+    L = ctypes.CDLL(_LIB_PATH)
+    L.oemb200_last_error.restype = ctypes.c_char_p
+    L.oemb200_version.restype = ctypes.c_char_p
+    L.oemb200_device_count.restype = ctypes.c_int
+    L.oemb200_default_opts.argtypes = [ctypes.POINTER(Opts)]
+    L.oemb200_penalty_id.argtypes = [ctypes.c_char_p]
+    L.oemb200_nlambda_max.argtypes = [ctypes.POINTER(Spec)]
+    vp, i64, ci, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
+    sp, op, rp = ctypes.POINTER(Spec), ctypes.POINTER(Opts), ctypes.POINTER(Result)
+    L.oemb200_fit_dense.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
+    L.oemb200_fit_big.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
+    L.oemb200_fit_logistic_dense.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
+    L.oemb200_xtx.argtypes = [vp, vp, ci, sp, vp, ci, op, rp]
+    L.oemb200_xval_dense.argtypes = [vp, i64, ci, i64, vp, sp, ci, vp, ctypes.c_char_p, op, rp]
+    L.oemb200_gram.argtypes = [vp, i64, ci, i64, vp, vp, vp, vp, ctypes.POINTER(dbl)]
+    L.oemb200_colstats.argtypes = [vp, i64, ci, i64, vp, vp, vp, vp, ctypes.POINTER(dbl)]
+    L.oemb200_xb_logistic.argtypes = [vp, i64, ci, i64, vp, dbl, vp, vp, vp, vp, vp, ctypes.POINTER(dbl)]
+    L.oemb200_top_eig.argtypes = [vp, ci, ctypes.POINTER(dbl), ctypes.POINTER(ci), vp]
+    _lib = L
+    return L
+
+
+EXPORTS = ["oemb200_last_error", "oemb200_version", "oemb200_device_count", "oemb200_default_opts",
+           "oemb200_penalty_id", "oemb200_nlambda_max", "oemb200_fit_dense", "oemb200_xtx", "oemb200_xval_dense",
+           "oemb200_fit_logistic_dense", "oemb200_fit_big", "oemb200_gram", "oemb200_colstats",
+           "oemb200_xb_logistic", "oemb200_top_eig"]
+
+
+def _check(rc):
+    if rc != 0:
+        raise OemB200Error(rc, load().oemb200_last_error().decode())
+
+
+def _is_torch_cuda(a):
+    return type(a).__module__.startswith("torch") and getattr(a, "is_cuda", False)
+
+
+class _Keep:
+    """Keeps the numpy temporaries backing raw pointers alive for the duration of a call."""
+
+    def __init__(self):
+        self.refs = []
+
+    def arr(self, a, dtype):
+        a = np.ascontiguousarray(np.asarray(a, dtype=dtype).ravel())
+        self.refs.append(a)
+        return a
+
+    def ptr(self, a, dtype):
+        a = self.arr(a, dtype)
+        return a.ctypes.data if a.size else None, a.size
+
+
+def _matrix_arg(x, keep):
+    """-> (pointer, n, p, ld) for a column-major matrix on host (numpy) or device (torch)."""
+    if _is_torch_cuda(x):
+        import torch
+        if x.dtype != torch.float64 or x.dim() != 2:
+            raise ValueError("device x must be a 2-D float64 tensor")
+        n, p = x.shape
+        if x.stride(0) != 1 and n > 1:
+            raise ValueError("device x must be column-major (stride (1, ld)); e.g. torch.empty(p, n).t()")
+        ld = x.stride(1) if p > 1 else n
+        keep.refs.append(x)
+        return x.data_ptr(), n, p, max(ld, n)
+    a = np.asfortranarray(np.asarray(x, dtype=np.float64))
+    if a.ndim != 2:
+        raise ValueError("x must be 2-D")
+    keep.refs.append(a)
+    return a.ctypes.data, a.shape[0], a.shape[1], a.shape[0]
+
+
+def _vector_arg(y, keep):
+    if _is_torch_cuda(y):
+        import torch
+        if y.dtype != torch.float64:
+            raise ValueError("device y must be float64")
+        y = y.contiguous().view(-1)
+        keep.refs.append(y)
+        return y.data_ptr(), y.numel()
+    a = keep.arr(y, np.float64)
+    return a.ctypes.data, a.size
+
+
+def make_opts(opts=None, comm=None):
+    """Reference `options` list (R/oem.R:438-444) -> Opts.  Keys use '_' or '.'; extra runtime
+    keys: device, stream.  `comm` is a oem_b200.dist.Comm (row-sharded multi-process runs)."""
+    o = Opts()
+    load().oemb200_default_opts(ctypes.byref(o))
+    for k, v in (opts or {}).items():
+        k = k.replace(".", "_")
+        if k == "hessian_type":
+            o.hessian_full = 1 if v == "full" else 0
+        elif k in ("maxit", "irls_maxit", "ncores", "device"):
+            setattr(o, k, int(v))
+        elif k in ("tol", "irls_tol", "gigs"):
+            setattr(o, k, float(v))
+        elif k == "accelerate":
+            o.accelerate = int(bool(v))
+        elif k == "stream":
+            o.stream = int(v)
+        else:
+            raise ValueError(f"unknown option {k}")
+    if comm is not None and comm.world > 1:
+        o.allreduce = comm.callback
+        o.rank, o.world = comm.rank, comm.world
+    return o
+
+
+def _make_spec(keep, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+               lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss):
+    s = Spec()
+    s.family = family.encode()
+    pens = [p.encode() for p in penalty]
+    arr = (ctypes.c_char_p * len(pens))(*pens)
+    keep.refs.append(arr)
+    s.n_penalty = len(pens)
+    s.penalty = arr
+    s.weights, s.n_weights = keep.ptr(weights if weights is not None else [], np.float64)
+    s.groups, s.n_groups = keep.ptr(groups if groups is not None else [], np.int32)
+    s.unique_groups, s.n_unique_groups = keep.ptr(unique_groups if unique_groups is not None else [], np.int32)
+    s.group_weights, s.n_group_weights = keep.ptr(group_weights if group_weights is not None else [], np.float64)
+    lam_list = list(lambda_) if lambda_ is not None else []
+    given = len(lam_list) > 0 and np.asarray(lam_list[0]).size >= 1
+    if given:
+        if len(lam_list) != len(pens):
+            raise ValueError("lambda must be a list with one vector per penalty")
+        ptrs = (ctypes.c_void_p * len(pens))()
+        lens = np.zeros(len(pens), dtype=np.int32)
+        for i, lv in enumerate(lam_list):
+            a = keep.arr(lv, np.float64)
+            ptrs[i] = a.ctypes.data
+            lens[i] = a.size
+        keep.refs += [ptrs, lens]
+        s.lambda_ = ptrs
+        s.n_lambda = lens.ctypes.data
+    s.nlambda = int(nlambda)
+    s.lambda_min_ratio = float(lmin_ratio)
+    s.alpha = float(alpha)
+    s.gamma, s.n_gamma = keep.ptr(np.atleast_1d(gamma), np.float64)
+    s.tau = float(tau)
+    s.penalty_factor, _ = keep.ptr(penalty_factor, np.float64)
+    s.standardize = int(bool(standardize))
+    s.intercept = int(bool(intercept))
+    s.compute_loss = int(bool(compute_loss))
+    return s
+
+
+class _Out:
+    def __init__(self, P, L, rows, xval=False):
+        self.P, self.L, self.rows = P, L, rows
+        self.beta = np.zeros((P, L, rows))
+        self.lam = np.zeros((P, L))
+        self.niter = np.zeros((P, L), dtype=np.int32)
+        self.loss = np.zeros((P, L))
+        self.d = np.zeros(1)
+        self.cvm = np.zeros((P, L)) if xval else None
+        self.cvsd = np.zeros((P, L)) if xval else None
+        self.nlam = np.zeros(P, dtype=np.int32)
+        self.stats = Stats()
+        r = Result()
+        r.beta, r.lambda_, r.niter = self.beta.ctypes.data, self.lam.ctypes.data, self.niter.ctypes.data
+        r.loss, r.d, r.nlam_out = self.loss.ctypes.data, self.d.ctypes.data, self.nlam.ctypes.data
+        if xval:
+            r.cvm, r.cvsd = self.cvm.ctypes.data, self.cvsd.ctypes.data
+        r.stats = ctypes.pointer(self.stats)
+        self.res = r
+
+    def as_dict(self):
+        out = dict(beta=[], lambda_=[], niter=[], loss=[], d=float(self.d[0]), stats=self.stats.as_dict())
+        for pp in range(self.P):
+            k = int(self.nlam[pp])
+            out["beta"].append(np.asfortranarray(self.beta[pp, :k, :].T))      # rows x k, column-major
+            out["lambda_"].append(self.lam[pp].copy())
+            out["niter"].append(self.niter[pp, :k].copy())
+            out["loss"].append(self.loss[pp, :k].copy())
+        if self.cvm is not None:
+            out["cvm"] = [self.cvm[pp, :int(self.nlam[pp])].copy() for pp in range(self.P)]
+            out["cvsd"] = [self.cvsd[pp, :int(self.nlam[pp])].copy() for pp in range(self.P)]
+        return out
+
+
+def _run_xy(fn_name, x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+            lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss, opts, comm,
+            extra=None):
+    L = load()
+    keep = _Keep()
+    xp, n, p, ld = _matrix_arg(x, keep)
+    yp, ny = _vector_arg(y, keep)
+    if ny != n:
+        raise ValueError("length of y must equal nrow(x)")
+    spec = _make_spec(keep, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+                      lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss)
+    o = opts if isinstance(opts, Opts) else make_opts(opts, comm)
+    Lmax = L.oemb200_nlambda_max(ctypes.byref(spec))
+    out = _Out(len(penalty), Lmax, p + 1, xval=(fn_name == "oemb200_xval_dense"))
+    fn = getattr(L, fn_name)
+    if extra is None:
+        rc = fn(xp, n, p, ld, yp, ctypes.byref(spec), ctypes.byref(o), ctypes.byref(out.res))
+    else:
+        rc = fn(xp, n, p, ld, yp, ctypes.byref(spec), *extra(keep), ctypes.byref(o), ctypes.byref(out.res))
+    _check(rc)
+    return out.as_dict()
+
+
+def oem_fit_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+                  lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss, opts,
+                  comm=None):
+    """src/oem_dense.cpp:30-309."""
+    return _run_xy("oemb200_fit_dense", x, y, family, penalty, weights, groups, unique_groups, group_weights,
+                   lambda_, nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept,
+                   compute_loss, opts, comm)
+
+
+def oem_fit_big(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+                lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss, opts,
+                comm=None):
+    """src/oem_big.cpp:30-258 (x = the big.matrix payload: n x p column-major doubles)."""
+    return _run_xy("oemb200_fit_big", x, y, family, penalty, weights, groups, unique_groups, group_weights,
+                   lambda_, nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept,
+                   compute_loss, opts, comm)
+
+
+def oem_fit_logistic_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_,
+                           nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept,
+                           compute_loss, opts, comm=None):
+    """src/oem_logistic_dense.cpp:29-313."""
+    return _run_xy("oemb200_fit_logistic_dense", x, y, family, penalty, weights, groups, unique_groups,
+                   group_weights, lambda_, nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize,
+                   intercept, compute_loss, opts, comm)
+
+
+def oem_xval_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+                   lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, nfolds, foldid,
+                   compute_loss, type_measure, opts, comm=None):
+    """src/oem_xval_dense.cpp:31-477."""
+    def extra(keep):
+        f = keep.arr(foldid, np.int32)
+        return [int(nfolds), f.ctypes.data, type_measure.encode()]
+    return _run_xy("oemb200_xval_dense", x, y, family, penalty, weights, groups, unique_groups, group_weights,
+                   lambda_, nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept,
+                   compute_loss, opts, comm, extra=extra)
+
+
+def oem_xtx(xtx, xty, family, penalty, groups, unique_groups, group_weights, lambda_, nlambda, lmin_ratio,
+            alpha, gamma, tau, scale_factor, penalty_factor, opts):
+    """src/oem_xtx.cpp:29-219.  beta is p x nlambda (no intercept row)."""
+    L = load()
+    keep = _Keep()
+    xp, p, p2, ld = _matrix_arg(xtx, keep)
+    if p != p2 or ld != p:
+        raise ValueError("xtx must be a dense square matrix")
+    yp, ny = _vector_arg(xty, keep)
+    if ny != p:
+        raise ValueError("xty must have length ncol(xtx)")
+    spec = _make_spec(keep, family, penalty, [], groups, unique_groups, group_weights, lambda_, nlambda,
+                      lmin_ratio, alpha, gamma, tau, penalty_factor, False, False, False)
+    o = opts if isinstance(opts, Opts) else make_opts(opts)
+    Lmax = L.oemb200_nlambda_max(ctypes.byref(spec))
+    out = _Out(len(penalty), Lmax, p)
+    sfp, nsf = keep.ptr(scale_factor if scale_factor is not None else [], np.float64)
+    _check(L.oemb200_xtx(xp, yp, p, ctypes.byref(spec), sfp, nsf, ctypes.byref(o), ctypes.byref(out.res)))
+    return out.as_dict()

@@ -1,0 +1,539 @@
+// entries.cu -- host drivers of the reference's entry points on top of the sm_100a kernels, and
+// the extern "C" layer of include/oem_b200.h.
+//
+//   oemb200_fit_dense   <- oem_fit_dense   src/oem_dense.cpp:30-309  (+ DataStd.h, oem_dense.h)
+//   oemb200_xtx         <- oem_xtx         src/oem_xtx.cpp:29-219    (+ oem_xtx.h)
+//   oemb200_fit_big     <- oem_fit_big     src/oem_big.cpp:30-258    (+ oem_big.h)
+// (logistic: entry_logistic.cu, xval: entry_xval.cu)
+//
+// Each driver owns only bookkeeping: which sums to take over X, the lambda grid (host libm, so it
+// is bit-identical to a CPU implementation), the penalty x lambda layout of the result.  All
+// arithmetic on X, on the Gram and on beta runs in the CUDA kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "host_common.h"
+
+namespace oemb200 {
+
+thread_local std::string g_last_error;
+
+void check_common(const oemb200_spec *s, const oemb200_opts *o, const oemb200_result *r, const char *want_family) {
+    if (!s || !o || !r) fail(OEMB200_EINVAL, "spec / opts / result must not be NULL");
+    if (!s->family || strcmp(s->family, want_family) != 0) {
+        if (strcmp(want_family, "gaussian") == 0)
+            fail(OEMB200_EINVAL, "binomial not available for oem_fit_dense, use oem_fit_logistic_dense");
+        fail(OEMB200_EINVAL, "family must be \"%s\"", want_family);
+    }
+    if (s->n_weights > 0) fail(OEMB200_EUNSUPPORTED, "weights not implemented yet.");   // R/oem.R:244
+    if (!r->beta || !r->lambda || !r->niter || !r->d) fail(OEMB200_EINVAL, "result buffers beta/lambda/niter/d are required");
+    if (o->maxit < 1) fail(OEMB200_EINVAL, "maxit must be >= 1");
+}
+
+// Bring an n x p column-major matrix to the device (even leading dimension so that the TMA and
+// 128-bit paths apply).  Device inputs are used in place.
+void to_device_matrix(Ctx &cx, const double *x, int64_t n, int p, int64_t ldx, DevMatrix &m) {
+    if (is_device_ptr(x)) { m.p = x; m.ld = ldx; return; }
+    size_t free_b = 0, total_b = 0;
+    OEM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    m.ld = n + (n & 1);
+    const size_t need = (size_t)m.ld * p * 8;
+    if (need + (2ull << 30) > free_b)
+        fail(OEMB200_EUNSUPPORTED, "x (%.1f GB) does not fit next to the workspace on the device (%.1f GB free); "
+             "use oem_fit_big (streams row chunks) or shard the rows over more GPUs", need / 1e9, free_b / 1e9);
+    m.own.alloc((size_t)m.ld * p);
+    if (m.ld != n) m.own.zero(cx.stream);
+    OEM_CUDA(cudaMemcpy2DAsync(m.own.p, (size_t)m.ld * 8, x, (size_t)ldx * 8, (size_t)n * 8, p, cudaMemcpyHostToDevice,
+                               cx.stream));
+    cx.st.h2d_bytes += (int64_t)n * p * 8;
+    m.p = m.own.p;
+}
+void to_device_vector(Ctx &cx, const double *v, int64_t n, DevVector &d) {
+    if (is_device_ptr(v)) { d.p = v; return; }
+    d.own.alloc(n + (n & 1));
+    d.own.zero(cx.stream);
+    d.own.upload(v, n, cx.stream);
+    cx.st.h2d_bytes += n * 8;
+    d.p = d.own.p;
+}
+
+void fill_common_outputs(const Setup &su, oemb200_result *res) {
+    const int L = su.Lmax;
+    for (int pp = 0; pp < su.P; ++pp) {
+        for (int i = 0; i < L; ++i) {
+            res->lambda[(size_t)pp * L + i] = i < (int)su.lam[pp].size() ? su.lam[pp][i] : 0.0;
+            if (res->loss) res->loss[(size_t)pp * L + i] = 1e99;
+        }
+        if (res->nlam_out) res->nlam_out[pp] = su.nlam_run[pp];
+    }
+}
+
+void finish_stats(Ctx &cx, PhaseTimers &tm, size_t total_id, oemb200_result *res) {
+    tm.stop(total_id);
+    cx.sync();
+    tm.collect();
+    if (res->stats) *res->stats = cx.st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// oem_fit_big: one raw pass over X (row chunks, streamed from the host when X lives there)
+// ------------------------------------------------------------------------------------------------
+static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s,
+                    const oemb200_opts *o, oemb200_result *res) {
+    check_common(s, o, res, "gaussian");
+    if (n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
+    const int icpt = s->intercept ? 1 : 0, q = p + icpt;
+    Ctx cx(o);
+    PhaseTimers tm(cx.stream);
+    const size_t t_total = tm.start(&cx.st.ms_total);
+    Setup su;
+    su.parse(s, q, /*scan=*/p, /*zero_w0=*/false);      // v < nvars quirk: src/oem_big.h:445
+
+    // bundle = [G p*p | stats 3p | sum y, sum y^2 | n]  -> one all-reduce
+    const size_t nb = (size_t)p * p + 3 * (size_t)p + 3;
+    DBuf<double> bundle(nb);
+    bundle.zero(cx.stream);
+    double *G = bundle.p, *stats = G + (size_t)p * p, *ysum = stats + 3 * (size_t)p, *nobs = ysum + 2;
+
+    DevVector yv;
+    to_device_vector(cx, y, n, yv);
+    const size_t t_y = tm.start(&cx.st.ms_colstats);
+    vecsum_launch(cx, yv.p, n, 0.0, ysum, false);
+    tm.stop(t_y);
+
+    if (is_device_ptr(x)) {
+        const size_t t1 = tm.start(&cx.st.ms_colstats);
+        colstats_launch(cx, x, n, p, ldx, nullptr, yv.p, nullptr, stats, false);
+        tm.stop(t1);
+        const size_t t2 = tm.start(&cx.st.ms_gram);
+        gram_launch(cx, x, n, p, ldx, {RowSegment{0, n, 0}}, 1, nullptr, nullptr, G, false);
+        tm.stop(t2);
+    } else {
+        // host X: double-buffered row chunks; H2D of chunk c+1 overlaps the kernels of chunk c
+        const double gigs = o->gigs > 0 ? o->gigs : 1.0;
+        int64_t rows = (int64_t)(gigs * 1e9 / (8.0 * p));
+        const int64_t align = 2 * gram_kt();
+        rows = std::max<int64_t>(align, rows / align * align);
+        rows = std::min<int64_t>(rows, (n + align - 1) / align * align);
+        DBuf<double> stage[2];
+        stage[0].alloc((size_t)rows * p);
+        stage[1].alloc((size_t)rows * p);
+        cudaStream_t cs;
+        OEM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaEvent_t ready[2], freed[2];
+        for (int b = 0; b < 2; ++b) {
+            OEM_CUDA(cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
+            OEM_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
+        }
+        const int64_t nchunks = (n + rows - 1) / rows;
+        auto issue_copy = [&](int64_t c) {
+            const int b = (int)(c & 1);
+            const int64_t r0 = c * rows, nr = std::min(rows, n - r0);
+            if (c >= 2) OEM_CUDA(cudaStreamWaitEvent(cs, freed[b], 0));
+            OEM_CUDA(cudaMemcpy2DAsync(stage[b].p, (size_t)rows * 8, x + r0, (size_t)ldx * 8, (size_t)nr * 8, p,
+                                       cudaMemcpyHostToDevice, cs));
+            OEM_CUDA(cudaEventRecord(ready[b], cs));
+            cx.st.h2d_bytes += nr * (int64_t)p * 8;
+        };
+        const size_t t_h = tm.start(&cx.st.ms_h2d);   // whole streamed pass (copies overlap the kernels)
+        issue_copy(0);
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int b = (int)(c & 1);
+            const int64_t r0 = c * rows, nr = std::min(rows, n - r0);
+            if (c + 1 < nchunks) issue_copy(c + 1);
+            OEM_CUDA(cudaStreamWaitEvent(cx.stream, ready[b], 0));
+            colstats_launch(cx, stage[b].p, nr, p, rows, nullptr, yv.p + r0, nullptr, stats, c > 0);
+            gram_launch(cx, stage[b].p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, nullptr, G, c > 0);
+            OEM_CUDA(cudaEventRecord(freed[b], cx.stream));
+        }
+        tm.stop(t_h);
+        cx.sync();
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ready[b]); cudaEventDestroy(freed[b]); }
+        cudaStreamDestroy(cs);
+    }
+    const double nd = (double)n;
+    OEM_CUDA(cudaMemcpyAsync(nobs, &nd, 8, cudaMemcpyHostToDevice, cx.stream));
+    const size_t t_ar = tm.start(&cx.st.ms_allreduce);
+    cx.all_reduce(bundle.p, (int64_t)nb);
+    tm.stop(t_ar);
+
+    double n_tot = 0.0;
+    OEM_CUDA(cudaMemcpyAsync(&n_tot, nobs, 8, cudaMemcpyDeviceToHost, cx.stream));
+    cx.sync();
+    if (!(n_tot > q)) fail(OEMB200_EUNSUPPORTED, "n <= p branch (XX' form, src/oem_big.h:363-366) is outside the hot path");
+
+    const size_t t_as = tm.start(&cx.st.ms_assemble);
+    DBuf<double> XX((size_t)q * q), XY(q), cinv(p);
+    // corner = n (XX(0,0) = nobs, src/oem_big.h:527), divisor = n
+    assemble_aug_launch(cx, p, icpt, s->standardize ? 1 : 0, 1, 1, G, stats, ysum, nobs, nobs, XX.p, XY.p, cinv.p, nullptr);
+    std::vector<double> hXY(q), hcinv(p);
+    XY.download(hXY.data(), q, cx.stream);
+    cinv.download(hcinv.data(), p, cx.stream);
+    tm.stop(t_as);
+    cx.sync();
+
+    double lmax = 0.0;   // includes the intercept entry: src/oem_big.h:844-848
+    for (int j = 0; j < q; ++j) lmax = std::max(lmax, std::fabs(hXY[j]));
+    su.build_lambdas(s, lmax, false);
+
+    std::vector<double> pf(q, 0.0);
+    for (int j = 0; j < p; ++j) pf[icpt + j] = s->penalty_factor[j];
+    PathBuffers pb;
+    const size_t t_p = tm.start(&cx.st.ms_path);
+    run_paths(cx, su, o, q, 1, XX.p, XY.p, pf, 1.0, 1.005, false, nullptr, pb);
+    tm.stop(t_p);
+
+    const int L = su.Lmax;
+    fill_common_outputs(su, res);
+    memset(res->beta, 0, sizeof(double) * (size_t)su.P * (p + 1) * L);
+    for (int pp = 0; pp < su.P; ++pp)
+        for (int i = 0; i < su.nlam_run[pp]; ++i) {
+            const double *raw = &pb.h_beta[((size_t)pp * L + i) * q];
+            double *out = res->beta + ((size_t)pp * L + i) * (p + 1);
+            if (icpt) out[0] = raw[0];
+            for (int j = 0; j < p; ++j) out[1 + j] = s->standardize ? raw[icpt + j] * hcinv[j] : raw[icpt + j];
+            res->niter[(size_t)pp * L + i] = pb.h_niter[(size_t)pp * L + i];
+        }
+    *res->d = pb.h_d[0];
+    finish_stats(cx, tm, t_total, res);
+}
+
+// ------------------------------------------------------------------------------------------------
+// oem_fit_dense
+// ------------------------------------------------------------------------------------------------
+static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s,
+                      const oemb200_opts *o, oemb200_result *res) {
+    check_common(s, o, res, "gaussian");
+    if (n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
+    const int flag = (s->standardize ? 1 : 0) + 2 * (s->intercept ? 1 : 0);
+    Ctx cx(o);
+    PhaseTimers tm(cx.stream);
+    const size_t t_total = tm.start(&cx.st.ms_total);
+    Setup su;
+    su.parse(s, p, p, false);
+
+    const size_t t_h = tm.start(&cx.st.ms_h2d);
+    DevMatrix X;
+    to_device_matrix(cx, x, n, p, ldx, X);
+    DevVector yv;
+    to_device_vector(cx, y, n, yv);
+    tm.stop(t_h);
+
+    // ---- pass 1: column sums, sum y, n ----
+    const size_t nb1 = 3 * (size_t)p + 3;
+    DBuf<double> b1(nb1);
+    double *stats1 = b1.p, *ysum = stats1 + 3 * (size_t)p, *nobs = ysum + 2;
+    const size_t t_c1 = tm.start(&cx.st.ms_colstats);
+    if (flag != 0) colstats_launch(cx, X.p, n, p, X.ld, nullptr, nullptr, nullptr, stats1, false);
+    else b1.zero(cx.stream);
+    vecsum_launch(cx, yv.p, n, 0.0, ysum, false);
+    const double nd = (double)n;
+    OEM_CUDA(cudaMemcpyAsync(nobs, &nd, 8, cudaMemcpyHostToDevice, cx.stream));
+    tm.stop(t_c1);
+    cx.all_reduce(b1.p, (int64_t)nb1);
+    std::vector<double> h1(nb1);
+    b1.download(h1.data(), nb1, cx.stream);
+    cx.sync();
+    const double n_tot = h1[nb1 - 1];
+    if (!(n_tot > p)) fail(OEMB200_EUNSUPPORTED, "n <= p branch (XX' form, src/oem_dense.h:363-366) is outside the hot path");
+
+    std::vector<double> meanX(p, 0.0), scaleX(p, 1.0);
+    double meanY = 0.0, scaleY = 1.0;
+    const bool center_x = (flag == 2 || flag == 3);
+    if (flag != 0) for (int j = 0; j < p; ++j) meanX[j] = h1[j] / n_tot;
+    DBuf<double> d_mean(p);
+    d_mean.upload(meanX.data(), p, cx.stream);
+
+    // ---- y standardisation (DataStd.h:102-138; flag 2 falls through into flag 3) ----
+    DBuf<double> ys;
+    const double *yuse = yv.p;
+    if (flag != 0) {
+        const double ybar = h1[3 * (size_t)p] / n_tot;
+        DBuf<double> yss(2);
+        vecsum_launch(cx, yv.p, n, ybar, yss.p, false);
+        cx.all_reduce(yss.p, 2);
+        double h[2];
+        yss.download(h, 2, cx.stream);
+        cx.sync();
+        const double n_invsqrt = 1.0 / std::sqrt(n_tot);
+        if (flag == 1) scaleY = std::sqrt(h[1]) / std::sqrt(n_tot);        // sd_n(Y)
+        else { meanY = ybar; scaleY = std::sqrt(h[1]) * n_invsqrt; }       // Y.norm() * n_invsqrt after centring
+        ys.alloc(n + (n & 1));
+        ys.zero(cx.stream);
+        affine_launch(cx, yv.p, n, flag == 1 ? 0.0 : meanY, scaleY, ys.p);
+        yuse = ys.p;
+    }
+
+    // ---- pass 2: X' ys (centred like X), centred sums of squares; pass 3: the Gram ----
+    const size_t nb2 = (size_t)p * p + 2 * (size_t)p;
+    DBuf<double> b2(nb2), stats2(3 * (size_t)p);
+    double *G = b2.p, *xy = G + (size_t)p * p, *css = xy + p;
+    const size_t t_c2 = tm.start(&cx.st.ms_colstats);
+    colstats_launch(cx, X.p, n, p, X.ld, yuse, nullptr, center_x ? d_mean.p : nullptr, stats2.p, false);
+    OEM_CUDA(cudaMemcpyAsync(xy, stats2.p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
+    if (flag == 1) {   // sd about the mean although X itself is not centred
+        DBuf<double> stats3(3 * (size_t)p);
+        colstats_launch(cx, X.p, n, p, X.ld, nullptr, nullptr, d_mean.p, stats3.p, false);
+        OEM_CUDA(cudaMemcpyAsync(css, stats3.p + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
+        cx.sync();
+    } else {
+        OEM_CUDA(cudaMemcpyAsync(css, stats2.p + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
+    }
+    tm.stop(t_c2);
+    const size_t t_g = tm.start(&cx.st.ms_gram);
+    gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, center_x ? d_mean.p : nullptr, nullptr, G, false);
+    tm.stop(t_g);
+    const size_t t_ar = tm.start(&cx.st.ms_allreduce);
+    cx.all_reduce(b2.p, (int64_t)nb2);
+    tm.stop(t_ar);
+
+    const size_t t_as = tm.start(&cx.st.ms_assemble);
+    DBuf<double> XX((size_t)p * p), XY(p), d_scalex(p);
+    assemble_dense_launch(cx, p, flag, n_tot, G, xy, css, XX.p, XY.p, d_scalex.p);
+    std::vector<double> hXY(p);
+    XY.download(hXY.data(), p, cx.stream);
+    d_scalex.download(scaleX.data(), p, cx.stream);
+    tm.stop(t_as);
+    cx.sync();
+
+    double lmax = 0.0;
+    for (int j = 0; j < p; ++j) lmax = std::max(lmax, std::fabs(hXY[j]));
+    lmax *= scaleY;                                   // src/oem_dense.cpp:176
+    su.build_lambdas(s, lmax, false);
+    std::vector<double> pf(s->penalty_factor, s->penalty_factor + p);
+    PathBuffers pb;
+    const size_t t_p = tm.start(&cx.st.ms_path);
+    run_paths(cx, su, o, p, 1, XX.p, XY.p, pf, scaleY, 1.005, o->accelerate != 0, nullptr, pb);
+    tm.stop(t_p);
+
+    // ---- recover (DataStd.h:269-293) ----
+    const int L = su.Lmax;
+    fill_common_outputs(su, res);
+    memset(res->beta, 0, sizeof(double) * (size_t)su.P * (p + 1) * L);
+    DBuf<double> d_b, d_eta, d_l2;
+    for (int pp = 0; pp < su.P; ++pp)
+        for (int i = 0; i < su.nlam_run[pp]; ++i) {
+            const double *raw = &pb.h_beta[((size_t)pp * L + i) * p];
+            double *out = res->beta + ((size_t)pp * L + i) * (p + 1);
+            double b0 = 0.0;
+            for (int j = 0; j < p; ++j) {
+                double c = raw[j];
+                if (flag == 1 || flag == 3) c /= scaleX[j];
+                if (flag != 0) c *= scaleY;
+                out[1 + j] = c;
+            }
+            if (flag == 2 || flag == 3) {
+                double acc = 0.0;
+                for (int j = 0; j < p; ++j) acc += out[1 + j] * meanX[j];
+                b0 = meanY - acc;
+            }
+            out[0] = b0;
+            res->niter[(size_t)pp * L + i] = pb.h_niter[(size_t)pp * L + i];
+            if (s->compute_loss && res->loss) {
+                // get_loss(): ||Y_std - X_std beta_std||^2 (src/oem_dense.h:759-770) as one more X b pass:
+                // X_std b = X (b / s) - sum_j m_j b_j / s_j
+                std::vector<double> bs(p);
+                double off = 0.0;
+                for (int j = 0; j < p; ++j) {
+                    bs[j] = (flag == 1 || flag == 3) ? raw[j] / scaleX[j] : raw[j];
+                    if (center_x) off -= bs[j] * meanX[j];
+                }
+                if (!d_b.p) { d_b.alloc(p); d_eta.alloc(n + (n & 1)); d_l2.alloc(2); }
+                d_b.upload(bs.data(), p, cx.stream);
+                // eta = ys - X_std b  is formed as  -(X bs + off) + ys  via the resid output of the xb epilogue
+                xb_launch(cx, X.p, n, p, X.ld, d_b.p, off, nullptr, d_eta.p, nullptr, nullptr, nullptr, false);
+                affine_launch(cx, d_eta.p, n, 0.0, -1.0, d_eta.p);
+                axpy_launch(cx, n, 1.0, yuse, d_eta.p);
+                vecsum_launch(cx, d_eta.p, n, 0.0, d_l2.p, false);
+                cx.all_reduce(d_l2.p, 2);
+                double h[2];
+                d_l2.download(h, 2, cx.stream);
+                cx.sync();
+                res->loss[(size_t)pp * L + i] = h[1];
+            }
+        }
+    *res->d = pb.h_d[0];
+    finish_stats(cx, tm, t_total, res);
+}
+
+// ------------------------------------------------------------------------------------------------
+// oem_xtx
+// ------------------------------------------------------------------------------------------------
+static void fit_xtx(const double *xtx, const double *xty, int p, const oemb200_spec *s, const double *scale_factor,
+                    int n_sf, const oemb200_opts *o, oemb200_result *res) {
+    check_common(s, o, res, "gaussian");
+    if (p < 1 || !xtx || !xty) fail(OEMB200_EINVAL, "xtx / xty missing");
+    if (n_sf != 0 && n_sf != p) fail(OEMB200_EINVAL, "scale_factor must have length p");
+    Ctx cx(o);
+    PhaseTimers tm(cx.stream);
+    const size_t t_total = tm.start(&cx.st.ms_total);
+    Setup su;
+    su.parse(s, p, p, false);
+    DBuf<double> XXin, XYin, XX((size_t)p * p), XY(p), sinv;
+    const double *pxx = xtx, *pxy = xty;
+    if (!is_device_ptr(xtx)) { XXin.alloc((size_t)p * p); XXin.upload(xtx, (size_t)p * p, cx.stream); pxx = XXin.p; cx.st.h2d_bytes += (int64_t)p * p * 8; }
+    if (!is_device_ptr(xty)) { XYin.alloc(p); XYin.upload(xty, p, cx.stream); pxy = XYin.p; cx.st.h2d_bytes += p * 8; }
+    std::vector<double> hs;
+    if (n_sf) {
+        hs.resize(p);
+        for (int j = 0; j < p; ++j) hs[j] = 1.0 / scale_factor[j];
+        sinv.alloc(p);
+        sinv.upload(hs.data(), p, cx.stream);
+    }
+    const size_t t_as = tm.start(&cx.st.ms_assemble);
+    scale_sym_launch(cx, p, n_sf ? sinv.p : nullptr, pxx, pxy, XX.p, XY.p);
+    std::vector<double> hXY(p);
+    XY.download(hXY.data(), p, cx.stream);
+    tm.stop(t_as);
+    cx.sync();
+    double lmax = 0.0;
+    for (int j = 0; j < p; ++j) lmax = std::max(lmax, std::fabs(hXY[j]));
+    su.build_lambdas(s, lmax, false);
+    std::vector<double> pf(s->penalty_factor, s->penalty_factor + p);
+    PathBuffers pb;
+    const size_t t_p = tm.start(&cx.st.ms_path);
+    run_paths(cx, su, o, p, 1, XX.p, XY.p, pf, 1.0, 1.005, false, n_sf ? sinv.p : nullptr, pb);
+    tm.stop(t_p);
+    const int L = su.Lmax;
+    fill_common_outputs(su, res);
+    memset(res->beta, 0, sizeof(double) * (size_t)su.P * p * L);
+    for (int pp = 0; pp < su.P; ++pp)
+        for (int i = 0; i < su.nlam_run[pp]; ++i) {
+            memcpy(res->beta + ((size_t)pp * L + i) * p, &pb.h_beta[((size_t)pp * L + i) * p], sizeof(double) * p);
+            res->niter[(size_t)pp * L + i] = pb.h_niter[(size_t)pp * L + i];
+        }
+    *res->d = pb.h_d[0];
+    finish_stats(cx, tm, t_total, res);
+}
+
+void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s,
+                  const oemb200_opts *o, oemb200_result *res);
+void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s, int nfolds,
+              const int *foldid, const char *type_measure, const oemb200_opts *o, oemb200_result *res);
+
+template <typename F>
+static int guarded(F &&f) {
+    try {
+        f();
+        return OEMB200_OK;
+    } catch (const Error &e) {
+        g_last_error = e.what();
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return OEMB200_EINVAL;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return OEMB200_EINVAL;
+    }
+}
+
+}  // namespace oemb200
+
+using namespace oemb200;
+
+extern "C" {
+
+const char *oemb200_last_error(void) { return g_last_error.c_str(); }
+const char *oemb200_version(void) { return "oem_b200 0.1 (sm_100a)"; }
+int oemb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+void oemb200_default_opts(oemb200_opts *o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->maxit = 500; o->tol = 1e-7; o->irls_maxit = 100; o->irls_tol = 1e-3; o->ncores = -1;
+    o->hessian_full = 0; o->accelerate = 0; o->gigs = 4.0; o->device = -1; o->world = 1;
+}
+int oemb200_penalty_id(const char *name) { return penalty_id(name); }
+int oemb200_nlambda_max(const oemb200_spec *s) {
+    if (!s) return 0;
+    if (s->n_lambda && s->lambda && s->n_lambda[0] >= 1) return s->n_lambda[0];
+    return s->nlambda;
+}
+
+int oemb200_fit_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *spec,
+                      const oemb200_opts *opts, oemb200_result *res) {
+    return guarded([&] { fit_dense(x, n, p, ldx, y, spec, opts, res); });
+}
+int oemb200_xtx(const double *xtx, const double *xty, int p, const oemb200_spec *spec, const double *scale_factor,
+                int n_scale_factor, const oemb200_opts *opts, oemb200_result *res) {
+    return guarded([&] { fit_xtx(xtx, xty, p, spec, scale_factor, n_scale_factor, opts, res); });
+}
+int oemb200_fit_big(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *spec,
+                    const oemb200_opts *opts, oemb200_result *res) {
+    return guarded([&] { fit_big(x, n, p, ldx, y, spec, opts, res); });
+}
+int oemb200_fit_logistic_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y,
+                               const oemb200_spec *spec, const oemb200_opts *opts, oemb200_result *res) {
+    return guarded([&] { fit_logistic(x, n, p, ldx, y, spec, opts, res); });
+}
+int oemb200_xval_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *spec,
+                       int nfolds, const int *foldid, const char *type_measure, const oemb200_opts *opts,
+                       oemb200_result *res) {
+    return guarded([&] { fit_xval(x, n, p, ldx, y, spec, nfolds, foldid, type_measure, opts, res); });
+}
+
+// ---------------- phase-level entries ----------------
+static void phase_ctx_opts(oemb200_opts &o, void *stream) {
+    oemb200_default_opts(&o);
+    o.stream = stream;
+}
+static double elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+#define OEM_PHASE_TIMED(body)                                                    \
+    oemb200_opts o_; phase_ctx_opts(o_, stream);                                 \
+    Ctx cx(&o_);                                                                 \
+    cudaEvent_t ea, eb;                                                          \
+    OEM_CUDA(cudaEventCreate(&ea)); OEM_CUDA(cudaEventCreate(&eb));              \
+    OEM_CUDA(cudaEventRecord(ea, cx.stream));                                    \
+    body;                                                                        \
+    OEM_CUDA(cudaEventRecord(eb, cx.stream));                                    \
+    cx.sync();                                                                   \
+    if (ms_out) *ms_out = elapsed_ms(ea, eb);                                    \
+    cudaEventDestroy(ea); cudaEventDestroy(eb);
+
+int oemb200_gram(const double *x_dev, int64_t n, int p, int64_t ldx, const double *mean_dev, const double *row_w_dev,
+                 double *g_dev, void *stream, double *ms_out) {
+    return guarded([&] {
+        OEM_PHASE_TIMED(gram_launch(cx, x_dev, n, p, ldx, {RowSegment{0, n, 0}}, 1, mean_dev, row_w_dev, g_dev, false));
+    });
+}
+int oemb200_colstats(const double *x_dev, int64_t n, int p, int64_t ldx, const double *v0_dev, const double *v1_dev,
+                     double *out_dev, void *stream, double *ms_out) {
+    return guarded([&] { OEM_PHASE_TIMED(colstats_launch(cx, x_dev, n, p, ldx, v0_dev, v1_dev, nullptr, out_dev, false)); });
+}
+int oemb200_xb_logistic(const double *x_dev, int64_t n, int p, int64_t ldx, const double *b_dev, double b0,
+                        const double *y_dev, double *prob_dev, double *resid_dev, double *w_dev, void *stream,
+                        double *ms_out) {
+    return guarded([&] {
+        OEM_PHASE_TIMED(xb_launch(cx, x_dev, n, p, ldx, b_dev, b0, y_dev, nullptr, prob_dev, resid_dev, w_dev, true));
+    });
+}
+int oemb200_top_eig(const double *xx_dev, int q, double *lambda_max_out, int *steps_out, void *stream) {
+    return guarded([&] {
+        oemb200_opts o_; phase_ctx_opts(o_, stream);
+        Ctx cx(&o_);
+        DBuf<double> d(1), xy(q);
+        DBuf<int> lz(1);
+        xy.zero(cx.stream);
+        PathProblem pp;
+        pp.q = q; pp.ngram = 1; pp.XX = xx_dev; pp.XY = xy.p; pp.d = d.p; pp.compute_eig = true;
+        pp.eig_factor = 1.0; pp.eig_tol = 1e-10; pp.Lmax = 1; pp.lanczos_steps = lz.p;
+        path_launch(cx, pp);
+        double h; int k;
+        d.download(&h, 1, cx.stream);
+        lz.download(&k, 1, cx.stream);
+        cx.sync();
+        if (lambda_max_out) *lambda_max_out = h;
+        if (steps_out) *steps_out = k;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// entry_logistic.cu -- host driver of oem_fit_logistic_dense (src/oem_logistic_dense.cpp:29-313,
+// solver src/oem_logistic_dense.h:721-1036) on the sm_100a kernels.
+//
+// Per IRLS iteration the data passes are the two HBM-bound sweeps the reference performs:
+//   prob = sigma(X (beta o w) + beta0)        -> xb_kernel        (oem_logistic_dense.h:864-949)
+//   grad = [sum(y-prob), X'(y-prob) o w] / n  -> colstats_kernel  (oem_logistic_dense.h:970-992)
+// plus, when the Hessian bound is (re)built, X'WX on the FP64 tensor pipe with the row weight fused
+// into the fragment load (gram_syrk_kernel<WEIGHT>) and the Lanczos eigenvalue inside the path kernel.
+// Row-sharded runs all-reduce the (p+1)-vector gradient and the Hessian bundle.
+// The reference's quirks are kept: the data pass is skipped on the
+// first IRLS iteration of a warm lambda, W is clamped at index = IRLS counter, eigen factor 1.0005.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "host_common.h"
+
+namespace oemb200 {
+
+__global__ void clamp_one_kernel(double *w, long long idx, double lo) {
+    if (w[idx] < lo) w[idx] = lo;
+}
+
+// loss of get_loss(): src/oem_logistic_dense.h:1057-1088 (uses whatever prob currently holds)
+__global__ void logistic_loss_kernel(const double *__restrict__ y, const double *__restrict__ prob, long long n,
+                                     double *__restrict__ partial) {
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double pr = prob[i];
+        if (y[i] == 1.0) s += (pr > 1e-5) ? log(1.0 / pr) : log(1.0 / 1e-5);
+        else s += (pr <= 1.0 - 1e-5) ? log(1.0 / (1.0 - pr)) : log(1.0 / 1e-5);
+    }
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s,
+                  const oemb200_opts *o, oemb200_result *res) {
+    check_common(s, o, res, "binomial");
+    if (n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
+    const int icpt = s->intercept ? 1 : 0, q = p + icpt;
+    const bool stdz = s->standardize != 0;
+    Ctx cx(o);
+    PhaseTimers tm(cx.stream);
+    const size_t t_total = tm.start(&cx.st.ms_total);
+    Setup su;
+    su.parse(s, q, q, /*zero_w0=*/true);
+
+    const size_t t_h = tm.start(&cx.st.ms_h2d);
+    DevMatrix X;
+    to_device_matrix(cx, x, n, p, ldx, X);
+    DevVector yv;
+    to_device_vector(cx, y, n, yv);
+    tm.stop(t_h);
+
+    // ---- init_oem: colsq, X'y, sum y (oem_logistic_dense.h:721-793) ----
+    const size_t nb0 = 3 * (size_t)p + 3;
+    DBuf<double> b0(nb0);
+    double *stats0 = b0.p, *ysum = stats0 + 3 * (size_t)p, *nobs = ysum + 2;
+    const size_t t_c = tm.start(&cx.st.ms_colstats);
+    colstats_launch(cx, X.p, n, p, X.ld, nullptr, yv.p, nullptr, stats0, false);
+    vecsum_launch(cx, yv.p, n, 0.0, ysum, false);
+    tm.stop(t_c);
+    const double nd = (double)n;
+    OEM_CUDA(cudaMemcpyAsync(nobs, &nd, 8, cudaMemcpyHostToDevice, cx.stream));
+    cx.all_reduce(b0.p, (int64_t)nb0);
+    std::vector<double> h0(nb0);
+    b0.download(h0.data(), nb0, cx.stream);
+    cx.sync();
+    const double n_tot = h0[nb0 - 1];
+    if (!(n_tot > q)) fail(OEMB200_EUNSUPPORTED, "n <= p logistic branch is outside the hot path");
+    std::vector<double> cinv(p, 1.0);
+    if (stdz)
+        for (int j = 0; j < p; ++j) {
+            double sq = h0[2 * (size_t)p + j] / (n_tot - 1.0);
+            if (sq == 0.0) sq = 1.0;
+            cinv[j] = 1.0 / std::sqrt(sq);
+        }
+    std::vector<double> XY0(q, 0.0);
+    if (icpt) XY0[0] = h0[3 * (size_t)p];
+    for (int j = 0; j < p; ++j) XY0[icpt + j] = stdz ? h0[(size_t)p + j] * cinv[j] : h0[(size_t)p + j];
+    for (auto &v : XY0) v /= n_tot;
+    double lmax = 0.0;
+    for (int j = 0; j < p; ++j) lmax = std::max(lmax, std::fabs(XY0[icpt + j]));
+    su.build_lambdas(s, lmax, /*logistic_fudge=*/true);
+
+    // ---- device state ----
+    std::vector<double> pf(q, 0.0);
+    for (int j = 0; j < p; ++j) pf[icpt + j] = s->penalty_factor[j];
+    DBuf<double> d_pf(q), d_b(p), d_beta(q), d_grad(q), d_XY(q), d_XX((size_t)q * q), d_d(1), d_lam(1);
+    DBuf<double> d_prob(n + (n & 1)), d_res(n + (n & 1)), d_W(n + (n & 1));
+    DBuf<double> d_beta_out(q), d_beta_final(q);
+    DBuf<int> d_niter(1), d_lz(1);
+    d_prob.zero(cx.stream);
+    d_pf.upload(pf.data(), q, cx.stream);
+    DBuf<int> g_unique, g_ptr, g_idx, g_cover;
+    DBuf<double> g_w;
+    if (su.any_group) {
+        g_unique.alloc(su.unique.size()); g_unique.upload(su.unique.data(), su.unique.size(), cx.stream);
+        g_ptr.alloc(su.ptr.size());       g_ptr.upload(su.ptr.data(), su.ptr.size(), cx.stream);
+        g_idx.alloc(std::max<size_t>(1, su.idx.size()));
+        if (!su.idx.empty()) g_idx.upload(su.idx.data(), su.idx.size(), cx.stream);
+        g_w.alloc(su.gw.size());          g_w.upload(su.gw.data(), su.gw.size(), cx.stream);
+        g_cover.alloc(q);                 g_cover.upload(su.cover.data(), q, cx.stream);
+    }
+    // Hessian bundle: [G p*p | stats 3p | sum W, sum W^2]
+    const size_t nbh = (size_t)p * p + 3 * (size_t)p + 2;
+    DBuf<double> bh(nbh), d_nobs(1);
+    d_nobs.upload(&n_tot, 1, cx.stream);
+    DBuf<double> gradb(3 * (size_t)p + 2);   // [stats 3p | sum r, sum r^2]
+    DBuf<double> d_losspart(1024);
+
+    const int L = su.Lmax;
+    fill_common_outputs(su, res);
+    memset(res->beta, 0, sizeof(double) * (size_t)su.P * (p + 1) * L);
+    std::vector<double> beta(q, 0.0), beta_prev(q), hgrad(3 * (size_t)p + 2), hb(p), gvec(q);
+    double dval = 0.0;
+
+    for (int pp = 0; pp < su.P; ++pp) {
+        std::fill(beta.begin(), beta.end(), 0.0);              // init(): beta = 0, on_lam_1 = true
+        for (int i = 0; i < su.nlam_run[pp]; ++i) {
+            const bool on_lam_1 = (i == 0);
+            const double lam = su.lam[pp][i];
+            int it = 0;
+            bool broke = false;
+            for (it = 0; it < o->irls_maxit; ++it) {
+                beta_prev = beta;
+                bool rebuilt = false;
+                if (!(it == 0 && !on_lam_1)) {
+                    for (int j = 0; j < p; ++j) hb[j] = stdz ? beta[icpt + j] * cinv[j] : beta[icpt + j];
+                    d_b.upload(hb.data(), p, cx.stream);
+                    const size_t t1 = tm.start(&cx.st.ms_irls_xb);
+                    xb_launch(cx, X.p, n, p, X.ld, d_b.p, icpt ? beta[0] : 0.0, yv.p, nullptr, d_prob.p, d_res.p, d_W.p, true);
+                    tm.stop(t1);
+                    cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
+                    if (o->rank == 0 && it < n) {            // W(i) clamp, sic (oem_logistic_dense.h:953-959)
+                        clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, it, 1e-5);
+                        cx.st.kernel_launches += 1;
+                    }
+                    if ((it == 0 && on_lam_1) || o->hessian_full) {
+                        // X'WX / n with the intercept border (oem_logistic_dense.h:458-522)
+                        double *G = bh.p, *st = G + (size_t)p * p, *ws = st + 3 * (size_t)p;
+                        const size_t tg = tm.start(&cx.st.ms_gram);
+                        gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, nullptr, d_W.p, G, false);
+                        tm.stop(tg);
+                        const size_t tc = tm.start(&cx.st.ms_colstats);
+                        colstats_launch(cx, X.p, n, p, X.ld, d_W.p, nullptr, nullptr, st, false);
+                        vecsum_launch(cx, d_W.p, n, 0.0, ws, false);
+                        tm.stop(tc);
+                        cx.all_reduce(bh.p, (int64_t)nbh);
+                        // border = (W'X) o w, corner = sum W, divisor n; uncentred scale from the DATA colsq:
+                        // assemble_aug derives w from stats row 2, so put sum x^2 there
+                        OEM_CUDA(cudaMemcpyAsync(st + 2 * (size_t)p, stats0 + 2 * (size_t)p, (size_t)p * 8,
+                                                 cudaMemcpyDeviceToDevice, cx.stream));
+                        assemble_aug_launch(cx, p, icpt, stdz ? 1 : 0, 1, 1, G, st, ws, ws, d_nobs.p, d_XX.p, nullptr,
+                                            nullptr, nullptr);
+                        rebuilt = true;
+                    }
+                    const size_t t2 = tm.start(&cx.st.ms_irls_xtr);
+                    colstats_launch(cx, X.p, n, p, X.ld, d_res.p, nullptr, nullptr, gradb.p, false);
+                    vecsum_launch(cx, d_res.p, n, 0.0, gradb.p + 3 * (size_t)p, false);
+                    tm.stop(t2);
+                    cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
+                    cx.all_reduce(gradb.p, (int64_t)(3 * (size_t)p + 2));
+                    gradb.download(hgrad.data(), hgrad.size(), cx.stream);
+                    cx.sync();
+                    if (icpt) gvec[0] = hgrad[3 * (size_t)p] / n_tot;
+                    for (int j = 0; j < p; ++j) {
+                        double g = hgrad[j] / n_tot;
+                        if (stdz) g *= cinv[j];
+                        gvec[icpt + j] = g;
+                    }
+                    d_grad.upload(gvec.data(), q, cx.stream);
+                    d_beta.upload(beta.data(), q, cx.stream);
+                    symv_add_launch(cx, q, d_XX.p, d_beta.p, d_grad.p, d_XY.p);     // XY = XX beta + grad (:999)
+                } else {
+                    d_beta.upload(beta.data(), q, cx.stream);
+                }
+                // inner OEM loop: one chain, one lambda, warm start (oem_logistic_dense.h:1010-1022)
+                d_lam.upload(&lam, 1, cx.stream);
+                PathProblem pr;
+                pr.q = q; pr.ngram = 1; pr.XX = d_XX.p; pr.XY = d_XY.p; pr.d = d_d.p;
+                pr.compute_eig = rebuilt; pr.eig_factor = 1.0005; pr.eig_tol = 1e-10;
+                ChainDesc c;
+                c.gram = 0; c.penalty = su.pen[pp]; c.nlam = 1; c.lam_off = 0; c.alpha = su.alpha;
+                c.gamma = su.gamma[pp]; c.tau = su.tau; c.out_off = 0;
+                pr.chains.push_back(c);
+                pr.lambdas = d_lam.p; pr.Lmax = 1; pr.pen_fact = d_pf.p;
+                pr.ngroups = su.any_group ? (int)su.unique.size() : 0;
+                pr.unique_groups = g_unique.p; pr.grp_ptr = g_ptr.p; pr.grp_idx = g_idx.p;
+                pr.group_weights = g_w.p; pr.grp_cover = g_cover.p;
+                pr.beta_init = d_beta.p; pr.beta_final = d_beta_final.p;
+                pr.maxit = o->maxit; pr.tol = o->tol;
+                pr.beta_out = d_beta_out.p; pr.niter_out = d_niter.p; pr.lanczos_steps = d_lz.p;
+                const size_t t3 = tm.start(&cx.st.ms_path);
+                path_launch(cx, pr);
+                tm.stop(t3);
+                d_beta_out.download(beta.data(), q, cx.stream);
+                int hn = 0;
+                d_niter.download(&hn, 1, cx.stream);
+                if (rebuilt) d_d.download(&dval, 1, cx.stream);
+                cx.sync();
+                cx.st.total_oem_iters += hn;
+                if (stop_rule_host(beta, beta_prev, o->irls_tol)) { broke = true; break; }
+            }
+            res->niter[(size_t)pp * L + i] = (broke ? it : o->irls_maxit) + 1;
+            double *out = res->beta + ((size_t)pp * L + i) * (p + 1);
+            if (icpt) out[0] = beta[0];
+            for (int j = 0; j < p; ++j) out[1 + j] = stdz ? beta[icpt + j] * cinv[j] : beta[icpt + j];
+            if (s->compute_loss && res->loss) {
+                logistic_loss_kernel<<<1024, 256, 0, cx.stream>>>(yv.p, d_prob.p, n, d_losspart.p);
+                cx.st.kernel_launches += 1;
+                DBuf<double> tot(2);
+                vecsum_launch(cx, d_losspart.p, 1024, 0.0, tot.p, false);
+                cx.all_reduce(tot.p, 2);
+                double h[2];
+                tot.download(h, 2, cx.stream);
+                cx.sync();
+                res->loss[(size_t)pp * L + i] = h[0];
+            }
+        }
+    }
+    *res->d = dval;
+    finish_stats(cx, tm, t_total, res);
+}
+
+}  // namespace oemb200

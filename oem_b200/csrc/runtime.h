@@ -1,0 +1,169 @@
+// runtime.h -- host-side runtime shared by the entry-point drivers: device context, RAII device
+// buffers, phase timers, and the declarations of the kernel launchers (one .cu file each).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/oem_b200.h"
+#include "common.cuh"
+
+namespace oemb200 {
+
+struct Ctx {
+    int device = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    oemb200_stats st;              // accumulated by the launchers
+    oemb200_allreduce_fn allreduce = nullptr;
+    void *allreduce_ctx = nullptr;
+
+    explicit Ctx(const oemb200_opts *o);
+    ~Ctx();
+    void sync() { OEM_CUDA(cudaStreamSynchronize(stream)); }
+    void all_reduce(double *dev_buf, int64_t count);
+};
+
+// RAII device buffer
+template <typename T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    explicit DBuf(size_t n_) { alloc(n_); }
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf &operator=(DBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DBuf() { release(); }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) OEM_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void zero(cudaStream_t s) { if (n) OEM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void upload(const T *h, size_t cnt, cudaStream_t s) {
+        OEM_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T *h, size_t cnt, cudaStream_t s) const {
+        OEM_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+// CUDA-event phase timer: adds elapsed ms to *acc when stopped (after a stream sync at the end
+// of the call: see PhaseTimers::collect()).
+struct PhaseTimers {
+    struct Rec { cudaEvent_t a, b; double *acc; };
+    std::vector<Rec> recs;
+    cudaStream_t s;
+    explicit PhaseTimers(cudaStream_t s_) : s(s_) {}
+    ~PhaseTimers() { for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
+    size_t start(double *acc) {
+        Rec r; r.acc = acc;
+        OEM_CUDA(cudaEventCreate(&r.a)); OEM_CUDA(cudaEventCreate(&r.b));
+        OEM_CUDA(cudaEventRecord(r.a, s));
+        recs.push_back(r);
+        return recs.size() - 1;
+    }
+    void stop(size_t i) { OEM_CUDA(cudaEventRecord(recs[i].b, s)); }
+    void collect() {   // call after the stream is synchronized
+        for (auto &r : recs) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.acc) *r.acc += ms;
+        }
+    }
+};
+
+bool is_device_ptr(const void *p);
+
+// ---------------- gram_syrk.cu ----------------
+struct RowSegment { int64_t row0, row1; int out; };   // rows [row0,row1) accumulate into Gram #out
+// G[out] (q x q col-major, full symmetric; nout matrices, stride q*q) (+)= X_seg' diag(w) X_seg with
+// optional column centring.  Segment boundaries must be multiples of 36 rows except at n.
+void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const std::vector<RowSegment> &segs,
+                 int nout, const double *mean, const double *roww, double *G, bool accumulate);
+int gram_kt();   // rows per pipeline stage (segment alignment)
+
+// ---------------- colstats.cu ----------------
+// with xs = x - shift_j (shift may be NULL):
+// out[0*p + j] = sum_i xs_ij v0_i, out[1*p + j] = sum_i xs_ij v1_i, out[2*p + j] = sum_i xs_ij^2 (NULL v = ones)
+void colstats_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const double *v0, const double *v1,
+                     const double *shift, double *out3p, bool accumulate);
+// out2[0] (+)= sum (v - shift), out2[1] (+)= sum (v - shift)^2
+void vecsum_launch(Ctx &cx, const double *v, int64_t n, double shift, double *out2, bool accumulate);
+// out = (v - shift) / divisor
+void affine_launch(Ctx &cx, const double *v, int64_t n, double shift, double divisor, double *out);
+// y += a * x
+void axpy_launch(Ctx &cx, int64_t n, double a, const double *x, double *y);
+// eta = X b + b0 (+ logistic epilogue: prob, resid = y - prob, w = prob (1 - prob))
+void xb_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const double *b, double b0, const double *y,
+               double *eta, double *prob, double *resid, double *w, bool logistic);
+
+// ---------------- path_kernel.cu ----------------
+struct ChainDesc {          // one warm-started lambda path: (Gram, penalty)
+    int gram;               // index of the Gram / XY this chain runs on
+    int penalty;            // OEMB200_PEN_*
+    int nlam;               // number of lambdas
+    int lam_off;            // offset into the lambda array
+    double alpha, gamma, tau;
+    int out_off;            // chain slot in beta_out / niter_out (units of chains)
+};
+struct PathProblem {
+    int q = 0;              // dimension of beta
+    int ngram = 0;          // number of Grams (teams)
+    const double *XX = nullptr;    // device, ngram x q x q (already scaled, / n)
+    const double *XY = nullptr;    // device, ngram x q
+    double *d = nullptr;           // device, ngram: in (compute_eig=0) or out (compute_eig=1)
+    bool compute_eig = true;
+    double eig_factor = 1.005;
+    double eig_tol = 1e-11;
+    std::vector<ChainDesc> chains;
+    const double *lambdas = nullptr;   // device, concatenated
+    int Lmax = 0;                      // stride (in lambdas) of a chain's output block
+    const double *pen_fact = nullptr;  // device, q
+    // group structure (device), CSR over unique groups
+    int ngroups = 0;
+    const int *unique_groups = nullptr, *grp_ptr = nullptr, *grp_idx = nullptr;
+    const double *group_weights = nullptr;
+    const int *grp_cover = nullptr;       // device, q: 1 if the variable belongs to a listed group
+    const double *post_scale = nullptr;   // oem_xtx scale.factor quirk: beta *= post_scale after each lambda
+    const double *beta_init = nullptr;    // device, nchains x q warm start (NULL = zeros)
+    double *beta_final = nullptr;         // device, nchains x q: iterate after the last lambda (may be NULL)
+    int maxit = 500;
+    double tol = 1e-7;
+    bool accelerate = false;
+    double *beta_out = nullptr;    // device, nchains x Lmax x q  (raw iterates)
+    int *niter_out = nullptr;      // device, nchains x Lmax
+    int *lanczos_steps = nullptr;  // device, ngram (may be NULL)
+};
+void path_launch(Ctx &cx, const PathProblem &pp);
+
+// ---------------- assemble.cu ----------------
+// oem_big / logistic / xval convention: explicit intercept border, uncentred scaling.
+// Output o sums all parts except part o-1 (o = 0: all).  XY / colsq_inv / nobs_out may be NULL.
+void assemble_aug_launch(Ctx &cx, int p, int intercept, int standardize, int nparts, int nout,
+                         const double *G_parts /*nparts x p x p*/, const double *stats_parts /*nparts x 3 x p*/,
+                         const double *ysum_parts /*nparts*/, const double *corner_parts /*nparts*/,
+                         const double *nobs_parts /*nparts*/, double *XX /*nout x q x q*/, double *XY /*nout x q*/,
+                         double *colsq_inv /*nout x p*/, double *nobs_out /*nout*/);
+// oem_dense convention: G is the Gram of centred (flag 2,3) or raw (flag 0,1) columns
+void assemble_dense_launch(Ctx &cx, int p, int flag, double n, const double *G, const double *xy, const double *css,
+                           double *XX, double *XY, double *scalex);
+// oem_xtx scale.factor (sinv may be NULL = plain copy)
+void scale_sym_launch(Ctx &cx, int p, const double *sinv, const double *XXin, const double *XYin, double *XX,
+                      double *XY);
+// y = M x + add for a symmetric q x q M
+void symv_add_launch(Ctx &cx, int q, const double *M, const double *x, const double *add, double *y);
+
+}  // namespace oemb200

@@ -1,0 +1,136 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI, via oem_b200.api) against the CPU oracle
+on the same seeded inputs.  Bar: max|delta beta| <= 1e-8 (FP64), lambda sequences <= 4 ulp, d to 1e-9."""
+import numpy as np
+import pytest
+
+from cases import args_xy, assert_same_fit, binomial_problem, gaussian_problem
+
+pytestmark = pytest.mark.gpu
+
+ALL_COORD = ["lasso", "ols", "elastic.net", "scad", "scad.net", "mcp", "mcp.net"]
+ALL_GROUP = ["grp.lasso", "grp.lasso.net", "grp.mcp", "grp.scad", "grp.mcp.net", "grp.scad.net", "sparse.grp.lasso"]
+
+
+@pytest.mark.parametrize("standardize,intercept", [(False, False), (True, False), (False, True), (True, True)])
+def test_dense_flags(lib, oracle, standardize, intercept):
+    X, y = gaussian_problem(11, 3000, 60, sd_x=2.0, mean_x=0.7)
+    a = args_xy(X, y, "gaussian", ["lasso", "mcp"], standardize=standardize, intercept=intercept, nlambda=30,
+                opts=dict(tol=1e-10))
+    assert_same_fit(lib.oem_fit_dense(*a), oracle.oem_fit_dense(*a))
+
+
+def test_dense_readme_lasso_config1_small(lib, oracle):
+    # BASELINE config 1 shape (README.md:45-65) at n = 2e4: elastic.net alpha=1, intercept, no standardize
+    X, y = gaussian_problem(101, 20000, 100, sd_x=3.0)
+    a = args_xy(X, y, "gaussian", ["elastic.net"], standardize=False, intercept=True, opts=dict(tol=1e-10))
+    assert_same_fit(lib.oem_fit_dense(*a), oracle.oem_fit_dense(*a))
+
+
+def test_dense_nonconvex_config2(lib, oracle):
+    # BASELINE config 2 at full size: MCP gamma=2 + SCAD gamma=4, n=5000 p=200, 200 lambdas, batched
+    X, y = gaussian_problem(102, 5000, 200, sd_x=3.0)
+    a = args_xy(X, y, "gaussian", ["mcp", "scad"], gamma=[2.0, 4.0], nlambda=200, opts=dict(tol=1e-10))
+    got = lib.oem_fit_dense(*a)
+    ref = oracle.oem_fit_dense(*a)
+    assert_same_fit(got, ref)
+    # the per-penalty gamma extension reduces to two scalar-gamma calls of the reference interface
+    a1 = args_xy(X, y, "gaussian", ["scad"], gamma=4.0, nlambda=200, opts=dict(tol=1e-10))
+    ref1 = oracle.oem_fit_dense(*a1)
+    assert np.max(np.abs(got["beta"][1] - ref1["beta"][0])) <= 1e-8
+
+
+def test_dense_all_penalties(lib, oracle):
+    X, y = gaussian_problem(7, 2000, 40)
+    groups = np.repeat(np.arange(1, 9), 5)
+    groups[:3] = 0
+    a = args_xy(X, y, "gaussian", ALL_COORD + ALL_GROUP, groups=groups, unique_groups=np.unique(groups), alpha=0.6,
+                gamma=3.0, tau=0.4, nlambda=25, opts=dict(tol=1e-10))
+    assert_same_fit(lib.oem_fit_dense(*a), oracle.oem_fit_dense(*a))
+
+
+def test_dense_odd_rows_user_lambda_accelerate_loss(lib, oracle):
+    X, y = gaussian_problem(5, 1501, 33)       # odd n: the non-TMA loader path
+    lam = [np.geomspace(1.0, 1e-3, 12), np.geomspace(0.5, 1e-3, 12)]
+    pf = np.ones(33); pf[:2] = 0.0; pf[5] = 2.5
+    a = args_xy(X, y, "gaussian", ["lasso", "scad"], lambda_=lam, penalty_factor=pf, compute_loss=True,
+                opts=dict(tol=1e-9, accelerate=True))
+    got, ref = lib.oem_fit_dense(*a), oracle.oem_fit_dense(*a)
+    assert_same_fit(got, ref)
+    for lg, lr in zip(got["loss"], ref["loss"]):
+        assert np.allclose(lg, lr, rtol=1e-10)
+
+
+def test_xtx_identity_and_scale_factor(lib, oracle):
+    X, y = gaussian_problem(3, 4000, 50)
+    n = X.shape[0]
+    xtx, xty = X.T @ X / n, X.T @ y / n
+    pens = ["lasso", "mcp", "grp.lasso"]
+    groups = np.repeat(np.arange(1, 11), 5)
+    common = ["gaussian", pens, groups, np.unique(groups), [], [], 40, 1e-3, 1.0, 3.0, 0.5]
+    o = dict(maxit=500, tol=1e-10)
+    got = lib.oem_xtx(xtx, xty, *common, [], np.ones(50), o)
+    ref = oracle.oem_xtx(xtx, xty, *common, [], np.ones(50), o)
+    assert_same_fit(got, ref, lam_ulps=4)
+    # the reference's own printed identity (R/oem_xtx.R:69-103): oem(standardize=F, intercept=F) == oem.xtx
+    a = args_xy(X, y, "gaussian", pens, groups=groups, unique_groups=np.unique(groups), standardize=False,
+                intercept=False, nlambda=40, lmin_ratio=1e-3, opts=dict(tol=1e-10))
+    dense = lib.oem_fit_dense(*a)
+    for pp in range(len(pens)):
+        assert np.max(np.abs(dense["beta"][pp][1:, :] - got["beta"][pp])) <= 1e-10
+    sf = np.sqrt(np.diag(xtx))
+    got = lib.oem_xtx(xtx, xty, *common, sf, np.ones(50), o)
+    ref = oracle.oem_xtx(xtx, xty, *common, sf, np.ones(50), o)
+    assert_same_fit(got, ref)
+
+
+@pytest.mark.parametrize("standardize,intercept", [(True, True), (False, True), (True, False)])
+def test_big_small(lib, oracle, standardize, intercept):
+    X, y = gaussian_problem(105, 6000, 130, mean_x=0.3)
+    groups = np.concatenate([[0], np.repeat(np.arange(1, 14), 10)]) if intercept else np.repeat(np.arange(1, 14), 10)
+    a = args_xy(X, y, "gaussian", ["lasso", "scad", "mcp", "grp.lasso"], gamma=[3.0, 3.7, 3.0, 3.0], groups=groups,
+                unique_groups=np.unique(groups), standardize=standardize, intercept=intercept, nlambda=50)
+    assert_same_fit(lib.oem_fit_big(*a), oracle.oem_fit_big(*a))
+
+
+def test_big_streams_host_chunks(lib, oracle):
+    # host X larger than one streaming chunk (gigs) -> several accumulate passes, same answer
+    X, y = gaussian_problem(106, 20000, 64)
+    a = args_xy(X, y, "gaussian", ["lasso"], nlambda=20, opts=dict(gigs=0.002))
+    assert_same_fit(lib.oem_fit_big(*a), oracle.oem_fit_big(*a))
+
+
+def test_big_device_resident(lib, oracle):
+    import torch
+    X, y = gaussian_problem(107, 9000, 257)
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t()       # column-major on the device
+    yd = torch.from_numpy(y).cuda()
+    a = args_xy(X, y, "gaussian", ["lasso", "mcp"], nlambda=30)
+    ref = oracle.oem_fit_big(*a)
+    a[0], a[1] = Xd, yd
+    assert_same_fit(lib.oem_fit_big(*a), ref)
+
+
+@pytest.mark.parametrize("hessian", ["upper.bound", "full"])
+def test_logistic(lib, oracle, hessian):
+    X, y = binomial_problem(104, 4000, 40)
+    groups = np.concatenate([[0], np.repeat(np.arange(1, 9), 5)])
+    a = args_xy(X, y, "binomial", ["lasso", "mcp.net", "grp.lasso"], groups=groups, unique_groups=np.unique(groups),
+                alpha=0.7, nlambda=15, lmin_ratio=1e-2, compute_loss=True, opts=dict(hessian_type=hessian))
+    got, ref = lib.oem_fit_logistic_dense(*a), oracle.oem_fit_logistic_dense(*a)
+    assert_same_fit(got, ref, tol=1e-8)
+    for lg, lr in zip(got["loss"], ref["loss"]):
+        assert np.allclose(lg, lr, rtol=1e-9)
+
+
+def test_errors_mirror_reference(lib):
+    X, y = gaussian_problem(1, 100, 5)
+    a = args_xy(X, y, "binomial", ["lasso"])
+    with pytest.raises(lib.OemB200Error, match="binomial not available"):
+        lib.oem_fit_dense(*a)
+    a = args_xy(X, y, "gaussian", ["lasso"])
+    a[4] = np.ones(100)
+    with pytest.raises(lib.OemB200Error, match="weights not implemented"):
+        lib.oem_fit_dense(*a)
+    a = args_xy(X, y, "gaussian", ["nope"])
+    with pytest.raises(lib.OemB200Error, match="unknown penalty"):
+        lib.oem_fit_big(*a)
