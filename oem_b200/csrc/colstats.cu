@@ -116,7 +116,6 @@ void colstats_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, con
     OEM_CUDA(cudaGetLastError());
     cx.st.kernel_launches += 2;
     cx.st.xtr_launches += 1;
-    OEM_CUDA(cudaStreamSynchronize(cx.stream));   // partial is freed on return
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -151,7 +150,6 @@ void vecsum_launch(Ctx &cx, const double *v, int64_t n, double shift, double *ou
     sum_partials_kernel<<<1, 32, 0, cx.stream>>>(partial.p, nchunks, 2, out2, accumulate ? 1 : 0);
     OEM_CUDA(cudaGetLastError());
     cx.st.kernel_launches += 2;
-    OEM_CUDA(cudaStreamSynchronize(cx.stream));
 }
 
 __global__ void affine_kernel(const double *__restrict__ v, long long n, double shift, double divisor,

@@ -70,8 +70,7 @@ void fill_common_outputs(const Setup &su, oemb200_result *res) {
 
 void finish_stats(Ctx &cx, PhaseTimers &tm, size_t total_id, oemb200_result *res) {
     tm.stop(total_id);
-    cx.sync();
-    tm.collect();
+    cx.finish();
     if (res->stats) *res->stats = cx.st;
 }
 
@@ -84,7 +83,7 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
     if (n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
     const int icpt = s->intercept ? 1 : 0, q = p + icpt;
     Ctx cx(o);
-    PhaseTimers tm(cx.stream);
+    PhaseTimers &tm = *cx.tm;
     const size_t t_total = tm.start(&cx.st.ms_total);
     Setup su;
     su.parse(s, q, /*scan=*/p, /*zero_w0=*/false);      // v < nvars quirk: src/oem_big.h:445
@@ -105,9 +104,7 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
         const size_t t1 = tm.start(&cx.st.ms_colstats);
         colstats_launch(cx, x, n, p, ldx, nullptr, yv.p, nullptr, stats, false);
         tm.stop(t1);
-        const size_t t2 = tm.start(&cx.st.ms_gram);
         gram_launch(cx, x, n, p, ldx, {RowSegment{0, n, 0}}, 1, nullptr, nullptr, G, false);
-        tm.stop(t2);
     } else {
         // host X: double-buffered row chunks; H2D of chunk c+1 overlaps the kernels of chunk c
         const double gigs = o->gigs > 0 ? o->gigs : 1.0;
@@ -207,7 +204,7 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
     if (n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
     const int flag = (s->standardize ? 1 : 0) + 2 * (s->intercept ? 1 : 0);
     Ctx cx(o);
-    PhaseTimers tm(cx.stream);
+    PhaseTimers &tm = *cx.tm;
     const size_t t_total = tm.start(&cx.st.ms_total);
     Setup su;
     su.parse(s, p, p, false);
@@ -280,9 +277,7 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
         OEM_CUDA(cudaMemcpyAsync(css, stats2.p + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
     }
     tm.stop(t_c2);
-    const size_t t_g = tm.start(&cx.st.ms_gram);
     gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, center_x ? d_mean.p : nullptr, nullptr, G, false);
-    tm.stop(t_g);
     const size_t t_ar = tm.start(&cx.st.ms_allreduce);
     cx.all_reduce(b2.p, (int64_t)nb2);
     tm.stop(t_ar);
@@ -365,7 +360,7 @@ static void fit_xtx(const double *xtx, const double *xty, int p, const oemb200_s
     if (p < 1 || !xtx || !xty) fail(OEMB200_EINVAL, "xtx / xty missing");
     if (n_sf != 0 && n_sf != p) fail(OEMB200_EINVAL, "scale_factor must have length p");
     Ctx cx(o);
-    PhaseTimers tm(cx.stream);
+    PhaseTimers &tm = *cx.tm;
     const size_t t_total = tm.start(&cx.st.ms_total);
     Setup su;
     su.parse(s, p, p, false);

@@ -48,7 +48,7 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     const int icpt = s->intercept ? 1 : 0, q = p + icpt;
     const bool stdz = s->standardize != 0;
     Ctx cx(o);
-    PhaseTimers tm(cx.stream);
+    PhaseTimers &tm = *cx.tm;
     const size_t t_total = tm.start(&cx.st.ms_total);
     Setup su;
     su.parse(s, q, q, /*zero_w0=*/true);
@@ -147,9 +147,7 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                     if ((it == 0 && on_lam_1) || o->hessian_full) {
                         // X'WX / n with the intercept border (oem_logistic_dense.h:458-522)
                         double *G = bh.p, *st = G + (size_t)p * p, *ws = st + 3 * (size_t)p;
-                        const size_t tg = tm.start(&cx.st.ms_gram);
                         gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, nullptr, d_W.p, G, false);
-                        tm.stop(tg);
                         const size_t tc = tm.start(&cx.st.ms_colstats);
                         colstats_launch(cx, X.p, n, p, X.ld, d_W.p, nullptr, nullptr, st, false);
                         vecsum_launch(cx, d_W.p, n, 0.0, ws, false);

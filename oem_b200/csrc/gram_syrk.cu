@@ -352,6 +352,7 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
 
     const int ni = (int)items.size();
     const bool C = mean != nullptr, W = roww != nullptr;
+    const size_t t_k = cx.tm->start(&cx.st.ms_gram);      // the DMMA kernel alone
 #define OEM_GRAM_DISPATCH(CC, WW)                                                                           \
     if (use_tma) launch_variant<CC, WW, true>(cx, tm, X, ld, n, q, d_items.p, ni, mean, roww, ws.p);        \
     else launch_variant<CC, WW, false>(cx, tm, X, ld, n, q, d_items.p, ni, mean, roww, ws.p)
@@ -360,16 +361,17 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     else if (W) { OEM_GRAM_DISPATCH(false, true); }
     else { OEM_GRAM_DISPATCH(false, false); }
 #undef OEM_GRAM_DISPATCH
+    cx.tm->stop(t_k);
+    const size_t t_r = cx.tm->start(&cx.st.ms_gram_reduce);
 
     dim3 rg(G_TILE * G_TILE / 256, (unsigned)tiles.size());
     gram_reduce_kernel<<<rg, 256, 0, cx.stream>>>(ws.p, d_tiles.p, G, q, accumulate ? 1 : 0);
     OEM_CUDA(cudaGetLastError());
+    cx.tm->stop(t_r);
     cx.st.kernel_launches += 2;
     cx.st.gram_launches += 1;
     cx.st.gram_flops += (double)rows_total * q * (q + 1.0);
-    // the workspace and item lists are freed when the DBufs go out of scope; cudaFree synchronizes,
-    // which is fine here: the Gram is followed by a host-side step in every entry point.
-    OEM_CUDA(cudaStreamSynchronize(cx.stream));
+    // workspace / item lists go back to the pool on return; stream order protects them (runtime.h)
 }
 
 }  // namespace oemb200

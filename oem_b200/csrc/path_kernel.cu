@@ -573,7 +573,6 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     void *kargs[] = {&a};
     OEM_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(G * team), dim3(PK_THREADS), kargs, smem_bytes, cx.stream));
     cx.st.kernel_launches += 1;
-    OEM_CUDA(cudaStreamSynchronize(cx.stream));
 }
 
 }  // namespace oemb200

@@ -1,4 +1,6 @@
 // runtime.cu -- device context and small runtime helpers (see runtime.h).
+#include <map>
+#include <exception>
 #include "runtime.h"
 
 namespace oemb200 {
@@ -30,10 +32,66 @@ Ctx::Ctx(const oemb200_opts *o) {
         own_stream = true;
     }
     if (o) { allreduce = o->allreduce; allreduce_ctx = o->allreduce_ctx; }
+    tm = new PhaseTimers(stream);
 }
 
 Ctx::~Ctx() {
+    if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();   // unwinding: let queued kernels drain before buffers recycle
+    delete tm;
     if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+void Ctx::finish() {
+    OEM_CUDA(cudaStreamSynchronize(stream));
+    if (tm) {
+        tm->collect();
+        delete tm;
+        tm = new PhaseTimers(stream);
+    }
+}
+
+// ---- thread-local caching allocator ----
+namespace {
+struct Pool {
+    std::multimap<size_t, void *> free_blocks;
+    std::map<void *, size_t> live;
+};
+thread_local Pool g_pool;
+}  // namespace
+
+void *pool_alloc(size_t bytes) {
+    const size_t sz = (bytes + 511) & ~size_t(511);
+    auto it = g_pool.free_blocks.lower_bound(sz);
+    if (it != g_pool.free_blocks.end() && it->first <= sz + sz / 8) {   // reuse a block at most 12.5% larger
+        void *p = it->second;
+        g_pool.live[p] = it->first;
+        g_pool.free_blocks.erase(it);
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_release_all();                       // drop the cache and retry once
+        e = cudaMalloc(&p, sz);
+        if (e != cudaSuccess) fail(OEMB200_ECUDA, "cudaMalloc of %.3f GB failed: %s", sz / 1e9, cudaGetErrorString(e));
+    }
+    g_pool.live[p] = sz;
+    return p;
+}
+
+void pool_free(void *p) {
+    auto it = g_pool.live.find(p);
+    if (it == g_pool.live.end()) { cudaFree(p); return; }
+    // very large blocks (the uploaded copy of X) are not worth caching
+    if (it->second > (size_t(4) << 30)) cudaFree(p);
+    else g_pool.free_blocks.emplace(it->second, p);
+    g_pool.live.erase(it);
+}
+
+void pool_release_all() {
+    for (auto &kv : g_pool.free_blocks) cudaFree(kv.second);
+    g_pool.free_blocks.clear();
 }
 
 void Ctx::all_reduce(double *dev_buf, int64_t count) {

@@ -11,6 +11,31 @@
 
 namespace oemb200 {
 
+// CUDA-event phase timer: adds elapsed ms to *acc when stopped (after a stream sync at the end
+// of the call: see PhaseTimers::collect()).
+struct PhaseTimers {
+    struct Rec { cudaEvent_t a, b; double *acc; };
+    std::vector<Rec> recs;
+    cudaStream_t s;
+    explicit PhaseTimers(cudaStream_t s_) : s(s_) {}
+    PhaseTimers(const PhaseTimers &) = delete;
+    ~PhaseTimers() { for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
+    size_t start(double *acc) {
+        Rec r; r.acc = acc;
+        OEM_CUDA(cudaEventCreate(&r.a)); OEM_CUDA(cudaEventCreate(&r.b));
+        OEM_CUDA(cudaEventRecord(r.a, s));
+        recs.push_back(r);
+        return recs.size() - 1;
+    }
+    void stop(size_t i) { OEM_CUDA(cudaEventRecord(recs[i].b, s)); }
+    void collect() {   // call after the stream is synchronized
+        for (auto &r : recs) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.acc) *r.acc += ms;
+        }
+    }
+};
+
 struct Ctx {
     int device = 0;
     int num_sms = 148;
@@ -20,14 +45,25 @@ struct Ctx {
     oemb200_stats st;              // accumulated by the launchers
     oemb200_allreduce_fn allreduce = nullptr;
     void *allreduce_ctx = nullptr;
+    PhaseTimers *tm = nullptr;     // created with the context, collected by finish()
 
     explicit Ctx(const oemb200_opts *o);
     ~Ctx();
     void sync() { OEM_CUDA(cudaStreamSynchronize(stream)); }
     void all_reduce(double *dev_buf, int64_t count);
+    void finish();                 // sync the stream, fold the event timings into st
 };
 
-// RAII device buffer
+// Thread-local caching device allocator: entry calls repeat the same shapes, so after the first call
+// no cudaMalloc / cudaFree (and none of their implicit device syncs) happen in steady state.  Blocks are
+// handed back while kernels using them may still be queued; that is safe because every block is only
+// ever reused by the same host thread on the call's single compute stream (stream order), and each
+// entry point synchronizes its stream before returning.
+void *pool_alloc(size_t bytes);
+void pool_free(void *p);
+void pool_release_all();      // cudaFree everything cached by this thread
+
+// RAII device buffer (pooled)
 template <typename T>
 struct DBuf {
     T *p = nullptr;
@@ -45,10 +81,10 @@ struct DBuf {
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) OEM_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T)));
+        if (n) p = static_cast<T *>(pool_alloc(n * sizeof(T)));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr;
         n = 0;
     }
@@ -58,30 +94,6 @@ struct DBuf {
     }
     void download(T *h, size_t cnt, cudaStream_t s) const {
         OEM_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s));
-    }
-};
-
-// CUDA-event phase timer: adds elapsed ms to *acc when stopped (after a stream sync at the end
-// of the call: see PhaseTimers::collect()).
-struct PhaseTimers {
-    struct Rec { cudaEvent_t a, b; double *acc; };
-    std::vector<Rec> recs;
-    cudaStream_t s;
-    explicit PhaseTimers(cudaStream_t s_) : s(s_) {}
-    ~PhaseTimers() { for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
-    size_t start(double *acc) {
-        Rec r; r.acc = acc;
-        OEM_CUDA(cudaEventCreate(&r.a)); OEM_CUDA(cudaEventCreate(&r.b));
-        OEM_CUDA(cudaEventRecord(r.a, s));
-        recs.push_back(r);
-        return recs.size() - 1;
-    }
-    void stop(size_t i) { OEM_CUDA(cudaEventRecord(recs[i].b, s)); }
-    void collect() {   // call after the stream is synchronized
-        for (auto &r : recs) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.acc) *r.acc += ms;
-        }
     }
 };
 
