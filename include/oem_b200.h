@@ -129,6 +129,11 @@ int  oemb200_device_count(void);
 void oemb200_default_opts(oemb200_opts *o);
 int  oemb200_penalty_id(const char *name);          /* -1 if unknown */
 int  oemb200_nlambda_max(const oemb200_spec *s);    /* L used to size the result buffers */
+/* Host-only helpers (no device needed): the lambda grid exp(LinSpaced(nl, log lmax, log(ratio*lmax)))
+ * of src/oem_dense.cpp:179-186, and stopRule of src/utils.cpp:537-549. */
+int  oemb200_lambda_grid(double lmax, int nlambda, double lambda_min_ratio, double *out);
+int  oemb200_stop_rule(const double *cur, const double *prev, int q, double tol);
+void oemb200_release_cache(void);                   /* free the calling thread's cached device buffers */
 
 /* src/oem_dense.cpp:30 -- x: n x p column-major (ldx >= n), y: n. */
 int oemb200_fit_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y,

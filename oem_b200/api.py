@@ -101,6 +101,9 @@ def load():
     L.oemb200_colstats.argtypes = [vp, i64, ci, i64, vp, vp, vp, vp, ctypes.POINTER(dbl)]
     L.oemb200_xb_logistic.argtypes = [vp, i64, ci, i64, vp, dbl, vp, vp, vp, vp, vp, ctypes.POINTER(dbl)]
     L.oemb200_top_eig.argtypes = [vp, ci, ctypes.POINTER(dbl), ctypes.POINTER(ci), vp]
+    L.oemb200_lambda_grid.argtypes = [dbl, ci, dbl, vp]
+    L.oemb200_stop_rule.argtypes = [vp, vp, ci, dbl]
+    L.oemb200_release_cache.restype = None
     _lib = L
     return L
 
@@ -108,7 +111,21 @@ def load():
 EXPORTS = ["oemb200_last_error", "oemb200_version", "oemb200_device_count", "oemb200_default_opts",
            "oemb200_penalty_id", "oemb200_nlambda_max", "oemb200_fit_dense", "oemb200_xtx", "oemb200_xval_dense",
            "oemb200_fit_logistic_dense", "oemb200_fit_big", "oemb200_gram", "oemb200_colstats",
-           "oemb200_xb_logistic", "oemb200_top_eig"]
+           "oemb200_xb_logistic", "oemb200_top_eig", "oemb200_lambda_grid", "oemb200_stop_rule",
+           "oemb200_release_cache"]
+
+
+def lambda_grid(lmax, nlambda, lmin_ratio):
+    """Host-side lambda grid of the library (src/oem_dense.cpp:179-186)."""
+    out = np.zeros(int(nlambda))
+    _check(load().oemb200_lambda_grid(float(lmax), int(nlambda), float(lmin_ratio), out.ctypes.data))
+    return out
+
+
+def stop_rule(cur, prev, tol):
+    cur = np.ascontiguousarray(cur, dtype=np.float64)
+    prev = np.ascontiguousarray(prev, dtype=np.float64)
+    return bool(load().oemb200_stop_rule(cur.ctypes.data, prev.ctypes.data, cur.size, float(tol)))
 
 
 def _check(rc):

@@ -450,6 +450,19 @@ int oemb200_nlambda_max(const oemb200_spec *s) {
     return s->nlambda;
 }
 
+int oemb200_lambda_grid(double lmax, int nlambda, double lambda_min_ratio, double *out) {
+    return guarded([&] {
+        if (nlambda < 1 || !out) fail(OEMB200_EINVAL, "lambda_grid: nlambda < 1 or NULL output");
+        const std::vector<double> v = lambda_base(lmax, nlambda, lambda_min_ratio);
+        memcpy(out, v.data(), sizeof(double) * v.size());
+    });
+}
+int oemb200_stop_rule(const double *cur, const double *prev, int q, double tol) {
+    std::vector<double> a(cur, cur + q), b(prev, prev + q);
+    return stop_rule_host(a, b, tol) ? 1 : 0;
+}
+void oemb200_release_cache(void) { pool_release_all(); }
+
 int oemb200_fit_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *spec,
                       const oemb200_opts *opts, oemb200_result *res) {
     return guarded([&] { fit_dense(x, n, p, ldx, y, spec, opts, res); });

@@ -1,0 +1,93 @@
+"""CPU tests of the boundary: the C-ABI library builds (nvcc cross-compiles sm_100a without a GPU), loads,
+exports every symbol include/oem_b200.h declares, has no dependency on the oracle, and its compute entries
+fail loudly (OEMB200_ENODEVICE) instead of falling back to a CPU path when no device is present."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from cases import args_xy, gaussian_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    h = open(os.path.join(ROOT, "include", "oem_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(oemb200_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    L = lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/oem_b200.h but not exported"
+    assert set(lib.EXPORTS) == set(syms)
+    nm = subprocess.run(["nm", "-D", "--defined-only", lib.lib_path()], capture_output=True, text=True).stdout
+    for s in syms:
+        assert re.search(rf"\bT {s}\b", nm), s
+
+
+def test_product_does_not_touch_the_oracle(lib):
+    # the product library and package must not link, load or import anything under oracle/
+    ldd = subprocess.run(["ldd", lib.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "oem_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "liboem_oracle" not in src and "oem_oracle.c" not in src, f
+
+
+def test_sass_has_fp64_tensor_and_tma(lib):
+    # the Gram kernel must be the FP64 tensor-core path staged by TMA: DMMA + UTMALDG in the sm_100a SASS
+    out = subprocess.run(["cuobjdump", "-sass", lib.lib_path()], capture_output=True, text=True).stdout
+    assert "DMMA.8x8x4" in out and "UTMALDG" in out
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", lib.lib_path()], capture_output=True, text=True).stdout
+
+
+def test_host_helpers_match_oracle_bit_for_bit(lib, oracle):
+    from oem_b200 import api
+    for lmax, nl, r in [(0.731, 100, 1e-4), (12.5, 7, 1e-2), (3e-3, 200, 1e-4), (1.0, 1, 0.5)]:
+        assert np.array_equal(api.lambda_grid(lmax, nl, r), oracle.lambda_base(lmax, nl, r))
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        a = rng.normal(size=6) * (rng.uniform(size=6) > 0.3)
+        b = a * (1 + rng.normal(size=6) * 10 ** rng.uniform(-9, -5)) * (rng.uniform(size=6) > 0.05)
+        tol = 10 ** rng.uniform(-9, -5)
+        assert api.stop_rule(a, b, tol) == oracle.stop_rule(a, b, tol)
+    L = lib.load()
+    names = ["lasso", "ols", "elastic.net", "scad", "scad.net", "mcp", "mcp.net", "grp.lasso", "grp.lasso.net",
+             "grp.mcp", "grp.scad", "grp.mcp.net", "grp.scad.net", "sparse.grp.lasso"]
+    assert [L.oemb200_penalty_id(n.encode()) for n in names] == [oracle.PEN_ID[n] for n in names]
+    assert L.oemb200_penalty_id(b"ridge") == -1
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the no-device behaviour is checked on the CPU box")
+    X, y = gaussian_problem(1, 200, 5)
+    a = args_xy(X, y, "gaussian", ["lasso"])
+    for fn in (lib.oem_fit_dense, lib.oem_fit_big):
+        with pytest.raises(lib.OemB200Error) as ei:
+            fn(*a)
+        assert ei.value.code == 2 and "no CPU fallback" in str(ei.value)
+    with pytest.raises(lib.OemB200Error) as ei:
+        lib.oem_xtx(np.eye(5), np.ones(5), "gaussian", ["lasso"], [], [], [], [], 10, 1e-2, 1.0, 3.0, 0.5, [], np.ones(5), {})
+    assert ei.value.code == 2
+
+
+def test_argument_validation_precedes_device_use(lib):
+    from oem_b200 import api
+    X, y = gaussian_problem(1, 50, 4)
+    with pytest.raises(ValueError):
+        lib.oem_fit_dense(*args_xy(X, y[:-1], "gaussian", ["lasso"]))
+    with pytest.raises(ValueError):
+        api.make_opts({"no_such_option": 1})
+    o = api.make_opts({"maxit": 10, "tol": 1e-9, "hessian.type": "full", "irls.maxit": 7})
+    assert (o.maxit, o.tol, o.hessian_full, o.irls_maxit) == (10, 1e-9, 1, 7)
