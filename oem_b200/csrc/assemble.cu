@@ -15,7 +15,7 @@ namespace oemb200 {
 
 // out o uses all parts except part (o-1) (o = 0: all parts).  One thread per element of XX.
 __global__ void assemble_aug_kernel(int p, int intercept, int standardize, int nparts, const double *__restrict__ G,
-                                    const double *__restrict__ stats, const double *__restrict__ ysum,
+                                    const double *__restrict__ stats, const double *__restrict__ ysum, int ysum_stride,
                                     const double *__restrict__ corner, const double *__restrict__ nobs,
                                     double *__restrict__ XX, double *__restrict__ XY, double *__restrict__ colsq_inv,
                                     double *__restrict__ nobs_out) {
@@ -62,7 +62,7 @@ __global__ void assemble_aug_kernel(int p, int intercept, int standardize, int n
             double b = 0.0;
             if (xr < 0) {
                 for (int k = 0; k < nparts; ++k)
-                    if (k != skip) b += ysum[k];
+                    if (k != skip) b += ysum[(size_t)k * ysum_stride];
             } else {
                 for (int k = 0; k < nparts; ++k)
                     if (k != skip) b += stats[((size_t)k * 3 + 1) * p + xr];
@@ -76,12 +76,12 @@ __global__ void assemble_aug_kernel(int p, int intercept, int standardize, int n
 }
 
 void assemble_aug_launch(Ctx &cx, int p, int intercept, int standardize, int nparts, int nout, const double *G_parts,
-                         const double *stats_parts, const double *ysum_parts, const double *corner_parts,
+                         const double *stats_parts, const double *ysum_parts, int ysum_stride, const double *corner_parts,
                          const double *nobs_parts, double *XX, double *XY, double *colsq_inv, double *nobs_out) {
     const int q = p + intercept;
     dim3 grid((unsigned)(((long long)q * q + 255) / 256), nout);
     assemble_aug_kernel<<<grid, 256, 0, cx.stream>>>(p, intercept, standardize, nparts, G_parts, stats_parts,
-                                                    ysum_parts, corner_parts, nobs_parts, XX, XY, colsq_inv, nobs_out);
+                                                    ysum_parts, ysum_stride, corner_parts, nobs_parts, XX, XY, colsq_inv, nobs_out);
     OEM_CUDA(cudaGetLastError());
     cx.st.kernel_launches += 1;
 }

@@ -1,0 +1,350 @@
+// cvscore.cu -- the second data pass of xval.oem: out-of-fold prediction errors for every
+// (penalty, lambda) column with running mean / M2, without materialising the n x (P*L) predictions.
+//
+// Replaces the CV-scoring loop of oem_xval_dense (src/oem_xval_dense.cpp:345-464):
+//     for each row i:  pred = x_i . B_fold(i)[1:, :] + B_fold(i)[0, :];  t = (y_i - pred)^2  or |y_i - pred|
+//     Welford over i:  cvm = mean(t),  cvsd = sqrt(M2 / (n-1)) / sqrt(n)
+// As a GEMM:  T(rows x NC) = X_k (rows x p) * B_k (p x NC)  per fold segment k (rows are fold-sorted by
+// fold_gather_kernel), on the FP64 tensor pipe (DMMA.8x8x4) with both operands staged by TMA:
+//   X box  [68 rows x 20 cols]  (64 used; the 4 extra rows make the k-stride 68 = 4 mod 16: conflict-free)
+//   B box  2 x [164 cols x 20 rows] (160 used each, stride 164 = 4 mod 16)
+// CTA tile = 64 rows x 320 columns, 8 warps as 2 x 4 with 32 x 80 warp tiles (80 accumulator doubles per
+// thread).  A CTA walks a contiguous range of row tiles of one fold and keeps (count, mean, M2) per column
+// with Chan's pairwise update, so one partial per CTA reaches the fixed-order final merge.
+#include <algorithm>
+#include <array>
+#include "runtime.h"
+
+namespace oemb200 {
+
+constexpr int CV_ROWS = 64;
+constexpr int CV_XBOX = 68;
+constexpr int CV_KC = 20;
+constexpr int CV_KSTEPS = CV_KC / 4;
+constexpr int CV_COLS = 320;
+constexpr int CV_BHALF = 160;
+constexpr int CV_BBOX = 164;
+constexpr int CV_STAGES = 3;
+constexpr int CV_THREADS = 256;
+constexpr int CV_X_BYTES = CV_KC * CV_XBOX * 8;                 // 10880
+constexpr int CV_B_BYTES = CV_KC * CV_BBOX * 8;                 // 26240
+constexpr int CV_STAGE_BYTES = CV_X_BYTES + 2 * CV_B_BYTES;     // 63360
+constexpr int CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 128 + (2 * 2 * CV_COLS + 2 * CV_COLS + CV_ROWS + 8) * 8;
+
+struct CvItem {
+    int fold, colblock, pad0, pad1;
+    long long row0;       // first row of the item in the fold-sorted matrix (multiple of 64 from the segment start)
+    long long row_end;    // end of the item's rows (exclusive)
+    long long valid_end;  // rows >= valid_end are padding
+};
+
+// scatter rows into fold-sorted order: Xs[dest[i], j] = X[i, j]
+__global__ void __launch_bounds__(256)
+fold_gather_kernel(const double *__restrict__ X, long long n, int p, long long ld, const int *__restrict__ dest,
+                   double *__restrict__ Xs, long long lds, const double *__restrict__ y, double *__restrict__ ys) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const long long d = dest[i];
+    const int j0 = blockIdx.y * 32;
+    const int j1 = min(p, j0 + 32);
+    for (int j = j0; j < j1; ++j) Xs[(size_t)j * lds + d] = X[(size_t)j * ld + i];
+    if (blockIdx.y == 0 && y) ys[d] = y[i];
+}
+
+void fold_gather_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const int *dest, double *Xs,
+                        int64_t lds, const double *y, double *ys) {
+    dim3 grid((unsigned)((n + 255) / 256), (p + 31) / 32);
+    fold_gather_kernel<<<grid, 256, 0, cx.stream>>>(X, n, p, ld, dest, Xs, lds, y, ys);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+}
+
+template <bool MAE>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, int p, int ncld,
+               const CvItem *__restrict__ items, const double *__restrict__ ys, const double *__restrict__ b0,
+               double *__restrict__ partial, int part_stride) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + CV_STAGES * CV_STAGE_BYTES);
+    uint64_t *empty = full + CV_STAGES;
+    double *red = reinterpret_cast<double *>(smem_raw + CV_STAGES * CV_STAGE_BYTES + 128);   // [2][2][CV_COLS]
+    double *run_mean = red + 2 * 2 * CV_COLS;     // [CV_COLS]
+    double *run_m2 = run_mean + CV_COLS;          // [CV_COLS]
+    double *ytile = run_m2 + CV_COLS;             // [CV_ROWS]
+
+    const CvItem it = items[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int nkt = (p + CV_KC - 1) / CV_KC;
+    const int ntiles = (int)((it.row_end - it.row0 + CV_ROWS - 1) / CV_ROWS);
+    const long long total = (long long)ntiles * nkt;
+    const int col0 = it.colblock * CV_COLS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CV_THREADS / 32); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmB);
+    }
+    for (int c = threadIdx.x; c < CV_COLS; c += CV_THREADS) { run_mean[c] = 0.0; run_m2[c] = 0.0; }
+    __syncthreads();
+
+    auto issue = [&](long long idx) {      // thread 0 only
+        const int s = (int)(idx % CV_STAGES);
+        const int tile = (int)(idx / nkt), kt = (int)(idx - (long long)tile * nkt);
+        unsigned char *base = smem_raw + (size_t)s * CV_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], CV_STAGE_BYTES);
+        tma_load_2d(base, &tmX, &full[s], (int)(it.row0 + (long long)tile * CV_ROWS), kt * CV_KC);
+        tma_load_2d(base + CV_X_BYTES, &tmB, &full[s], col0, it.fold * p + kt * CV_KC);
+        tma_load_2d(base + CV_X_BYTES + CV_B_BYTES, &tmB, &full[s], col0 + CV_BHALF, it.fold * p + kt * CV_KC);
+    };
+    if (threadIdx.x == 0)
+        for (long long i = 0; i < CV_STAGES && i < total; ++i) issue(i);
+
+    const int offA = wm * 32 + g;                         // + ma*8 + (k)*CV_XBOX
+    const int offB = (wn & 1) * 80 + g;                   // + na*8 + (k)*CV_BBOX, box = wn >> 1
+    double run_cnt = 0.0;
+
+    long long idx = 0;
+    for (int tile = 0; tile < ntiles; ++tile) {
+        double acc[4][10][2];
+#pragma unroll
+        for (int ma = 0; ma < 4; ++ma)
+#pragma unroll
+            for (int na = 0; na < 10; ++na) acc[ma][na][0] = acc[ma][na][1] = 0.0;
+        const long long trow0 = it.row0 + (long long)tile * CV_ROWS;
+        if (threadIdx.x < CV_ROWS) {
+            const long long r = trow0 + threadIdx.x;
+            ytile[threadIdx.x] = r < it.valid_end ? ys[r] : 0.0;
+        }
+        for (int kt = 0; kt < nkt; ++kt, ++idx) {
+            const int s = (int)(idx % CV_STAGES);
+            const uint32_t ph = (uint32_t)((idx / CV_STAGES) & 1);
+            mbar_wait(&full[s], ph);
+            const double *xs = reinterpret_cast<const double *>(smem_raw + (size_t)s * CV_STAGE_BYTES);
+            const double *bs = xs + CV_KC * CV_XBOX + (wn >> 1) * (CV_KC * CV_BBOX);
+#pragma unroll
+            for (int ks = 0; ks < CV_KSTEPS; ++ks) {
+                double a[4], b[10];
+                const int k = ks * 4 + t;
+#pragma unroll
+                for (int ma = 0; ma < 4; ++ma) a[ma] = xs[k * CV_XBOX + offA + ma * 8];
+#pragma unroll
+                for (int na = 0; na < 10; ++na) b[na] = bs[k * CV_BBOX + offB + na * 8];
+#pragma unroll
+                for (int ma = 0; ma < 4; ++ma)
+#pragma unroll
+                    for (int na = 0; na < 10; ++na) dmma884(acc[ma][na][0], acc[ma][na][1], a[ma], b[na]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (threadIdx.x == 0 && idx + CV_STAGES < total) {
+                mbar_wait(&empty[s], ph);
+                issue(idx + CV_STAGES);
+            }
+        }
+        // ---------------- epilogue: t = measure(y - b0 - pred), tile (count, mean, M2) per column ----------------
+        __syncthreads();     // ytile visible
+        const int cbase = (wn >> 1) * CV_BHALF + (wn & 1) * 80 + 2 * t;      // + na*8 + {0,1}
+        double s1[20];
+#pragma unroll
+        for (int c = 0; c < 20; ++c) s1[c] = 0.0;
+#pragma unroll
+        for (int ma = 0; ma < 4; ++ma) {
+            const int rl = wm * 32 + ma * 8 + g;
+            const bool valid = (trow0 + rl) < it.valid_end;
+            const double yv = ytile[rl];
+#pragma unroll
+            for (int na = 0; na < 10; ++na)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = cbase + na * 8 + h;
+                    const double r = yv - (acc[ma][na][h] + __ldg(b0 + (size_t)it.fold * ncld + col0 + c));
+                    const double tv = valid ? (MAE ? fabs(r) : r * r) : 0.0;
+                    acc[ma][na][h] = tv;
+                    s1[na * 2 + h] += tv;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 20; ++c) {
+            double v = s1[c];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            s1[c] = v;
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int na = 0; na < 10; ++na)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) red[(0 * 2 + wm) * CV_COLS + cbase + na * 8 + h] = s1[na * 2 + h];
+        }
+        __syncthreads();
+        const double cnt = (double)max(0ll, min((long long)CV_ROWS, it.valid_end - trow0));
+        double m2[20];
+#pragma unroll
+        for (int c = 0; c < 20; ++c) m2[c] = 0.0;
+        if (cnt > 0.0) {
+#pragma unroll
+            for (int na = 0; na < 10; ++na)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = cbase + na * 8 + h;
+                    const double mean = (red[c] + red[CV_COLS + c]) / cnt;
+#pragma unroll
+                    for (int ma = 0; ma < 4; ++ma) {
+                        const bool valid = (trow0 + wm * 32 + ma * 8 + g) < it.valid_end;
+                        const double dlt = acc[ma][na][h] - mean;
+                        m2[na * 2 + h] += valid ? dlt * dlt : 0.0;
+                    }
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 20; ++c) {
+            double v = m2[c];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            m2[c] = v;
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int na = 0; na < 10; ++na)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) red[(1 * 2 + wm) * CV_COLS + cbase + na * 8 + h] = m2[na * 2 + h];
+        }
+        __syncthreads();
+        // Chan merge of the tile into the running state, one thread per column
+        if (cnt > 0.0) {
+            for (int c = threadIdx.x; c < CV_COLS; c += CV_THREADS) {
+                const double tmean = (red[c] + red[CV_COLS + c]) / cnt;
+                const double tm2 = red[2 * CV_COLS + c] + red[3 * CV_COLS + c];
+                const double ntot = run_cnt + cnt;
+                const double dlt = tmean - run_mean[c];
+                run_mean[c] += dlt * (cnt / ntot);
+                run_m2[c] += tm2 + dlt * dlt * (run_cnt * cnt / ntot);
+            }
+        }
+        run_cnt += cnt;
+        __syncthreads();
+    }
+    double *out = partial + (size_t)blockIdx.x * part_stride;
+    if (threadIdx.x == 0) out[0] = run_cnt;
+    for (int c = threadIdx.x; c < CV_COLS; c += CV_THREADS) {
+        out[1 + 2 * c] = run_mean[c];
+        out[2 + 2 * c] = run_m2[c];
+    }
+}
+
+// out[c] = (count, mean, M2) merged over this column block's items in item order
+__global__ void cv_merge_kernel(const double *__restrict__ partial, int part_stride, const CvItem *__restrict__ items,
+                                int nitems, int nc, double *__restrict__ out3) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const int cb = c / CV_COLS, cl = c - cb * CV_COLS;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int i = 0; i < nitems; ++i) {
+        if (items[i].colblock != cb) continue;
+        const double *pp = partial + (size_t)i * part_stride;
+        const double nb = pp[0];
+        if (nb <= 0.0) continue;
+        const double mb = pp[1 + 2 * cl], qb = pp[2 + 2 * cl];
+        const double nt = n + nb, dlt = mb - mean;
+        mean += dlt * (nb / nt);
+        m2 += qb + dlt * dlt * (n * nb / nt);
+        n = nt;
+    }
+    out3[c] = n;
+    out3[nc + c] = mean;
+    out3[2 * nc + c] = m2;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        fail(OEMB200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    return reinterpret_cast<EncodeTiledFn>(p);
+}
+
+int cv_ncld(int nc) { return (nc + CV_COLS - 1) / CV_COLS * CV_COLS + 8; }
+
+// Xs: fold-sorted, column-major, leading dimension lds (even), nrows_total rows.  B: nfolds x p x ncld (column index
+// contiguous), b0: nfolds x ncld.  segs[k] = {row0, padded end, valid end}.  out3: 3 x nc (count, mean, M2).
+void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys, int nfolds,
+                    const std::vector<std::array<int64_t, 3>> &segs, const double *B, const double *b0, int nc,
+                    bool mae, double *out3) {
+    const int ncld = cv_ncld(nc);
+    const int ncb = (nc + CV_COLS - 1) / CV_COLS;
+    if ((lds & 1) || (reinterpret_cast<uintptr_t>(Xs) & 15))
+        fail(OEMB200_EINVAL, "cvscore: fold-sorted X must have an even leading dimension and a 16-byte aligned base");
+    // items: contiguous ranges of 64-row tiles, a few waves of CTAs
+    int64_t tiles_total = 0;
+    for (auto &s : segs) tiles_total += (s[2] - s[0] + CV_ROWS - 1) / CV_ROWS;
+    const int64_t target = std::max<int64_t>(1, (int64_t)cx.num_sms * 4 / ncb);
+    const int64_t tiles_per_item = std::max<int64_t>(1, (tiles_total + target - 1) / target);
+    std::vector<CvItem> items;
+    for (int cb = 0; cb < ncb; ++cb)
+        for (int k = 0; k < nfolds; ++k) {
+            const int64_t nt = (segs[k][2] - segs[k][0] + CV_ROWS - 1) / CV_ROWS;
+            for (int64_t t0 = 0; t0 < nt; t0 += tiles_per_item) {
+                CvItem it;
+                it.fold = k; it.colblock = cb; it.pad0 = it.pad1 = 0;
+                it.row0 = segs[k][0] + t0 * CV_ROWS;
+                it.row_end = segs[k][0] + std::min(nt, t0 + tiles_per_item) * CV_ROWS;
+                it.valid_end = segs[k][2];
+                items.push_back(it);
+            }
+        }
+    if (items.empty()) fail(OEMB200_EINVAL, "cvscore: no rows");
+    const int part_stride = 1 + 2 * CV_COLS;
+    DBuf<CvItem> d_items(items.size());
+    DBuf<double> partial(items.size() * (size_t)part_stride);
+    d_items.upload(items.data(), items.size(), cx.stream);
+
+    CUtensorMap tmX, tmB;
+    EncodeTiledFn enc = encode_fn();
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)nrows_total, (cuuint64_t)p};
+        cuuint64_t strides[1] = {(cuuint64_t)lds * 8};
+        cuuint32_t box[2] = {CV_XBOX, CV_KC};
+        cuuint32_t es[2] = {1, 1};
+        if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(Xs), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            fail(OEMB200_ECUDA, "cvscore: tensor map for X failed");
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)ncld, (cuuint64_t)nfolds * p};
+        cuuint64_t strides[1] = {(cuuint64_t)ncld * 8};
+        cuuint32_t box[2] = {CV_BBOX, CV_KC};
+        cuuint32_t es[2] = {1, 1};
+        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(B), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            fail(OEMB200_ECUDA, "cvscore: tensor map for B failed");
+    }
+    const size_t t0 = cx.tm->start(&cx.st.ms_cvscore);
+    if (mae) {
+        OEM_CUDA(cudaFuncSetAttribute(cvscore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+        cvscore_kernel<true><<<(unsigned)items.size(), CV_THREADS, CV_SMEM_BYTES, cx.stream>>>(
+            tmX, tmB, p, ncld, d_items.p, ys, b0, partial.p, part_stride);
+    } else {
+        OEM_CUDA(cudaFuncSetAttribute(cvscore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+        cvscore_kernel<false><<<(unsigned)items.size(), CV_THREADS, CV_SMEM_BYTES, cx.stream>>>(
+            tmX, tmB, p, ncld, d_items.p, ys, b0, partial.p, part_stride);
+    }
+    OEM_CUDA(cudaGetLastError());
+    cv_merge_kernel<<<(nc + 127) / 128, 128, 0, cx.stream>>>(partial.p, part_stride, d_items.p, (int)items.size(), nc, out3);
+    OEM_CUDA(cudaGetLastError());
+    cx.tm->stop(t0);
+    cx.st.kernel_launches += 2;
+}
+
+}  // namespace oemb200

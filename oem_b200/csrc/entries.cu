@@ -162,7 +162,7 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
     const size_t t_as = tm.start(&cx.st.ms_assemble);
     DBuf<double> XX((size_t)q * q), XY(q), cinv(p);
     // corner = n (XX(0,0) = nobs, src/oem_big.h:527), divisor = n
-    assemble_aug_launch(cx, p, icpt, s->standardize ? 1 : 0, 1, 1, G, stats, ysum, nobs, nobs, XX.p, XY.p, cinv.p, nullptr);
+    assemble_aug_launch(cx, p, icpt, s->standardize ? 1 : 0, 1, 1, G, stats, ysum, 1, nobs, nobs, XX.p, XY.p, cinv.p, nullptr);
     std::vector<double> hXY(q), hcinv(p);
     XY.download(hXY.data(), q, cx.stream);
     cinv.download(hcinv.data(), p, cx.stream);

@@ -157,7 +157,7 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                         // assemble_aug derives w from stats row 2, so put sum x^2 there
                         OEM_CUDA(cudaMemcpyAsync(st + 2 * (size_t)p, stats0 + 2 * (size_t)p, (size_t)p * 8,
                                                  cudaMemcpyDeviceToDevice, cx.stream));
-                        assemble_aug_launch(cx, p, icpt, stdz ? 1 : 0, 1, 1, G, st, ws, ws, d_nobs.p, d_XX.p, nullptr,
+                        assemble_aug_launch(cx, p, icpt, stdz ? 1 : 0, 1, 1, G, st, ws, 1, ws, d_nobs.p, d_XX.p, nullptr,
                                             nullptr, nullptr);
                         rebuilt = true;
                     }

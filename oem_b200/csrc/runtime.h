@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <array>
 #include <vector>
 #include "../../include/oem_b200.h"
 #include "common.cuh"
@@ -166,7 +167,8 @@ void path_launch(Ctx &cx, const PathProblem &pp);
 // Output o sums all parts except part o-1 (o = 0: all).  XY / colsq_inv / nobs_out may be NULL.
 void assemble_aug_launch(Ctx &cx, int p, int intercept, int standardize, int nparts, int nout,
                          const double *G_parts /*nparts x p x p*/, const double *stats_parts /*nparts x 3 x p*/,
-                         const double *ysum_parts /*nparts*/, const double *corner_parts /*nparts*/,
+                         const double *ysum_parts /*nparts, stride ysum_stride*/, int ysum_stride,
+                         const double *corner_parts /*nparts*/,
                          const double *nobs_parts /*nparts*/, double *XX /*nout x q x q*/, double *XY /*nout x q*/,
                          double *colsq_inv /*nout x p*/, double *nobs_out /*nout*/);
 // oem_dense convention: G is the Gram of centred (flag 2,3) or raw (flag 0,1) columns
@@ -177,5 +179,14 @@ void scale_sym_launch(Ctx &cx, int p, const double *sinv, const double *XXin, co
                       double *XY);
 // y = M x + add for a symmetric q x q M
 void symv_add_launch(Ctx &cx, int q, const double *M, const double *x, const double *add, double *y);
+
+// ---------------- cvscore.cu ----------------
+void fold_gather_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const int *dest, double *Xs,
+                        int64_t lds, const double *y, double *ys);
+int cv_ncld(int nc);     // leading dimension (columns) of the coefficient matrices handed to cvscore_launch
+// out3 = 3 x nc: (count, mean, M2) of t = (y - pred)^2 | |y - pred| over all valid rows, per column
+void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys, int nfolds,
+                    const std::vector<std::array<int64_t, 3>> &segs, const double *B, const double *b0, int nc,
+                    bool mae, double *out3);
 
 }  // namespace oemb200

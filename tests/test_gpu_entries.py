@@ -134,3 +134,55 @@ def test_errors_mirror_reference(lib):
     a = args_xy(X, y, "gaussian", ["nope"])
     with pytest.raises(lib.OemB200Error, match="unknown penalty"):
         lib.oem_fit_big(*a)
+
+
+def xval_args(X, y, penalty, foldid, nfolds, **kw):
+    tm = kw.pop("type_measure", "mse")
+    cl = kw.get("compute_loss", False)
+    a = args_xy(X, y, "gaussian", penalty, **kw)
+    return a[:17] + [nfolds, foldid, cl, tm, a[18]]
+
+
+@pytest.mark.parametrize("standardize,intercept,measure", [(True, True, "mse"), (False, True, "mae"), (True, False, "mse")])
+def test_xval(lib, oracle, standardize, intercept, measure):
+    # BASELINE config 3 shape at n = 6000: lasso + grp.lasso + mcp, 10 folds, fold Grams in one pass
+    X, y = gaussian_problem(103, 6000, 50, coef="vignette", noise=4.0)
+    rng = np.random.default_rng(103)
+    foldid = 1 + rng.permutation(6000) % 10
+    g = np.repeat(np.arange(1, 11), 5)
+    groups = np.concatenate([[0], g]) if intercept else g
+    a = xval_args(X, y, ["lasso", "grp.lasso", "mcp"], foldid, 10, groups=groups, unique_groups=np.unique(groups),
+                  nlambda=30, standardize=standardize, intercept=intercept, type_measure=measure, compute_loss=True)
+    got, ref = lib.oem_xval_dense(*a), oracle.oem_xval_dense(*a)
+    assert_same_fit(got, ref)
+    for pp in range(3):
+        assert np.allclose(got["cvm"][pp], ref["cvm"][pp], rtol=1e-9, atol=0)
+        assert np.allclose(got["cvsd"][pp], ref["cvsd"][pp], rtol=1e-8, atol=0)
+        assert np.allclose(got["loss"][pp], ref["loss"][pp], rtol=1e-9)
+
+
+def test_xval_many_columns_uneven_folds(lib, oracle):
+    # more than 320 (penalty x lambda) columns -> two column blocks in the scoring GEMM; ragged folds; odd n
+    X, y = gaussian_problem(9, 2501, 23, noise=2.0)
+    rng = np.random.default_rng(9)
+    foldid = rng.choice([1, 2, 3], size=2501, p=[0.6, 0.3, 0.1])
+    a = xval_args(X, y, ["lasso", "scad", "mcp", "elastic.net"], foldid, 3, nlambda=90, alpha=0.5)
+    got, ref = lib.oem_xval_dense(*a), oracle.oem_xval_dense(*a)
+    assert_same_fit(got, ref)
+    for pp in range(4):
+        assert np.allclose(got["cvm"][pp], ref["cvm"][pp], rtol=1e-9)
+        assert np.allclose(got["cvsd"][pp], ref["cvsd"][pp], rtol=1e-8)
+
+
+def test_golden_on_gpu(lib):
+    import json, os
+    from golden.make_golden import CASES, run_case
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_oracle.json")))
+    for name in CASES:
+        got, ref = run_case(lib, name), gold[name]
+        assert np.allclose(got["d"], ref["d"], rtol=1e-9), name
+        for pp in range(len(ref["beta_checksum"])):
+            assert np.allclose(got["beta_checksum"][pp], ref["beta_checksum"][pp], rtol=0, atol=2e-7), name
+        if "cvm_checksum" in ref:
+            assert np.allclose(got["cvm_checksum"], ref["cvm_checksum"], rtol=1e-9), name
+            assert np.allclose(got["cvsd_checksum"], ref["cvsd_checksum"], rtol=1e-8), name
