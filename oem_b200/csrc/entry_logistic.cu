@@ -192,6 +192,7 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                 pr.chains.push_back(c);
                 pr.lambdas = d_lam.p; pr.Lmax = 1; pr.pen_fact = d_pf.p;
                 pr.ngroups = su.any_group ? (int)su.unique.size() : 0;
+                pr.ngidx = su.any_group ? (int)su.idx.size() : 0;
                 pr.unique_groups = g_unique.p; pr.grp_ptr = g_ptr.p; pr.grp_idx = g_idx.p;
                 pr.group_weights = g_w.p; pr.grp_cover = g_cover.p;
                 pr.beta_init = d_beta.p; pr.beta_final = d_beta_final.p;

@@ -172,6 +172,7 @@ void run_paths(Ctx &cx, const Setup &su, const oemb200_opts *o, int q, int ngram
         }
     pp.lambdas = pb.lambdas.p; pp.Lmax = L; pp.pen_fact = pb.pen_fact.p;
     pp.ngroups = su.any_group ? (int)su.unique.size() : 0;
+    pp.ngidx = su.any_group ? (int)su.idx.size() : 0;
     pp.unique_groups = pb.unique.p; pp.grp_ptr = pb.ptr.p; pp.grp_idx = pb.idx.p;
     pp.group_weights = pb.gw.p; pp.grp_cover = pb.cover.p;
     pp.post_scale = post_scale_dev;

@@ -1,4 +1,4 @@
-// path_kernel.cu -- everything after the Gram, in ONE persistent cooperative kernel:
+// path_kernel.cu -- everything after the Gram, in ONE persistent kernel:
 //   * top eigenvalue of XX by Lanczos  -> d = factor * lambda_max      (stands in for the
 //     Spectra::SymEigsSolver call sites: src/oem_dense.h:485-498, oem_xtx.h:357-369,
 //     oem_xval_dense.h:770-782,837-843, oem_logistic_dense.h:501-514, oem_big.h:546-559)
@@ -15,22 +15,36 @@
 // (A is symmetric, so a column slice is a row slice) which it keeps in SHARED MEMORY for the whole
 // path whenever it fits (148 x ~200 KB covers q = 1001 with room to spare); otherwise the slice
 // is streamed from L2.  Each OEM iteration is
-//     u[slice] = A[:,slice]' beta + XY[slice]   for all of the team's chains at once (the GEMV
-//                                               becomes a skinny GEMM: A is read once per iteration)
-//     exchange u through an L2-resident buffer + ONE team barrier
+//     u[slice] = A[:,slice]' beta + XY[slice]   for all of the team's chains at once: a skinny GEMM
+//                                               (columns x chains x q) on the FP64 TENSOR pipe
+//                                               (DMMA.8x8x4; measured on B200 the FP64 CUDA-core
+//                                               rate is ~1/4 of the DMMA rate, so even this small
+//                                               product belongs on the tensor pipe)
+//     ONE exchange of u + ONE team barrier
 //     every member redundantly applies the prox and the stop rule to the full vector
 // All members execute bit-identical arithmetic on identical inputs, so they take the same
 // convergence decisions without any further communication.  Reductions use fixed orders.
+// Three exchange modes, chosen on the host from q:
+//     MODE_SINGLE   the whole A fits one CTA: u goes straight into shared memory, __syncthreads only
+//     MODE_CLUSTER  A fits the shared memory of a thread-block cluster (<= 8 CTAs): every member stores
+//                   its u slice into all members' shared memory (DSMEM, st.shared::cluster) and the
+//                   barrier is the hardware cluster barrier
+//     MODE_GLOBAL   larger q: u goes through an L2-resident buffer, barrier = one atomic counter per team
+// Everything an iteration needs besides u (chain descriptors, lambdas, penalty factors, XY, group
+// tables) is copied to shared memory once: the gpu-scope synchronisation of the barrier invalidates
+// L1, so any per-iteration global read would be an L2 round trip on the critical path.  The prox
+// and the stop rule avoid FP64-pipe work for the (many) coordinates that are and stay zero.
 #include <algorithm>
+#include <cstdlib>
 #include "runtime.h"
 
 namespace oemb200 {
 
 constexpr int PK_THREADS = 256;
 constexpr int PK_WARPS = PK_THREADS / 32;
-constexpr int PK_CB = 4;          // chains per register batch in the mat-vec
-constexpr int LZ_MAX = 768;       // Lanczos step cap
+constexpr int LZ_MAX = 512;       // Lanczos step cap
 constexpr int PK_MAXCT = 32;      // chains per team cap
+constexpr int PK_PART = 8;        // partial 8x8 tiles kept in shared memory for the split-K mat-vec (<= 1 per warp)
 
 struct ChainDev {
     int gram, penalty, nlam, lam_off;
@@ -38,8 +52,11 @@ struct ChainDev {
     int out_off, pad;
 };
 
+enum { MODE_SINGLE = 0, MODE_CLUSTER = 1, MODE_GLOBAL = 2 };
+
 struct PathArgs {
-    int q, ngram, team_size, cpc, max_ct, Lmax, maxit, accelerate, compute_eig, a_in_smem, ngroups, pad0;
+    int q, qs, ngram, team_size, cpc, cpc_pad, max_ct, Lmax, maxit, accelerate, compute_eig, a_in_smem, ngroups, mode;
+    int ngidx, pad1;
     double tol, eig_factor, eig_tol;
     const double *XX, *XY;
     double *d, *Abuf;
@@ -52,6 +69,7 @@ struct PathArgs {
     int *niter_out, *lanczos_steps;
     double *ubuf;            // ngram x 2 x max_ct x q
     unsigned *barriers;      // ngram counters, zero-initialised
+    long long *prof;         // optional (debug): cycle counters of CTA 0 / thread 0
 };
 
 __device__ __forceinline__ double pk_warp_sum(double v) {
@@ -72,21 +90,61 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     return s;
 }
 
+// One arrival counter per team.  bar.sync orders the CTA's writes before thread 0's gpu-scope
+// release; the acquire poll + bar.sync makes the other members' writes visible to the whole CTA.
 __device__ __forceinline__ void team_barrier(unsigned *ctr, unsigned &target, int team_size) {
     __syncthreads();
     if (team_size > 1) {
         if (threadIdx.x == 0) {
             target += (unsigned)team_size;
-            __threadfence();
-            atomicAdd(ctr, 1u);
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
             unsigned v;
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             } while ((int)(v - target) < 0);
-            __threadfence();
         }
         __syncthreads();
     }
+}
+
+// |x| > thr for thr >= 0, on the integer pipe (IEEE-754 ordering of non-negative doubles)
+__device__ __forceinline__ bool abs_gt(double x, double thr) {
+    return (__double_as_longlong(x) & 0x7fffffffffffffffLL) > __double_as_longlong(thr);
+}
+
+// x / d given r = 1/d (correctly rounded): q0 = x r, residual by FMA, one correction (Markstein).  Gives the
+// IEEE quotient with 3 dependent FP64 operations instead of the ~30 of a full division -- on this part the
+// FP64 CUDA-core pipe is slow enough that the divisions of the few non-zero coefficients were the critical
+// path of every iteration.
+__device__ __forceinline__ double div_r(double x, double d, double r) {
+    const double q0 = x * r;
+    const double e = fma(-d, q0, x);
+    return fma(e, r, q0);
+}
+// same rules as st_lasso / st_mcp / st_scad below, with the reciprocals of the denominators precomputed
+__device__ __forceinline__ double st_lasso_r(double v, double pen, double d, double rd) {
+    if (v > pen) return div_r(v - pen, d, rd);
+    if (v < -pen) return div_r(v + pen, d, rd);
+    return 0.0;
+}
+__device__ __forceinline__ double st_mcp_r(double v, double pen, double d, double rd, double gammad, double dmg, double rdmg) {
+    if (fabs(v) > gammad * pen) return div_r(v, d, rd);
+    if (v > pen) return div_r(v - pen, dmg, rdmg);
+    if (v < -pen) return div_r(v + pen, dmg, rdmg);
+    return 0.0;
+}
+__device__ __forceinline__ double st_scad_r(double v, double pen, double d, double rd, double gamma, double gammad, double den2,
+                                            double rden2) {
+    if (fabs(v) > gammad * pen) return div_r(v, d, rd);
+    if (fabs(v) > (d + 1.0) * pen) {
+        const double gp = (gamma - 1.0) * v, gpen = gamma * pen;
+        if (gp > gpen) return div_r(gp - gpen, den2, rden2);
+        if (gp < -gpen) return div_r(gp + gpen, den2, rden2);
+        return 0.0;
+    }
+    if (v > pen) return div_r(v - pen, d, rd);
+    if (v < -pen) return div_r(v + pen, d, rd);
+    return 0.0;
 }
 
 // ---- thresholding family (coordinate-wise), operation order as in src/oem_dense.h:76-149 ----
@@ -137,31 +195,45 @@ __device__ __forceinline__ double mcp_norm(double b, double pen, double d, doubl
     return 0.0;
 }
 
+// shared-memory copies of the per-call tables
+struct SmemTabs {
+    const double *pf, *gw;
+    const int *grp_ptr, *grp_unique, *grp_idx, *cover;
+    int ngroups;
+};
+
 // prox of one chain, in place on v[0..q): on entry v = u, on exit v = next beta.
 // Dispatch: src/oem_dense.h:527-629.
-__device__ void prox_inplace(const PathArgs &a, const ChainDev &ch, double lambda, double d, double *v) {
-    const int q = a.q;
-    const double alpha = ch.alpha, gamma = ch.gamma;
+__device__ __noinline__ void prox_inplace(int q, const SmemTabs &tb, int pen, double alpha, double gamma, double tau, double lambda,
+                             double d, double *v) {
     double denom = d + (1.0 - alpha) * lambda;
     double lam = lambda * alpha;
-    const int pen = ch.penalty;
     if (pen == OEMB200_PEN_SCAD_NET && alpha == 0.0) { lam = 0.0; denom = d + lambda; }
     const bool net = (pen == OEMB200_PEN_ENET || pen == OEMB200_PEN_SCAD_NET || pen == OEMB200_PEN_MCP_NET ||
                       pen == OEMB200_PEN_GRP_LASSO_NET || pen == OEMB200_PEN_GRP_MCP_NET ||
                       pen == OEMB200_PEN_GRP_SCAD_NET);
     const double lp = net ? lam : lambda, dp = net ? denom : d;
     if (pen < OEMB200_PEN_GRP_LASSO) {
-        for (int j = threadIdx.x; j < q; j += PK_THREADS) {
-            const double u = v[j];
-            const double tp = __ldg(a.pen_fact + j) * lp;
-            double r;
-            switch (pen) {
-                case OEMB200_PEN_OLS: r = u / d; break;
-                case OEMB200_PEN_SCAD: case OEMB200_PEN_SCAD_NET: r = st_scad(u, tp, dp, gamma); break;
-                case OEMB200_PEN_MCP: case OEMB200_PEN_MCP_NET: r = st_mcp(u, tp, dp, gamma); break;
-                default: r = st_lasso(u, tp, dp); break;   // lasso, elastic.net
+        if (pen == OEMB200_PEN_OLS) {
+            for (int j = threadIdx.x; j < q; j += PK_THREADS) v[j] = v[j] / d;
+        } else {
+            // every rule returns 0 when |u| <= pen * min(1, gamma d) (lasso / elastic.net: |u| <= pen); that
+            // test runs on the integer pipe, so coordinates that stay zero cost no FP64 work beyond one multiply
+            const bool ncv = (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET || pen == OEMB200_PEN_MCP ||
+                              pen == OEMB200_PEN_MCP_NET);
+            const double zf = ncv ? fmin(1.0, gamma * dp) : 1.0;
+            const bool is_scad = (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET);
+            for (int j = threadIdx.x; j < q; j += PK_THREADS) {
+                const double u = v[j];
+                const double tp = tb.pf[j] * lp;
+                double r = 0.0;
+                if (abs_gt(u, tp * zf)) {
+                    if (!ncv) r = st_lasso(u, tp, dp);
+                    else if (is_scad) r = st_scad(u, tp, dp, gamma);
+                    else r = st_mcp(u, tp, dp, gamma);
+                }
+                v[j] = r;
             }
-            v[j] = r;
         }
         __syncthreads();
         return;
@@ -171,44 +243,46 @@ __device__ void prox_inplace(const PathArgs &a, const ChainDev &ch, double lambd
     if (pen == OEMB200_PEN_GRP_MCP || pen == OEMB200_PEN_GRP_MCP_NET) kind = 1;
     if (pen == OEMB200_PEN_GRP_SCAD || pen == OEMB200_PEN_GRP_SCAD_NET) kind = 2;
     if (pen == OEMB200_PEN_SPARSE_GRP_LASSO) {
-        const double lam_l1 = ch.tau * lambda;
-        glam = (1.0 - ch.tau) * lambda;
+        const double lam_l1 = tau * lambda;
+        glam = (1.0 - tau) * lambda;
         gd = d;
-        for (int j = threadIdx.x; j < q; j += PK_THREADS) v[j] = st_lasso(v[j], __ldg(a.pen_fact + j) * lam_l1, 1.0);
+        for (int j = threadIdx.x; j < q; j += PK_THREADS) v[j] = st_lasso(v[j], tb.pf[j] * lam_l1, 1.0);
         __syncthreads();
     }
     // one thread per group: sequential norm in member order like block_soft_threshold (src/oem_dense.h:193-315)
-    for (int g = threadIdx.x; g < a.ngroups; g += PK_THREADS) {
-        const int b0 = a.grp_ptr[g], b1 = a.grp_ptr[g + 1];
+    for (int g = threadIdx.x; g < tb.ngroups; g += PK_THREADS) {
+        const int b0 = tb.grp_ptr[g], b1 = tb.grp_ptr[g + 1];
         double tf;
-        if (a.unique_groups[g] == 0) tf = 1.0;
+        if (tb.grp_unique[g] == 0) tf = 1.0;
         else {
             double nrm = 0.0;
-            for (int k = b0; k < b1; ++k) { const double x = v[a.grp_idx[k]]; nrm += x * x; }
+            for (int k = b0; k < b1; ++k) { const double x = v[tb.grp_idx[k]]; nrm += x * x; }
             nrm = sqrt(nrm);
-            const double gw = a.group_weights[g];
+            const double gw = tb.gw[g];
             if (kind == 0) { const double t = 1.0 - glam * gw / nrm; tf = (0.0 < t) ? t : 0.0; }
             else if (kind == 1) tf = mcp_norm(nrm, glam * gw, gd, gamma);
             else tf = scad_norm(nrm, glam * gw, gd, gamma);
         }
         for (int k = b0; k < b1; ++k) {
-            const int c = a.grp_idx[k];
+            const int c = tb.grp_idx[k];
             v[c] = (tf != 0.0) ? v[c] * tf / gd : 0.0;
         }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < q; j += PK_THREADS)
-        if (!a.grp_cover[j]) v[j] = 0.0;      // variables in no listed group stay 0 (res.setZero())
+        if (!tb.cover[j]) v[j] = 0.0;      // variables in no listed group stay 0 (res.setZero())
     __syncthreads();
 }
 
-// Largest eigenvalue of the k x k symmetric tridiagonal (al, be) by 32-way multisection on the
-// Sturm count, then the backward eigenvector recurrence for the residual bound
-// be[k-1] * |s_k| / ||s||.  Executed by warp 0; out[0] = theta, out[1] = |s_k| / ||s||.
-__device__ void tridiag_top(const double *al, const double *be, int k, double *out) {
-    const int lane = threadIdx.x & 31;
+// Largest eigenvalue of the k x k symmetric tridiagonal (al, be) by 256-way multisection (one trial point
+// per thread of the CTA) on the Sturm sign pattern (division-free scaled determinant recurrence), then the
+// backward eigenvector recurrence for the residual bound be[k-1] * |s_k| / ||s||.
+// out[0] = theta, out[1] = |s_k| / ||s||, out[2] = lower bracket;  ibe[i] = 1 / be[i].  Called by all threads.
+__device__ __noinline__ void tridiag_top(const double *al, const double *be, const double *ibe, int k, double lo_hint, double *out,
+                            double *red, int *ibuf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double lo = -1e300, hi = -1e300;
-    for (int i = lane; i < k; i += 32) {
+    for (int i = threadIdx.x; i < k; i += PK_THREADS) {
         const double r = (i > 0 ? fabs(be[i - 1]) : 0.0) + (i + 1 < k ? fabs(be[i]) : 0.0);
         lo = fmax(lo, al[i]);
         hi = fmax(hi, al[i] + r);
@@ -218,115 +292,282 @@ __device__ void tridiag_top(const double *al, const double *be, int k, double *o
         lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o));
         hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
+    if (lane == 0) { red[warp] = lo; red[8 + warp] = hi; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < PK_WARPS; ++w) { lo = fmax(lo, red[w]); hi = fmax(hi, red[8 + w]); }
+    lo = fmax(lo, lo_hint);           // Ritz values grow with k (interlacing)
     hi += 1e-14 * fabs(hi) + 1e-300;
-    for (int round = 0; round < 14; ++round) {
+    for (int round = 0; round < 9; ++round) {
         const double w = hi - lo;
-        if (!(w > 2e-16 * fmax(fabs(hi), fabs(lo)))) break;
-        const double x = lo + w * (double)(lane + 1) / 33.0;
-        // all eigenvalues < x  <=>  every Sturm pivot negative
+        if (!(w > 2e-16 * fmax(fabs(hi), fabs(lo)))) break;      // uniform: lo / hi are identical in all threads
+        const double x = lo + w * (double)(threadIdx.x + 1) / (double)(PK_THREADS + 1);
+        // all eigenvalues < x  <=>  the leading principal minors p_i of (T - x I) alternate in sign, p_1 < 0
         bool all_below = true;
-        double qv = al[0] - x;
-        if (qv >= 0.0) all_below = false;
+        double pm = 1.0, pc = al[0] - x;
+        if (!(pc < 0.0)) all_below = false;
         for (int i = 1; i < k && all_below; ++i) {
-            qv = al[i] - x - be[i - 1] * be[i - 1] / qv;
-            if (qv >= 0.0) all_below = false;
+            const double b = be[i - 1];
+            const double pn = (al[i] - x) * pc - (b * b) * pm;
+            if (!(pn * pc < 0.0)) all_below = false;
+            pm = pc; pc = pn;
+            if (abs_gt(pc, 1e150)) { pc *= 1e-150; pm *= 1e-150; }
+            else if (!abs_gt(pc, 1e-150)) { pc *= 1e150; pm *= 1e150; }
         }
         const unsigned m = __ballot_sync(0xffffffffu, all_below);
-        if (m == 0u) { lo = __shfl_sync(0xffffffffu, x, 31); }
-        else {
-            const int f = __ffs(m) - 1;
-            const double nh = __shfl_sync(0xffffffffu, x, f);
-            const double nl = __shfl_sync(0xffffffffu, x, f > 0 ? f - 1 : 0);
-            hi = nh;
-            if (f > 0) lo = nl;
-        }
+        if (lane == 0) ibuf[warp] = m ? warp * 32 + __ffs(m) - 1 : PK_THREADS;
+        __syncthreads();
+        int f = PK_THREADS;
+#pragma unroll
+        for (int ww = 0; ww < PK_WARPS; ++ww) f = min(f, ibuf[ww]);
+        __syncthreads();
+        // trial point of thread i is lo + w (i+1)/(T+1): the eigenvalue lies in (x_{f-1}, x_f]
+        const double nlo = f > 0 ? lo + w * (double)f / (double)(PK_THREADS + 1) : lo;
+        if (f < PK_THREADS) hi = lo + w * (double)(f + 1) / (double)(PK_THREADS + 1);
+        lo = nlo;
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         const double theta = 0.5 * (lo + hi);
         // backward recurrence from s_k = 1 (the growing, hence stable, direction)
         double s_next = 0.0, s_cur = 1.0, nrm2 = 1.0, s_last = 1.0;   // s_last = s_k in current units
         for (int i = k - 1; i >= 1; --i) {
             // row i: be[i-1] s_{i-1} + (al[i]-theta) s_i + be[i] s_{i+1} = 0
             const double bi = (i + 1 < k) ? be[i] : 0.0;
-            const double s_prev = -((al[i] - theta) * s_cur + bi * s_next) / be[i - 1];
+            const double s_prev = -((al[i] - theta) * s_cur + bi * s_next) * ibe[i - 1];
             s_next = s_cur;
             s_cur = s_prev;
             nrm2 += s_cur * s_cur;
-            if (fabs(s_cur) > 1e120) { s_cur *= 1e-120; s_next *= 1e-120; nrm2 *= 1e-240; s_last *= 1e-120; }
+            if (abs_gt(s_cur, 1e120)) { s_cur *= 1e-120; s_next *= 1e-120; nrm2 *= 1e-240; s_last *= 1e-120; }
         }
         out[0] = theta;
         out[1] = s_last / sqrt(nrm2);   // |last eigenvector component| of the unit Ritz vector
+        out[2] = lo;
     }
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f64(double *local_smem_ptr, unsigned cta_rank, double v) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+
+// ---- mat-vec on the FP64 tensor pipe (kept out of line: the persistent loop must stay I-cache resident) ----
+struct MvCtx {
+    const double *Amine, *xy;
+    double *part, *us0, *ub;
+    int q, qs, c0, c1, natm, nvec, max_ct, team_size, nbuf;
+};
+
+template <int MODE>
+__device__ __forceinline__ void mv_publish(const MvCtx &m, int par, int c, int j, double val) {
+    double *dst = m.us0 + ((size_t)(par & (m.nbuf - 1)) * m.nvec + c) * m.qs + j;
+    if (MODE == MODE_SINGLE) *dst = val;
+    else if (MODE == MODE_CLUSTER) {
+        for (int r = 0; r < m.team_size; ++r) st_cluster_f64(dst, (unsigned)r, val);
+    } else m.ub[((size_t)par * m.max_ct + c) * m.q + j] = val;
+}
+
+// u[c][j] = sum_i S[i][j] vec_c[i] (+ xy[j]) for my columns j and nv vectors.
+// D(8 columns x 8 vectors) += A(8 columns x 4 rows) * B(4 rows x 8 vectors) per DMMA; a work unit is one
+// 8-column x 8-vector tile; with fewer than 8 units the K range is split across warps and the partial
+// tiles are summed in fixed order through shared memory.
+template <int MODE>
+__device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, int nv, const int *inactive, int add_xy, int par) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int qs = m.qs;
+    const int natn = (nv + 7) >> 3;
+    const int units = m.natm * natn;
+    const int ksplit = units >= PK_WARPS ? 1 : PK_WARPS / units;
+    const int ktot = qs >> 2;                                   // k4 steps (zero padded)
+    const int kper = (ktot + ksplit - 1) / ksplit;
+    const int tasks = units * ksplit;
+    for (int task = warp; task < tasks; task += PK_WARPS) {
+        const int unit = task / ksplit, kp = task - unit * ksplit;
+        const int am = unit % m.natm, an = unit / m.natm;
+        const double *ap = m.Amine + (size_t)(am * 8 + g) * qs + t;
+        const int cidx = an * 8 + g;
+        const bool bvalid = cidx < nv;
+        const double *bp = vec + (size_t)(bvalid ? cidx : 0) * qs + t;
+        const int k0 = kp * kper, k1 = min(ktot, k0 + kper);
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, c20 = 0.0, c21 = 0.0, c30 = 0.0, c31 = 0.0;
+        int ks = k0;
+#pragma unroll 1
+        for (; ks + 4 <= k1; ks += 4) {
+            const double a0 = ap[ks * 4], a1 = ap[ks * 4 + 4], a2 = ap[ks * 4 + 8], a3 = ap[ks * 4 + 12];
+            const double b0 = bvalid ? bp[ks * 4] : 0.0, b1 = bvalid ? bp[ks * 4 + 4] : 0.0;
+            const double b2 = bvalid ? bp[ks * 4 + 8] : 0.0, b3 = bvalid ? bp[ks * 4 + 12] : 0.0;
+            dmma884(c00, c01, a0, b0);
+            dmma884(c10, c11, a1, b1);
+            dmma884(c20, c21, a2, b2);
+            dmma884(c30, c31, a3, b3);
+        }
+#pragma unroll 1
+        for (; ks < k1; ++ks) {
+            const double a0 = ap[ks * 4];
+            const double b0 = bvalid ? bp[ks * 4] : 0.0;
+            dmma884(c00, c01, a0, b0);
+        }
+        const double r0 = (c00 + c10) + (c20 + c30), r1 = (c01 + c11) + (c21 + c31);
+        // this lane holds column (am*8 + g) for vectors an*8 + 2t, 2t+1
+        if (ksplit == 1) {
+            const int j = m.c0 + am * 8 + g;
+            const int cv = an * 8 + 2 * t;
+            if (j < m.c1) {
+                const double add = add_xy ? m.xy[j] : 0.0;
+                if (cv < nv && !(inactive && inactive[cv])) mv_publish<MODE>(m, par, cv, j, r0 + add);
+                if (cv + 1 < nv && !(inactive && inactive[cv + 1])) mv_publish<MODE>(m, par, cv + 1, j, r1 + add);
+            }
+        } else {
+            m.part[task * 64 + lane * 2] = r0;
+            m.part[task * 64 + lane * 2 + 1] = r1;
+        }
+    }
+    if (ksplit > 1) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < units * 64; e += PK_THREADS) {
+            const int unit = e >> 6, w = e & 63;
+            const int ln = w >> 1, h = w & 1;
+            double sacc = 0.0;
+            for (int kp = 0; kp < ksplit; ++kp) sacc += m.part[(unit * ksplit + kp) * 64 + w];
+            const int am = unit % m.natm, an = unit / m.natm;
+            const int j = m.c0 + am * 8 + (ln >> 2);
+            const int cv = an * 8 + 2 * (ln & 3) + h;
+            if (j < m.c1 && cv < nv && !(inactive && inactive[cv]))
+                mv_publish<MODE>(m, par, cv, j, sacc + (add_xy ? m.xy[j] : 0.0));
+        }
+    }
+}
+
+// slow path of the coordinate-wise prox (non-zero result), out of line for the same reason
+__device__ __noinline__ double prox_coord_nonzero(int kind, double u, double tp, const double *cp, double gamma) {
+    const double dp = cp[1], rdp = cp[4], gammad = cp[5], den2 = cp[6], rden2 = cp[7];
+    if (kind == 2) return st_scad_r(u, tp, dp, rdp, gamma, gammad, den2, rden2);
+    if (kind == 1) return st_mcp_r(u, tp, dp, rdp, gammad, den2, rden2);
+    return st_lasso_r(u, tp, dp, rdp);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs a) {
     extern __shared__ __align__(16) double sm[];
-    const int q = a.q;
+    const int q = a.q, qs = a.qs;            // qs = padded vector / slice stride, = 4 (mod 16), >= roundup(q, 4)
     const int team = blockIdx.x / a.team_size, rank = blockIdx.x - team * a.team_size;
     const int c0 = min(q, rank * a.cpc), c1 = min(q, c0 + a.cpc);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
     const int ct0 = a.team_ptr[team], nct = a.team_ptr[team + 1] - ct0;
     const int nvec = max(a.max_ct, 2);
 
-    double *Asl = sm;
-    double *beta = sm + (a.a_in_smem ? (size_t)a.cpc * q : 0);
-    double *us = beta + (size_t)nvec * q;
-    double *red = us + (size_t)nvec * q;           // 16
-    double *lz_al = red + 16;                      // LZ_MAX
-    double *lz_be = lz_al + LZ_MAX;                // LZ_MAX
-    double *ak = lz_be + LZ_MAX;                   // PK_MAXCT
-    double *misc = ak + PK_MAXCT;                  // 8
-    int *lam_idx = reinterpret_cast<int *>(misc + 8);   // PK_MAXCT each
+    // ---- shared-memory carve-up (doubles, then ints) ----
+    double *Asl = sm;                                      // cpc_pad x qs (slice of XX, then of A)
+    double *beta = sm + (a.a_in_smem ? (size_t)a.cpc_pad * qs : 0);   // nvec x qs, zero padded
+    constexpr int NBUF = (MODE == MODE_CLUSTER) ? 2 : 1;   // remote DSMEM stores need a second (parity) buffer
+    double *us0 = beta + (size_t)nvec * qs;                // exchange buffer(s), nvec x qs each
+    double *xy = us0 + (size_t)NBUF * nvec * qs;           // q
+    double *pf = xy + q;                                   // q
+    double *lam_sm = pf + q;                               // max_ct * Lmax
+    double *gw = lam_sm + (size_t)a.max_ct * a.Lmax;       // ngroups
+    double *part = gw + a.ngroups;                         // PK_PART x 64
+    double *red = part + PK_PART * 64;                     // 16
+    double *lz_al = red + 16;                              // LZ_MAX
+    double *lz_be = lz_al + LZ_MAX;                        // LZ_MAX
+    double *lz_ib = lz_be + LZ_MAX;                        // LZ_MAX
+    double *ak = lz_ib + LZ_MAX;                           // PK_MAXCT
+    double *chd = ak + PK_MAXCT;                           // 3 * PK_MAXCT: alpha, gamma, tau
+    double *misc = chd + 3 * PK_MAXCT;                     // 8
+    double *cpar = misc + 8;                               // 8 * PK_MAXCT: per-iteration derived constants
+    int *lam_idx = reinterpret_cast<int *>(cpar + 8 * PK_MAXCT);   // PK_MAXCT each
     int *iter = lam_idx + PK_MAXCT;
     int *done = iter + PK_MAXCT;
-    int *flag = done + PK_MAXCT;
+    int *chi = done + PK_MAXCT;                            // 3 * PK_MAXCT: penalty, nlam, out_off
+    int *grp_ptr = chi + 3 * PK_MAXCT;                     // ngroups + 1
+    int *grp_unique = grp_ptr + a.ngroups + 1;             // ngroups
+    int *grp_idx = grp_unique + a.ngroups;                 // ngidx
+    int *cover = grp_idx + a.ngidx;                        // q (only with groups)
 
     unsigned *bar = a.barriers + team;
     unsigned bar_target = 0;
-    double *ub = a.ubuf + (size_t)team * 2 * a.max_ct * q;
+    double *ub = a.ubuf ? a.ubuf + (size_t)team * 2 * a.max_ct * q : nullptr;
     const double *XXg = a.XX + (size_t)team * q * q;
-    double *Aglob = a.Abuf ? a.Abuf + (size_t)team * q * q : nullptr;
-    const double *XYg = a.XY + (size_t)team * q;
+    double *Amine = a.a_in_smem ? Asl : a.Abuf + ((size_t)team * a.team_size + rank) * a.cpc_pad * qs;
 
-    // ---- load my column slice of XX ----
-    for (int j = c0 + warp; j < c1; j += PK_WARPS) {
-        double *dst = a.a_in_smem ? Asl + (size_t)(j - c0) * q : Aglob + (size_t)j * q;
+    // ---- one-time loads: my column slice of XX (zero padded to cpc_pad x qs) and every table ----
+    for (int jl = warp; jl < a.cpc_pad; jl += PK_WARPS) {
+        const int j = c0 + jl;
+        double *dst = Amine + (size_t)jl * qs;
         const double *src = XXg + (size_t)j * q;
-        for (int i = lane; i < q; i += 32) dst[i] = src[i];
+        for (int i = lane; i < qs; i += 32) dst[i] = (j < c1 && i < q) ? src[i] : 0.0;
     }
-    __syncthreads();
+    for (int e = threadIdx.x; e < (1 + NBUF) * nvec * qs; e += PK_THREADS) beta[e] = 0.0;   // beta + exchange buffer(s)
+    for (int j = threadIdx.x; j < q; j += PK_THREADS) {
+        xy[j] = a.XY[(size_t)team * q + j];
+        pf[j] = a.pen_fact ? a.pen_fact[j] : 1.0;
+        if (a.ngroups) cover[j] = a.grp_cover[j];
+    }
+    for (int gi = threadIdx.x; gi < a.ngroups; gi += PK_THREADS) {
+        gw[gi] = a.group_weights[gi];
+        grp_unique[gi] = a.unique_groups[gi];
+    }
+    for (int gi = threadIdx.x; gi < a.ngroups + 1 && a.ngroups; gi += PK_THREADS) grp_ptr[gi] = a.grp_ptr[gi];
+    for (int k = threadIdx.x; k < a.ngidx; k += PK_THREADS) grp_idx[k] = a.grp_idx[k];
+    for (int c = threadIdx.x; c < nct; c += PK_THREADS) {
+        const ChainDev ch = a.chains[a.team_idx[ct0 + c]];
+        chi[c] = ch.penalty; chi[PK_MAXCT + c] = ch.nlam; chi[2 * PK_MAXCT + c] = ch.out_off;
+        chd[c] = ch.alpha; chd[PK_MAXCT + c] = ch.gamma; chd[2 * PK_MAXCT + c] = ch.tau;
+        lam_idx[c] = 0; iter[c] = 0; ak[c] = 1.0;
+        done[c] = (ch.nlam <= 0) ? 1 : 0;
+    }
+    for (int e = threadIdx.x; e < nct * a.Lmax; e += PK_THREADS) {
+        const int c = e / a.Lmax, l = e - c * a.Lmax;
+        const ChainDev ch = a.chains[a.team_idx[ct0 + c]];
+        lam_sm[e] = l < ch.nlam ? a.lambdas[ch.lam_off + l] : 0.0;
+    }
+    if (MODE == MODE_CLUSTER) cluster_sync_all();   // peers may start storing into my exchange buffers
+    else __syncthreads();
+    SmemTabs tb{pf, gw, grp_ptr, grp_unique, grp_idx, cover, a.ngroups};
 
-    // mat-vec over the owned columns for `nv` vectors stored at vec + c*q (c < nv, active[c] != 0):
-    // ubuf[par][c][j] = sign * sum_i S[i][j] vec_c[i] + add[j]
-    auto matvec = [&](const double *vec, int nv, const int *inactive, const double *add, int par) {
-        for (int j = c0 + warp; j < c1; j += PK_WARPS) {
-            const double *col = a.a_in_smem ? Asl + (size_t)(j - c0) * q : Aglob + (size_t)j * q;
-            for (int cb = 0; cb < nv; cb += PK_CB) {
-                double acc[PK_CB];
+    // ---- exchange primitives ----
+    auto exchange = [&](int par, int nv, const int *inactive) {
+        if (MODE == MODE_SINGLE) __syncthreads();
+        else if (MODE == MODE_CLUSTER) cluster_sync_all();
+        else {
+            team_barrier(bar, bar_target, a.team_size);
+            const double *src = ub + (size_t)par * a.max_ct * q;
+            double *dst = us0;
+            // per chain, 4 loads in flight per thread before the first use (one L2 round trip per batch)
+            for (int c = 0; c < nv; ++c) {
+                if (inactive && inactive[c]) continue;
+                const double *sc = src + (size_t)c * q;
+                double *dc = dst + (size_t)c * qs;
+                for (int j0 = threadIdx.x; j0 < q; j0 += 4 * PK_THREADS) {
+                    double tmp[4];
 #pragma unroll
-                for (int c = 0; c < PK_CB; ++c) acc[c] = 0.0;
-                for (int i = lane; i < q; i += 32) {
-                    const double av = col[i];
+                    for (int u = 0; u < 4; ++u) { const int j = j0 + u * PK_THREADS; tmp[u] = j < q ? ld_cg(sc + j) : 0.0; }
 #pragma unroll
-                    for (int c = 0; c < PK_CB; ++c)
-                        if (cb + c < nv) acc[c] = fma(av, vec[(size_t)(cb + c) * q + i], acc[c]);
-                }
-#pragma unroll
-                for (int c = 0; c < PK_CB; ++c) {
-                    if (cb + c < nv) {
-                        const double s = pk_warp_sum(acc[c]);
-                        if (lane == 0 && !(inactive && inactive[cb + c]))
-                            ub[((size_t)par * a.max_ct + cb + c) * q + j] = s + (add ? add[j] : 0.0);
-                    }
+                    for (int u = 0; u < 4; ++u) { const int j = j0 + u * PK_THREADS; if (j < q) dc[j] = tmp[u]; }
                 }
             }
+            __syncthreads();
         }
+    };
+
+    MvCtx mv;
+    mv.Amine = Amine; mv.xy = xy; mv.part = part; mv.us0 = us0; mv.ub = ub;
+    mv.q = q; mv.qs = qs; mv.c0 = c0; mv.c1 = c1; mv.natm = a.cpc_pad >> 3; mv.nvec = nvec; mv.max_ct = a.max_ct;
+    mv.team_size = a.team_size; mv.nbuf = NBUF;
+    auto matvec = [&](const double *vec, int nv, const int *inactive, bool add_xy, int par_) {
+        matvec_dmma<MODE>(mv, vec, nv, inactive, add_xy ? 1 : 0, par_);
     };
 
     // =========================== phase 0: top eigenvalue ===========================
     double dval;
+    int par = 0;
     if (a.compute_eig) {
-        double *v = beta, *vprev = beta + q, *w = us;
+        double *v = beta, *vprev = beta + qs;
         // deterministic pseudo-random start vector (fixed seed), normalised
         double ss = 0.0;
         for (int i = threadIdx.x; i < q; i += PK_THREADS) {
@@ -340,17 +581,17 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         const double inv = 1.0 / sqrt(ss);
         for (int i = threadIdx.x; i < q; i += PK_THREADS) v[i] *= inv;
         __syncthreads();
-        double beta_prev = 0.0, theta = 0.0;
-        int k = 0, par = 0;
+        double beta_prev = 0.0, theta = 0.0, lo_hint = -1e300;
+        int k = 0;
+        const long long tl0 = clock64();
+        long long ttri = 0;
         const int kmax = min(LZ_MAX, max(q, 1));
         bool conv = false;
         while (!conv) {
-            matvec(v, 1, nullptr, nullptr, par);
-            team_barrier(bar, bar_target, a.team_size);
-            const double *src = ub + (size_t)par * a.max_ct * q;
-            for (int i = threadIdx.x; i < q; i += PK_THREADS) w[i] = ld_cg(src + i);
+            matvec(v, 1, nullptr, false, par);
+            exchange(par, 1, nullptr);
+            double *w = us0 + (size_t)(par & (NBUF - 1)) * nvec * qs;
             par ^= 1;
-            __syncthreads();
             double dot = 0.0;
             for (int i = threadIdx.x; i < q; i += PK_THREADS) dot = fma(v[i], w[i], dot);
             const double alpha_k = block_sum(dot, red);
@@ -361,15 +602,18 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                 nn = fma(x, x, nn);
             }
             const double beta_k = sqrt(block_sum(nn, red));
-            if (threadIdx.x == 0) { lz_al[k] = alpha_k; lz_be[k] = beta_k; }
+            if (threadIdx.x == 0) { lz_al[k] = alpha_k; lz_be[k] = beta_k; lz_ib[k] = 1.0 / beta_k; }
             ++k;
             __syncthreads();
-            // convergence check (every step while small, then every 4th)
+            // convergence check: every step while the tridiagonal is tiny, then every 8th
             const bool breakdown = !(beta_k > 1e-14 * fabs(alpha_k));
-            if (k <= 8 || (k & 3) == 0 || breakdown || k >= kmax) {
-                if (warp == 0) tridiag_top(lz_al, lz_be, k, misc);
+            if (k <= 4 || (k & 7) == 0 || breakdown || k >= kmax) {
+                const long long tq = clock64();
+                tridiag_top(lz_al, lz_be, lz_ib, k, lo_hint, misc, red, reinterpret_cast<int *>(cpar));
                 __syncthreads();
+                ttri += clock64() - tq;
                 theta = misc[0];
+                lo_hint = misc[2];
                 const double res = beta_k * misc[1];
                 conv = breakdown || k >= kmax || (res <= a.eig_tol * fabs(theta));
                 __syncthreads();
@@ -385,6 +629,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
             }
         }
         dval = theta * a.eig_factor;
+        if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { a.prof[4] += clock64() - tl0; a.prof[5] += ttri; a.prof[6] += k; }
         if (rank == 0 && threadIdx.x == 0) {
             a.d[team] = dval;
             if (a.lanczos_steps) a.lanczos_steps[team] = k;
@@ -393,113 +638,190 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         dval = a.d[team];
     }
 
-    if (nct == 0) return;
-
-    // ---- A = d I - XX on my slice ----
-    for (int j = c0 + warp; j < c1; j += PK_WARPS) {
-        double *col = a.a_in_smem ? Asl + (size_t)(j - c0) * q : Aglob + (size_t)j * q;
-        for (int i = lane; i < q; i += 32) {
-            const double x = -col[i];
-            col[i] = (i == j) ? x + dval : x;
-        }
-    }
-    // ---- chain state ----
-    for (int c = threadIdx.x; c < nct; c += PK_THREADS) {
-        lam_idx[c] = 0; iter[c] = 0; ak[c] = 1.0;
-        done[c] = (a.chains[a.team_idx[ct0 + c]].nlam <= 0) ? 1 : 0;
-    }
-    for (int e = threadIdx.x; e < nct * q; e += PK_THREADS) {
-        const int c = e / q, j = e - c * q;
-        const int gc = a.team_idx[ct0 + c];
-        beta[e] = a.beta_init ? a.beta_init[(size_t)a.chains[gc].out_off * q + j] : 0.0;
-    }
-    __syncthreads();
-
-    // =========================== phase 1: lambda paths ===========================
-    int par = 0;
-    for (;;) {
-        int nactive = 0;
-        for (int c = 0; c < nct; ++c) nactive += done[c] ? 0 : 1;
-        if (nactive == 0) break;
-        matvec(beta, nct, done, XYg, par);
-        team_barrier(bar, bar_target, a.team_size);
-        const double *src = ub + (size_t)par * a.max_ct * q;
-        for (int e = threadIdx.x; e < nct * q; e += PK_THREADS) {
-            const int c = e / q;
-            if (!done[c]) us[e] = ld_cg(src + e);
-        }
-        if (threadIdx.x < nct) flag[threadIdx.x] = 1;
-        par ^= 1;
-        __syncthreads();
-        for (int c = 0; c < nct; ++c) {
-            if (done[c]) continue;
-            const ChainDev ch = a.chains[a.team_idx[ct0 + c]];
-            const double lambda = a.lambdas[ch.lam_off + lam_idx[c]];
-            double *bn = us + (size_t)c * q;
-            double *bo = beta + (size_t)c * q;
-            prox_inplace(a, ch, lambda, dval, bn);
-            if (a.accelerate) {     // src/oem_dense.h:633-651
-                const double ak_prev = ak[c];
-                const double ak_new = 0.5 * (1.0 + sqrt(1.0 + 4.0 * ak_prev * ak_prev));
-                const double ratio = (ak_prev - 1.0) / ak_new;
-                double adv = 0.0;
-                for (int j = threadIdx.x; j < q; j += PK_THREADS) {
-                    const double upd = bn[j];
-                    const double diff = upd - bo[j];
-                    const double acc = upd + ratio * diff;
-                    bn[j] = acc;
-                    adv += (acc - upd) * diff;
+    if (nct > 0) {
+        // ---- A = d I - XX on my slice ----
+        for (int jl = warp; jl < a.cpc_pad; jl += PK_WARPS) {
+            const int j = c0 + jl;
+            double *col = Amine + (size_t)jl * qs;
+            if (j < c1)
+                for (int i = lane; i < q; i += 32) {
+                    const double x = -col[i];
+                    col[i] = (i == j) ? x + dval : x;
                 }
-                adv = block_sum(adv, red);
-                if (threadIdx.x == 0) ak[c] = (adv > 0.0) ? 1.0 : ak_new;
-            }
-            // stop rule (src/utils.cpp:537-549)
-            bool ok = true;
-            for (int j = threadIdx.x; j < q; j += PK_THREADS) {
-                const double cur = bn[j], prev = bo[j];
-                const double ac = fabs(cur), ap = fabs(prev);
-                if ((ac > 1e-13 && ap <= 1e-13) || (ac <= 1e-13 && ap > 1e-13)) ok = false;
-                if (ac > 1e-13 && ap > 1e-13 && fabs((cur - prev) / prev) > a.tol) ok = false;
-            }
-            if (!ok) flag[c] = 0;
+        }
+        for (int e = threadIdx.x; e < nvec * qs; e += PK_THREADS) {
+            const int c = e / qs, j = e - c * qs;
+            beta[e] = (c < nct && j < q && a.beta_init) ? a.beta_init[(size_t)chi[2 * PK_MAXCT + c] * q + j] : 0.0;
         }
         __syncthreads();
-        for (int c = 0; c < nct; ++c) {
-            if (done[c]) continue;       // uniform: done[] only changes below, after the sync
-            const ChainDev ch = a.chains[a.team_idx[ct0 + c]];
-            double *bn = us + (size_t)c * q;
-            double *bo = beta + (size_t)c * q;
-            const int it = iter[c] + 1;
-            const bool finished = flag[c] || it >= a.maxit;
-            const int li = lam_idx[c];
-            if (finished && a.post_scale) {      // oem_xtx get_beta() quirk: src/oem_xtx.h:576-581
-                for (int j = threadIdx.x; j < q; j += PK_THREADS) bn[j] *= a.post_scale[j];
+
+        // =========================== phase 1: lambda paths ===========================
+        // Per iteration: mat-vec -> exchange -> one pass each for prox / stop rule / commit over ALL active
+        // chains (no block-wide sync between chains; 4 independent elements per thread in flight because
+        // with 8 warps per SM these passes are latency-, not throughput-bound).
+        int *flagw = reinterpret_cast<int *>(red);      // 8 words: per-warp "violated" bit masks
+        for (;;) {
+            int nactive = 0;
+            for (int c = 0; c < nct; ++c) nactive += done[c] ? 0 : 1;
+            if (nactive == 0) break;
+            long long t0 = clock64();
+            // derived per-chain constants for this iteration's lambda (read after the exchange's sync); done by
+            // the last warp, which has the lightest mat-vec share
+            if (warp == PK_WARPS - 1 && lane < nct && !done[lane]) {
+                const int c = lane, pen = chi[c];
+                const double alpha = chd[c], gamma = chd[PK_MAXCT + c];
+                const double lambda = lam_sm[(size_t)c * a.Lmax + lam_idx[c]];
+                double denom = dval + (1.0 - alpha) * lambda, lam = lambda * alpha;
+                if (pen == OEMB200_PEN_SCAD_NET && alpha == 0.0) { lam = 0.0; denom = dval + lambda; }
+                const bool net = (pen == OEMB200_PEN_ENET || pen == OEMB200_PEN_SCAD_NET || pen == OEMB200_PEN_MCP_NET);
+                const double lp = net ? lam : lambda, dp = net ? denom : dval;
+                const bool is_scad = (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET);
+                const bool is_mcp = (pen == OEMB200_PEN_MCP || pen == OEMB200_PEN_MCP_NET);
+                const double gammad = gamma * dp;
+                const double den2 = is_mcp ? dp - 1.0 / gamma : (gamma - 1.0) * dp - 1.0;   // second denominator
+                double *cp = cpar + c * 8;
+                cp[0] = lp; cp[1] = dp; cp[2] = (is_scad || is_mcp) ? fmin(1.0, gammad) : 1.0; cp[3] = lambda;
+                cp[4] = 1.0 / dp; cp[5] = gammad; cp[6] = den2; cp[7] = 1.0 / den2;
             }
-            for (int j = threadIdx.x; j < q; j += PK_THREADS) {
-                const double x = bn[j];
-                bo[j] = x;
-                if (finished && rank == 0) a.beta_out[((size_t)ch.out_off * a.Lmax + li) * q + j] = x;
+            matvec(beta, nct, done, true, par);
+            long long t1 = clock64();
+            exchange(par, nct, done);
+            long long t2 = clock64();
+            double *us = us0 + (size_t)(par & (NBUF - 1)) * nvec * qs;
+            par ^= 1;
+            // ---- coordinate-wise chains: prox (src/oem_dense.h:527-629), stop rule (src/utils.cpp:537-549) and
+            // commit fused in ONE pass: u -> next beta, compared with and written over the old beta.  Identical
+            // bit patterns (0 -> 0 above all) cost no arithmetic; |(cur-prev)/prev| > tol is evaluated as
+            // |cur-prev| > tol |prev|.  Group penalties and the Nesterov option take the three-pass route below.
+            unsigned bad = 0u;
+            bool any_slow = false;
+            for (int c = 0; c < nct; ++c) {
+                if (done[c]) continue;
+                const int pen = chi[c];
+                if (pen >= OEMB200_PEN_GRP_LASSO || a.accelerate) { any_slow = true; continue; }
+                const double *bn = us + (size_t)c * qs;
+                double *bo = beta + (size_t)c * qs;
+                const double *cp = cpar + c * 8;
+                const double lp = cp[0], zf = cp[2], rdp = cp[4];
+                const double gamma = chd[PK_MAXCT + c];
+                const bool is_ols = pen == OEMB200_PEN_OLS;
+                const int kind = (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET) ? 2
+                               : (pen == OEMB200_PEN_MCP || pen == OEMB200_PEN_MCP_NET) ? 1 : 0;
+                bool viol = false;
+                for (int j0 = threadIdx.x; j0 < q; j0 += 4 * PK_THREADS) {
+                    double u[4], tp[4], prev[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = j0 + k * PK_THREADS;
+                        u[k] = j < q ? bn[j] : 0.0;
+                        tp[k] = j < q ? pf[j] * lp : 0.0;
+                        prev[k] = j < q ? bo[j] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = j0 + k * PK_THREADS;
+                        double r = 0.0;
+                        if (is_ols) r = div_r(u[k], dval, rdp);        // ols: dp == d
+                        else if (abs_gt(u[k], tp[k] * zf))      // else: every rule returns 0, no further FP64 work
+                            r = prox_coord_nonzero(kind, u[k], tp[k], cp, gamma);
+                        if (j < q && __double_as_longlong(r) != __double_as_longlong(prev[k])) {
+                            const bool bc = abs_gt(r, 1e-13), bp = abs_gt(prev[k], 1e-13);
+                            if (bc != bp) viol = true;
+                            else if (bc && abs_gt(r - prev[k], a.tol * fabs(prev[k]))) viol = true;
+                            bo[j] = r;
+                        }
+                    }
+                }
+                if (viol) bad |= 1u << c;
+            }
+            const long long tA = clock64();
+            if (any_slow) {
+                __syncthreads();
+                for (int c = 0; c < nct; ++c) {
+                    if (done[c]) continue;
+                    const int pen = chi[c];
+                    if (!(pen >= OEMB200_PEN_GRP_LASSO || a.accelerate)) continue;
+                    double *bn = us + (size_t)c * qs;
+                    double *bo = beta + (size_t)c * qs;
+                    prox_inplace(q, tb, pen, chd[c], chd[PK_MAXCT + c], chd[2 * PK_MAXCT + c], cpar[c * 8 + 3], dval, bn);
+                    if (a.accelerate) {     // Nesterov step, src/oem_dense.h:633-651
+                        const double ak_prev = ak[c];
+                        const double ak_new = 0.5 * (1.0 + sqrt(1.0 + 4.0 * ak_prev * ak_prev));
+                        const double ratio = (ak_prev - 1.0) / ak_new;
+                        double adv = 0.0;
+                        for (int j = threadIdx.x; j < q; j += PK_THREADS) {
+                            const double upd = bn[j];
+                            const double diff = upd - bo[j];
+                            const double acc = upd + ratio * diff;
+                            bn[j] = acc;
+                            adv += (acc - upd) * diff;
+                        }
+                        adv = block_sum(adv, red);
+                        if (threadIdx.x == 0) ak[c] = (adv > 0.0) ? 1.0 : ak_new;
+                    }
+                    bool viol = false;
+                    for (int j = threadIdx.x; j < q; j += PK_THREADS) {
+                        const double cur = bn[j], prev = bo[j];
+                        if (__double_as_longlong(cur) == __double_as_longlong(prev)) continue;
+                        const bool bc = abs_gt(cur, 1e-13), bp = abs_gt(prev, 1e-13);
+                        if (bc != bp) viol = true;
+                        else if (bc && abs_gt(cur - prev, a.tol * fabs(prev))) viol = true;
+                        bo[j] = cur;
+                    }
+                    if (viol) bad |= 1u << c;
+                }
+            }
+            const long long tB = clock64();
+            bad = __reduce_or_sync(0xffffffffu, bad);
+            if (lane == 0) flagw[warp] = (int)bad;
+            __syncthreads();
+            bad = 0u;
+#pragma unroll
+            for (int w = 0; w < PK_WARPS; ++w) bad |= (unsigned)flagw[w];
+            const long long tC = clock64();
+            // ---- finished chains (rare): scale.factor quirk of oem_xtx, then their column of the path ----
+            for (int c = 0; c < nct; ++c) {
+                if (done[c]) continue;
+                const bool conv = !((bad >> c) & 1u);
+                if (!(conv || iter[c] + 1 >= a.maxit)) continue;
+                double *bo = beta + (size_t)c * qs;
+                double *gout = a.beta_out + ((size_t)chi[2 * PK_MAXCT + c] * a.Lmax + lam_idx[c]) * q;
+                for (int j = threadIdx.x; j < q; j += PK_THREADS) {
+                    double x = bo[j];
+                    if (a.post_scale) { x *= a.post_scale[j]; bo[j] = x; }   // get_beta() mutates the iterate: src/oem_xtx.h:576-581
+                    if (rank == 0) gout[j] = x;
+                }
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                if (finished) {
-                    if (rank == 0) a.niter_out[(size_t)ch.out_off * a.Lmax + li] = flag[c] ? it : a.maxit + 1;
+            const long long tD = clock64();
+            if (threadIdx.x < nct && !done[threadIdx.x]) {
+                const int c = threadIdx.x;
+                const int li = lam_idx[c], it = iter[c] + 1;
+                const bool conv = !((bad >> c) & 1u);
+                if (conv || it >= a.maxit) {
+                    if (rank == 0) a.niter_out[(size_t)chi[2 * PK_MAXCT + c] * a.Lmax + li] = conv ? it : a.maxit + 1;
                     iter[c] = 0;
                     lam_idx[c] = li + 1;
-                    if (li + 1 >= ch.nlam) done[c] = 1;
+                    if (li + 1 >= chi[PK_MAXCT + c]) done[c] = 1;
                 } else {
                     iter[c] = it;
                 }
             }
+            __syncthreads();
+            if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+                const long long t3 = clock64();
+                a.prof[0] += t1 - t0; a.prof[1] += t2 - t1; a.prof[2] += t3 - t2; a.prof[3] += 1;
+                a.prof[8] += tA - t2; a.prof[9] += tB - tA; a.prof[10] += tC - tB; a.prof[11] += tD - tC; a.prof[12] += t3 - tD;
+            }
         }
-        __syncthreads();
-    }
-    if (a.beta_final && rank == 0) {
-        for (int e = threadIdx.x; e < nct * q; e += PK_THREADS) {
-            const int c = e / q, j = e - c * q;
-            a.beta_final[(size_t)a.chains[a.team_idx[ct0 + c]].out_off * q + j] = beta[e];
+        if (a.beta_final && rank == 0) {
+            for (int e = threadIdx.x; e < nct * q; e += PK_THREADS) {
+                const int c = e / q, j = e - c * q;
+                a.beta_final[(size_t)chi[2 * PK_MAXCT + c] * q + j] = beta[(size_t)c * qs + j];
+            }
         }
     }
+    if (MODE == MODE_CLUSTER) cluster_sync_all();   // no member may exit while peers can still write its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -522,35 +844,63 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     std::vector<ChainDev> cd(pp.chains.size());
     for (size_t i = 0; i < pp.chains.size(); ++i) {
         const ChainDesc &c = pp.chains[i];
+        if (c.nlam > pp.Lmax) fail(OEMB200_EINVAL, "path: chain has more lambdas than Lmax");
         cd[i] = ChainDev{c.gram, c.penalty, c.nlam, c.lam_off, c.alpha, c.gamma, c.tau, c.out_off, 0};
     }
 
-    // ---- geometry: team size, column slice, shared memory ----
-    auto kern = oem_path_kernel;
+    // ---- geometry: mode, team size, column slice, shared memory ----
     const int nvec = std::max(max_ct, 2);
-    const size_t fixed_bytes = ((size_t)2 * nvec * q + 16 + 2 * LZ_MAX + PK_MAXCT + 8) * 8 + 4 * PK_MAXCT * 4;
+    const int q4 = (q + 3) / 4 * 4;
+    const int qs = q4 + (((4 - q4) % 16) + 16) % 16;      // smallest value >= roundup(q,4) that is 4 (mod 16)
+    const int ng = pp.ngroups, ngidx = ng ? pp.ngidx : 0;
+    auto fixed_for = [&](int nbuf) {
+        return ((size_t)(1 + nbuf) * nvec * qs + 2 * (size_t)q + (size_t)max_ct * std::max(pp.Lmax, 1) + ng + PK_PART * 64 + 16 +
+                3 * LZ_MAX + PK_MAXCT + 3 * PK_MAXCT + 8 + 8 * PK_MAXCT) * 8 +
+               ((size_t)6 * PK_MAXCT + (ng ? 2 * (size_t)ng + 1 + ngidx + q : 0)) * 4 + 16;
+    };
+    size_t fixed_bytes = fixed_for(1);
     const size_t smem_cap = cx.smem_optin;
-    if (fixed_bytes > smem_cap) fail(OEMB200_EUNSUPPORTED, "path: q=%d with %d chains per Gram exceeds shared memory", q, max_ct);
+    if (fixed_bytes > smem_cap)
+        fail(OEMB200_EUNSUPPORTED, "path: q=%d with %d chains per Gram and %d lambdas exceeds shared memory", q, max_ct, pp.Lmax);
+    auto slice_bytes = [&](int members) {
+        const int cpc_ = (q + members - 1) / members;
+        return (size_t)((cpc_ + 7) / 8 * 8) * qs * 8;
+    };
+    int mode, team;
+    if (slice_bytes(1) + fixed_bytes <= smem_cap) { mode = MODE_SINGLE; team = 1; }
+    else {
+        int cs = 0;
+        for (int c : {8, 4, 2})      // more members = less mat-vec work each; the cluster barrier costs the same
+            if (slice_bytes(c) + fixed_for(2) <= smem_cap && (q + c - 1) / c >= 16) { cs = c; break; }
+        if (cs && G * cs <= cx.num_sms) { mode = MODE_CLUSTER; team = cs; fixed_bytes = fixed_for(2); }
+        else { mode = MODE_GLOBAL; team = 0; }
+    }
+    void *kern = mode == MODE_SINGLE ? (void *)oem_path_kernel<MODE_SINGLE>
+               : mode == MODE_CLUSTER ? (void *)oem_path_kernel<MODE_CLUSTER> : (void *)oem_path_kernel<MODE_GLOBAL>;
     OEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-    int max_blocks_per_sm = 0;
-    OEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, PK_THREADS, smem_cap));
-    const int max_ctas = std::max(1, max_blocks_per_sm) * cx.num_sms;
-    if (G > max_ctas) fail(OEMB200_EUNSUPPORTED, "path: %d Grams exceed the %d co-resident CTAs", G, max_ctas);
-    int team = max_ctas / G;
-    team = std::min(team, (q + 3) / 4);                       // at least 4 columns per member
-    if ((size_t)q * q * 8 + fixed_bytes <= smem_cap) team = 1; // whole A fits in one CTA: no global barrier
-    team = std::max(team, 1);
+    if (mode == MODE_GLOBAL) {
+        int per_sm = 0;
+        OEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PK_THREADS, smem_cap));
+        const int max_ctas = std::max(1, per_sm) * cx.num_sms;
+        if (G > max_ctas) fail(OEMB200_EUNSUPPORTED, "path: %d Grams exceed the %d co-resident CTAs", G, max_ctas);
+        team = std::max(1, std::min(max_ctas / G, (q + 7) / 8));       // at least one 8-column MMA atom per member
+    }
     int cpc = (q + team - 1) / team;
-    team = (q + cpc - 1) / cpc;                               // drop members that would own nothing
-    const bool a_in_smem = (size_t)cpc * q * 8 + fixed_bytes <= smem_cap;
-    const size_t smem_bytes = fixed_bytes + (a_in_smem ? (size_t)cpc * q * 8 : 0);
+    if (mode == MODE_GLOBAL) {
+        cpc = (cpc + 7) / 8 * 8;                                       // whole atoms: no padded tensor work
+        team = (q + cpc - 1) / cpc;                                    // drop members that would own nothing
+    }
+    const int cpc_pad = (cpc + 7) / 8 * 8;
+    const bool a_in_smem = (size_t)cpc_pad * qs * 8 + fixed_bytes <= smem_cap;
+    const size_t smem_bytes = fixed_bytes + (a_in_smem ? (size_t)cpc_pad * qs * 8 : 0);
 
     DBuf<ChainDev> d_chains(std::max<size_t>(1, cd.size()));
     DBuf<int> d_tptr(tptr.size()), d_tidx(std::max<size_t>(1, tidx.size()));
-    DBuf<double> d_ubuf((size_t)G * 2 * max_ct * q);
+    DBuf<double> d_ubuf;
     DBuf<unsigned> d_bar(G);
     DBuf<double> d_A;
-    if (!a_in_smem) d_A.alloc((size_t)G * q * q);
+    if (mode == MODE_GLOBAL) d_ubuf.alloc((size_t)G * 2 * max_ct * q);
+    if (!a_in_smem) d_A.alloc((size_t)G * team * cpc_pad * qs);
     if (!cd.empty()) d_chains.upload(cd.data(), cd.size(), cx.stream);
     d_tptr.upload(tptr.data(), tptr.size(), cx.stream);
     if (!tidx.empty()) d_tidx.upload(tidx.data(), tidx.size(), cx.stream);
@@ -558,9 +908,10 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
 
     PathArgs a;
     memset(&a, 0, sizeof a);
-    a.q = q; a.ngram = G; a.team_size = team; a.cpc = cpc; a.max_ct = max_ct; a.Lmax = pp.Lmax;
+    a.q = q; a.qs = qs; a.ngram = G; a.team_size = team; a.cpc = cpc; a.cpc_pad = cpc_pad; a.max_ct = max_ct;
+    a.Lmax = std::max(pp.Lmax, 1);
     a.maxit = pp.maxit; a.accelerate = pp.accelerate ? 1 : 0; a.compute_eig = pp.compute_eig ? 1 : 0;
-    a.a_in_smem = a_in_smem ? 1 : 0; a.ngroups = pp.ngroups;
+    a.a_in_smem = a_in_smem ? 1 : 0; a.ngroups = ng; a.mode = mode; a.ngidx = ngidx;
     a.tol = pp.tol; a.eig_factor = pp.eig_factor; a.eig_tol = pp.eig_tol;
     a.XX = pp.XX; a.XY = pp.XY; a.d = pp.d; a.Abuf = d_A.p;
     a.chains = d_chains.p; a.team_ptr = d_tptr.p; a.team_idx = d_tidx.p;
@@ -570,9 +921,33 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     a.beta_final = pp.beta_final; a.beta_out = pp.beta_out; a.niter_out = pp.niter_out;
     a.lanczos_steps = pp.lanczos_steps; a.ubuf = d_ubuf.p; a.barriers = d_bar.p;
 
+    DBuf<long long> d_prof;
+    const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;
+    if (prof) { d_prof.alloc(16); d_prof.zero(cx.stream); a.prof = d_prof.p; }
     void *kargs[] = {&a};
-    OEM_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(G * team), dim3(PK_THREADS), kargs, smem_bytes, cx.stream));
+    if (mode == MODE_GLOBAL) {
+        OEM_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G * team), dim3(PK_THREADS), kargs, smem_bytes, cx.stream));
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(G * team); cfg.blockDim = dim3(PK_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = cx.stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        OEM_CUDA(cudaLaunchKernelExC(&cfg, kern, kargs));
+    }
     cx.st.kernel_launches += 1;
+    if (prof) {
+        long long h[16];
+        d_prof.download(h, 16, cx.stream);
+        OEM_CUDA(cudaStreamSynchronize(cx.stream));
+        fprintf(stderr, "[path prof] mode=%d team=%d cpc=%d q=%d nct=%d | iters=%lld cyc/iter: matvec=%.0f exchange=%.0f prox+update=%.0f | "
+                "lanczos: steps=%lld total=%lld cyc (tridiag %lld)\n", mode, team, cpc, q, max_ct, h[3],
+                h[3] ? (double)h[0] / h[3] : 0.0, h[3] ? (double)h[1] / h[3] : 0.0, h[3] ? (double)h[2] / h[3] : 0.0, h[6], h[4], h[5]);
+        if (h[3]) fprintf(stderr, "[path prof]   prox=%.0f group/accel=%.0f stop=%.0f commit=%.0f state=%.0f\n", (double)h[8] / h[3],
+                          (double)h[9] / h[3], (double)h[10] / h[3], (double)h[11] / h[3], (double)h[12] / h[3]);
+    }
 }
 
 }  // namespace oemb200

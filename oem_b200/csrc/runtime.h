@@ -147,6 +147,7 @@ struct PathProblem {
     const double *pen_fact = nullptr;  // device, q
     // group structure (device), CSR over unique groups
     int ngroups = 0;
+    int ngidx = 0;          // length of grp_idx
     const int *unique_groups = nullptr, *grp_ptr = nullptr, *grp_idx = nullptr;
     const double *group_weights = nullptr;
     const int *grp_cover = nullptr;       // device, q: 1 if the variable belongs to a listed group

@@ -1,0 +1,116 @@
+"""Secondary measurements: BASELINE.json configs[0..3] at full size on one B200, device-resident inputs,
+one JSON line per config with the library's own CUDA-event phase timings and the roofline figures of the
+dominant kernels (Gram TFLOP/s, logistic GEMV GB/s, CV-scoring TFLOP/s).  Not the headline bench (bench.py)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oem_b200  # noqa: E402
+from oem_b200 import api  # noqa: E402
+
+dev = torch.device("cuda", 0)
+
+
+def gen(n, p, seed, sd=1.0, coef=None, noise=1.0, binomial=False):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    ld = n + (n & 1)
+    Xt = torch.empty((p, ld), dtype=torch.float64, device=dev)
+    b = torch.zeros(p, dtype=torch.float64, device=dev)
+    b[:len(coef)] = torch.tensor(coef, dtype=torch.float64, device=dev)
+    eta = torch.zeros(n, dtype=torch.float64, device=dev)
+    step = max(1, min(p, (1 << 28) // ld))
+    for j in range(0, p, step):
+        blk = Xt[j:j + step]
+        blk.normal_(0.0, sd, generator=g)
+        eta += blk[:, :n].t() @ b[j:j + step]
+    if binomial:
+        y = (torch.rand(n, generator=g, dtype=torch.float64, device=dev) < torch.sigmoid(eta)).double()
+    else:
+        y = eta + noise * torch.randn(n, generator=g, dtype=torch.float64, device=dev)
+    return Xt.t()[:n], y
+
+
+def timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    outs, ts = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        outs.append(fn())
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    return min(ts), outs[-1]
+
+
+def line(name, wall, out, extra):
+    st = out["stats"]
+    d = {"config": name, "wall_s": wall, "phases_ms": {k: round(v, 3) for k, v in st.items() if k.startswith("ms_")},
+         "oem_iterations": st["total_oem_iters"], "kernel_launches": st["kernel_launches"]}
+    if st["gram_launches"]:
+        d["gram_tflops"] = st["gram_flops"] / (st["ms_gram"] / 1e3) / 1e12
+    d.update(extra(st) if extra else {})
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3,4")
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--scale", type=float, default=1.0, help="scale n (debug)")
+    a = ap.parse_args()
+    cfgs = [int(c) for c in a.configs.split(",")]
+    opts = dict(maxit=500, tol=1e-7)
+    if 1 in cfgs:      # README.md:45-73: published 1.617 s (CPU, single thread, unstated hardware)
+        n, p = int(1e6 * a.scale), 100
+        rng = np.random.default_rng(101)
+        X, y = gen(n, p, 101, sd=3.0, coef=list(rng.uniform(0, 1, 25)))
+        args = [X, y, "gaussian", ["elastic.net"], [], [], [], [], [], 100, 1e-4, 1.0, 3.0, 0.5, np.ones(p), False, True, False,
+                dict(opts, tol=1e-10)]
+        w, out = timed(lambda: oem_b200.oem_fit_dense(*args), a.reps)
+        line("configs[0] README lasso n=1e6 p=100 (published CPU 1.617 s)", w, out, None)
+        del X, y
+    if 2 in cfgs:      # README.md:100-157: published MCP 105.8 ms, SCAD 78.8 ms (separate calls)
+        n, p = 5000, 200
+        rng = np.random.default_rng(102)
+        X, y = gen(n, p, 102, sd=3.0, coef=list(rng.uniform(-0.5, 0.5, 25)))
+        args = [X, y, "gaussian", ["mcp", "scad"], [], [], [], [], [], 200, 1e-4, 1.0, [2.0, 4.0], 0.5, np.ones(p), True, True,
+                False, dict(opts, tol=1e-10)]
+        w, out = timed(lambda: oem_b200.oem_fit_dense(*args), a.reps)
+        line("configs[1] README MCP g=2 + SCAD g=4 n=5000 p=200 L=200 batched (published CPU 105.8 + 78.8 ms)", w, out, None)
+        del X, y
+    if 3 in cfgs:
+        n, p, F = int(1e7 * a.scale), 500, 10
+        X, y = gen(n, p, 103, coef=[.5, .5, -.5, -.5, 1.0], noise=4.0)
+        rng = np.random.default_rng(103)
+        foldid = (1 + rng.permutation(n) % F).astype(np.int32)
+        groups = np.concatenate([[0], np.repeat(np.arange(1, 51), 10)])
+        args = [X, y, "gaussian", ["lasso", "grp.lasso", "mcp"], [], groups, np.unique(groups), [], [], 100, 1e-4, 1.0, 3.0, 0.5,
+                np.ones(p), True, True, F, foldid, False, "mse", dict(opts)]
+        w, out = timed(lambda: oem_b200.oem_xval_dense(*args), a.reps)
+        line("configs[2] xval.oem 10-fold lasso+grp.lasso+mcp n=1e7 p=500", w, out,
+             lambda st: {"cvscore_tflops": 2.0 * n * p * 300 / (st["ms_cvscore"] / 1e3) / 1e12,
+                         "cvm_min_lasso": float(np.min(out["cvm"][0]))})
+        del X, y
+    if 4 in cfgs:
+        n, p = int(2e6 * a.scale), 1000
+        X, y = gen(n, p, 104, coef=[.15, .15, -.15, -.15, .25], binomial=True)
+        args = [X, y, "binomial", ["lasso"], [], [], [], [], [], 100, 1e-4, 1.0, 3.0, 0.5, np.ones(p), True, True, False, dict(opts)]
+        w, out = timed(lambda: oem_b200.oem_fit_logistic_dense(*args), max(1, a.reps - 1))
+        line("configs[3] logistic lasso n=2e6 p=1000", w, out,
+             lambda st: {"xb_gbs": (8.0 * n * p + 8.0 * (n + p)) * st["xb_launches"] / (st["ms_irls_xb"] / 1e3) / 1e9,
+                         "xtr_gbs": (st["gemv_bytes"] / 2) / (st["ms_irls_xtr"] / 1e3) / 1e9,
+                         "irls_iterations": int(np.sum(out["niter"][0])), "xb_launches": st["xb_launches"]})
+        del X, y
+    torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
