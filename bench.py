@@ -227,8 +227,13 @@ def run_ours(args):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(stream)
-        outs = [fn() for _ in range(steps)]
+        outs, walls = [], []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            outs.append(fn())
+            walls.append(round((time.perf_counter() - t0) * 1e3, 2))
         e.record(stream)
+        timed.last_walls = walls
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=device)
         if world > 1:
@@ -246,6 +251,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     ms_step, outs = timed(step_dev, args.steps)
+    walls_dev = timed.last_walls
     clocks = sampler.stop()
     st = outs[-1]["stats"]
     gram_ms = float(np.mean([o["stats"]["ms_gram"] / max(1, o["stats"]["gram_launches"]) for o in outs]))
@@ -258,7 +264,8 @@ def run_ours(args):
             "config": {"workload": workload_name(world, rows), "l2": "inputs (100 GB/GPU) exceed L2; no flush needed",
                        "phases_ms": {k: st[k] for k in ("ms_colstats", "ms_gram", "ms_gram_reduce", "ms_allreduce",
                                                         "ms_assemble", "ms_path", "ms_total")},
-                       "oem_iterations": st["total_oem_iters"], "lanczos_steps": st["lanczos_steps"]},
+                       "oem_iterations": st["total_oem_iters"], "lanczos_steps": st["lanczos_steps"],
+                       "host_wall_ms_per_step": walls_dev, "lib_ms_total_per_step": [round(o["stats"]["ms_total"], 2) for o in outs]},
             "clocks": clocks, "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "roofline": {"bound": "tensor", "kernel": "gram_syrk_kernel (FP64 DMMA.8x8x4, TMA-staged)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,

@@ -17,7 +17,9 @@
 //
 // Work decomposition.  Output tile = 128 x 128 (pair of column panels pi >= pj), 8 consumer warps
 // in a 2 x 4 grid with 64 x 32 warp tiles (64 accumulator doubles per thread); thread 0 doubles as the
-// TMA producer (a 9th warp would cap the kernel at 168 registers).
+// TMA producer (a 9th warp would cap the kernel at 168 registers).  Diagonal tiles (pi == pj) compute
+// only their lower triangle: warp w owns atom rows w and 15-w of the 16 x 16 atom grid (17 atoms each),
+// so a diagonal tile costs 17/32 of an off-diagonal one instead of wasting its upper half.
 // A work item = (tile, row range); the host builds the item list row-range-major so CTAs that run
 // together stream the same rows (panel reuse in L2).  Every item writes its partial tile to a
 // workspace slot; gram_reduce_kernel sums the slots of a tile in a fixed order (deterministic,
@@ -105,8 +107,9 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
     for (int kt = 0; kt < G_STAGES && kt < nk; ++kt) load_tile(kt);
 
     // ===================== consumer warps =====================
-    const int wm = warp >> 2, wn = warp & 3;
     const int g = lane >> 2, t = lane & 3;
+    if (!diag) {
+    const int wm = warp >> 2, wn = warp & 3;
     int offA[8], offB[4];
 #pragma unroll
     for (int ma = 0; ma < 8; ++ma) offA[ma] = (wm * 64 + ma * 8 + g) * G_KT + t;
@@ -198,6 +201,90 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
             const int j = wn * 32 + na * 8 + 2 * t;
             slot[(size_t)j * G_TILE + i] = acc[ma][na][0];
             slot[(size_t)(j + 1) * G_TILE + i] = acc[ma][na][1];
+        }
+    }
+        return;
+    }
+
+    // ===================== diagonal tile: lower triangle only =====================
+    // The 128 x 128 tile is 16 x 16 atoms of 8 x 8; only the 136 atoms on or below the diagonal are needed.
+    // Warp w takes atom rows w and 15-w: (w+1) + (16-w) = 17 atoms each, a perfectly balanced triangle.
+    // Slot s < = w is atom (w, s); slot s > w is atom (15-w, s-w-1).
+    {
+        const int rlo = warp, rhi = 15 - warp;
+        const int offAlo = (rlo * 8 + g) * G_KT + t, offAhi = (rhi * 8 + g) * G_KT + t;
+        int offS[17];
+#pragma unroll
+        for (int sl = 0; sl < 17; ++sl) {
+            const int col = sl <= warp ? sl : sl - warp - 1;
+            offS[sl] = (col * 8 + g) * G_KT + t;
+        }
+        double mlo = 0.0, mhi = 0.0, mS[17];
+        if (CENTER) {
+            const int clo = it.pi * G_TILE + rlo * 8 + g, chi = it.pi * G_TILE + rhi * 8 + g;
+            mlo = clo < q ? mean[clo] : 0.0;
+            mhi = chi < q ? mean[chi] : 0.0;
+#pragma unroll
+            for (int sl = 0; sl < 17; ++sl) {
+                const int col = sl <= warp ? sl : sl - warp - 1;
+                const int c = it.pi * G_TILE + col * 8 + g;
+                mS[sl] = c < q ? mean[c] : 0.0;
+            }
+        }
+        double acc[17][2];
+#pragma unroll
+        for (int sl = 0; sl < 17; ++sl) acc[sl][0] = acc[sl][1] = 0.0;
+
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt % G_STAGES;
+            const uint32_t ph = (kt / G_STAGES) & 1;
+            const long long rbase = it.row0 + (long long)kt * G_KT + t;
+            double wv[G_KSTEPS];
+            if (WEIGHT) {
+#pragma unroll
+                for (int ks = 0; ks < G_KSTEPS; ++ks) {
+                    const long long r = rbase + ks * 4;
+                    wv[ks] = r < nrows ? __ldg(roww + r) : 0.0;
+                }
+            }
+            const bool tail = CENTER && (it.row0 + (long long)(kt + 1) * G_KT > nrows);
+            mbar_wait(&full[s], ph);
+            const double *pA = panels + (size_t)s * 2 * G_PANEL;
+#pragma unroll
+            for (int ks = 0; ks < G_KSTEPS; ++ks) {
+                double alo = pA[offAlo + ks * 4], ahi = pA[offAhi + ks * 4];
+                const bool valid = !tail || (rbase + ks * 4 < nrows);
+                if (CENTER) { alo -= mlo; ahi -= mhi; }
+                if (WEIGHT) { alo *= wv[ks]; ahi *= wv[ks]; }
+#pragma unroll
+                for (int sl = 0; sl < 17; ++sl) {
+                    double b = pA[offS[sl] + ks * 4];
+                    if (CENTER) b = valid ? b - mS[sl] : 0.0;
+                    dmma884(acc[sl][0], acc[sl][1], sl <= warp ? alo : ahi, b);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (kt + G_STAGES < nk) {
+                if (USE_TMA) {
+                    if (threadIdx.x == 0) {
+                        mbar_wait(&empty[s], ph);
+                        load_tile(kt + G_STAGES);
+                    }
+                } else {
+                    mbar_wait(&empty[s], ph);
+                    load_tile(kt + G_STAGES);
+                }
+            }
+        }
+        double *slot = ws + (size_t)it.slot * (G_TILE * G_TILE);
+#pragma unroll
+        for (int sl = 0; sl < 17; ++sl) {
+            const int row = sl <= warp ? rlo : rhi;
+            const int col = sl <= warp ? sl : sl - warp - 1;
+            const int i = row * 8 + g, j = col * 8 + 2 * t;
+            slot[(size_t)j * G_TILE + i] = acc[sl][0];
+            slot[(size_t)(j + 1) * G_TILE + i] = acc[sl][1];
         }
     }
 }

@@ -17,13 +17,15 @@ Ctx::Ctx(const oemb200_opts *o) {
         OEM_CUDA(cudaSetDevice(o->device));
     }
     OEM_CUDA(cudaGetDevice(&device));
-    cudaDeviceProp prop;
-    OEM_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        fail(OEMB200_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
-             prop.minor);
-    num_sms = prop.multiProcessorCount;
-    smem_optin = prop.sharedMemPerBlockOptin;
+    int major = 0, minor = 0, sms = 0, optin = 0;      // cudaGetDeviceProperties is milliseconds; these are microseconds
+    OEM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    OEM_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    OEM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    OEM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (major < 10)
+        fail(OEMB200_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, major, minor);
+    num_sms = sms;
+    smem_optin = (size_t)optin;
     if (o && o->stream) {
         stream = static_cast<cudaStream_t>(o->stream);
         own_stream = false;
