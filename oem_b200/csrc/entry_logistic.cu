@@ -11,6 +11,7 @@
 // first IRLS iteration of a warm lambda, W is clamped at index = IRLS counter, eigen factor 1.0005.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "host_common.h"
 
@@ -115,7 +116,11 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     DBuf<double> bh(nbh), d_nobs(1);
     d_nobs.upload(&n_tot, 1, cx.stream);
     DBuf<double> gradb(3 * (size_t)p + 2);   // [stats 3p | sum r, sum r^2]
-    DBuf<double> d_losspart(1024);
+    DBuf<double> d_losspart(1024), gfused((size_t)p + 1);
+    // Default: two HBM-bound sweeps (xb_kernel + colstats_kernel), each at ~100 % of the measured HBM bandwidth.
+    // OEMB200_LOGIT_FUSED=1 selects the single-HBM-sweep kernel (logit_fused.cu): it reads X from HBM once but
+    // streams it over the L2 fabric twice and is bound there (measured 4.2 ms vs 4.65 ms per pass at config 4).
+    const bool fused = getenv("OEMB200_LOGIT_FUSED") != nullptr && logit_fused_supported(X.p, n, p, X.ld);
 
     const int L = su.Lmax;
     fill_common_outputs(su, res);
@@ -136,10 +141,18 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                 if (!(it == 0 && !on_lam_1)) {
                     for (int j = 0; j < p; ++j) hb[j] = stdz ? beta[icpt + j] * cinv[j] : beta[icpt + j];
                     d_b.upload(hb.data(), p, cx.stream);
-                    const size_t t1 = tm.start(&cx.st.ms_irls_xb);
-                    xb_launch(cx, X.p, n, p, X.ld, d_b.p, icpt ? beta[0] : 0.0, yv.p, nullptr, d_prob.p, d_res.p, d_W.p, true);
-                    tm.stop(t1);
-                    cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
+                    if (fused) {
+                        // one kernel, X read from HBM once: prob, W and the gradient sums [sum r, X'r]
+                        const size_t t1 = tm.start(&cx.st.ms_irls_xb);
+                        logit_fused_launch(cx, X.p, n, p, X.ld, d_b.p, icpt ? beta[0] : 0.0, yv.p, d_prob.p, d_W.p, gfused.p);
+                        tm.stop(t1);
+                        cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (3.0 * n + 2.0 * p);
+                    } else {
+                        const size_t t1 = tm.start(&cx.st.ms_irls_xb);
+                        xb_launch(cx, X.p, n, p, X.ld, d_b.p, icpt ? beta[0] : 0.0, yv.p, nullptr, d_prob.p, d_res.p, d_W.p, true);
+                        tm.stop(t1);
+                        cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
+                    }
                     if (o->rank == 0 && it < n) {            // W(i) clamp, sic (oem_logistic_dense.h:953-959)
                         clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, it, 1e-5);
                         cx.st.kernel_launches += 1;
@@ -161,14 +174,24 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                                             nullptr, nullptr);
                         rebuilt = true;
                     }
-                    const size_t t2 = tm.start(&cx.st.ms_irls_xtr);
-                    colstats_launch(cx, X.p, n, p, X.ld, d_res.p, nullptr, nullptr, gradb.p, false);
-                    vecsum_launch(cx, d_res.p, n, 0.0, gradb.p + 3 * (size_t)p, false);
-                    tm.stop(t2);
-                    cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
-                    cx.all_reduce(gradb.p, (int64_t)(3 * (size_t)p + 2));
-                    gradb.download(hgrad.data(), hgrad.size(), cx.stream);
-                    cx.sync();
+                    if (fused) {
+                        cx.all_reduce(gfused.p, (int64_t)p + 1);
+                        gfused.download(hgrad.data(), (size_t)p + 1, cx.stream);
+                        cx.sync();
+                        // same layout as the two-kernel route below: hgrad[j] = X'r, hgrad[3p] = sum r
+                        const double sr = hgrad[0];
+                        for (int j = 0; j < p; ++j) hgrad[j] = hgrad[j + 1];
+                        hgrad[3 * (size_t)p] = sr;
+                    } else {
+                        const size_t t2 = tm.start(&cx.st.ms_irls_xtr);
+                        colstats_launch(cx, X.p, n, p, X.ld, d_res.p, nullptr, nullptr, gradb.p, false);
+                        vecsum_launch(cx, d_res.p, n, 0.0, gradb.p + 3 * (size_t)p, false);
+                        tm.stop(t2);
+                        cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
+                        cx.all_reduce(gradb.p, (int64_t)(3 * (size_t)p + 2));
+                        gradb.download(hgrad.data(), hgrad.size(), cx.stream);
+                        cx.sync();
+                    }
                     if (icpt) gvec[0] = hgrad[3 * (size_t)p] / n_tot;
                     for (int j = 0; j < p; ++j) {
                         double g = hgrad[j] / n_tot;

@@ -181,6 +181,12 @@ void scale_sym_launch(Ctx &cx, int p, const double *sinv, const double *XXin, co
 // y = M x + add for a symmetric q x q M
 void symv_add_launch(Ctx &cx, int q, const double *M, const double *x, const double *add, double *y);
 
+// ---------------- logit_fused.cu ----------------
+bool logit_fused_supported(const double *X, int64_t n, int p, int64_t ld);
+// prob, w (may be NULL) and grad_out[0] = sum (y - prob), grad_out[1 + j] = sum_i x_ij (y_i - prob_i), one sweep of X
+void logit_fused_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const double *b, double b0,
+                        const double *y, double *prob, double *w, double *grad_out);
+
 // ---------------- cvscore.cu ----------------
 void fold_gather_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const int *dest, double *Xs,
                         int64_t lds, const double *y, double *ys);

@@ -105,8 +105,8 @@ def main():
         args = [X, y, "binomial", ["lasso"], [], [], [], [], [], 100, 1e-4, 1.0, 3.0, 0.5, np.ones(p), True, True, False, dict(opts)]
         w, out = timed(lambda: oem_b200.oem_fit_logistic_dense(*args), max(1, a.reps - 1))
         line("configs[3] logistic lasso n=2e6 p=1000", w, out,
-             lambda st: {"xb_gbs": (8.0 * n * p + 8.0 * (n + p)) * st["xb_launches"] / (st["ms_irls_xb"] / 1e3) / 1e9,
-                         "xtr_gbs": (st["gemv_bytes"] / 2) / (st["ms_irls_xtr"] / 1e3) / 1e9,
+             lambda st: {"data_pass_gbs": st["gemv_bytes"] / ((st["ms_irls_xb"] + st["ms_irls_xtr"]) / 1e3) / 1e9,
+                         "ms_per_irls_data_pass": (st["ms_irls_xb"] + st["ms_irls_xtr"]) / max(1, st["xb_launches"]),
                          "irls_iterations": int(np.sum(out["niter"][0])), "xb_launches": st["xb_launches"]})
         del X, y
     torch.cuda.empty_cache()
