@@ -1,0 +1,105 @@
+"""-m gpu: BASELINE-scale checks through size-independent properties (the CPU oracle cannot run these sizes):
+Gram symmetry / linearity in the row range / diagonal == column sums of squares / quadratic forms == ||Xv||^2,
+lasso KKT conditions of the returned path, and the closed form of the cross-validation score at lambda_max.
+Independent arithmetic comes from torch (cuBLAS FP64) on the same device-resident data."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(torch, n, p, seed, coef, noise=1.0):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    Xt = torch.empty((p, n), dtype=torch.float64, device="cuda")
+    b = torch.zeros(p, dtype=torch.float64, device="cuda")
+    b[:len(coef)] = torch.tensor(coef, dtype=torch.float64, device="cuda")
+    y = noise * torch.randn(n, generator=g, dtype=torch.float64, device="cuda")
+    for j in range(0, p, 50):
+        Xt[j:j + 50].normal_(generator=g)
+        y += Xt[j:j + 50].t() @ b[j:j + 50]
+    return Xt, y          # Xt[j] = column j of X; X = Xt.t() is column-major
+
+
+def _gram(lib, torch, Xt, n0, n1, mean=None, w=None):
+    L = lib.load()
+    p, ld = Xt.shape
+    G = torch.empty((p, p), dtype=torch.float64, device="cuda")
+    ms = ctypes.c_double()
+    rc = L.oemb200_gram(Xt.data_ptr() + 8 * n0, n1 - n0, p, ld, mean.data_ptr() if mean is not None else None,
+                        (w.data_ptr() + 8 * n0) if w is not None else None, G.data_ptr(),
+                        torch.cuda.current_stream().cuda_stream, ctypes.byref(ms))
+    assert rc == 0, L.oemb200_last_error()
+    return G, ms.value
+
+
+def test_gram_properties_at_shard_scale(lib):
+    import torch
+    n, p = 1_000_008, 1000            # 8 GB, rows a multiple of 72
+    Xt, y = _gen(torch, n, p, 5, [0.3, -0.2, 0.1])
+    G, ms = _gram(lib, torch, Xt, 0, n)
+    assert torch.equal(G, G.t())                                          # mirrored lower triangle
+    sq = (Xt * Xt).sum(dim=1)
+    assert torch.allclose(torch.diagonal(G), sq, rtol=1e-12, atol=0)      # diag = column sums of squares
+    half = 72 * 6000
+    G1, _ = _gram(lib, torch, Xt, 0, half)
+    G2, _ = _gram(lib, torch, Xt, half, n)
+    assert torch.allclose(G, G1 + G2, rtol=1e-12, atol=1e-9)              # linear in the row range (the all-reduce invariant)
+    blk = Xt[700:828] @ Xt[100:228].t()                                   # independent cuBLAS FP64 block
+    assert torch.allclose(G[700:828, 100:228], blk, rtol=1e-11, atol=1e-8)
+    v = torch.randn(p, dtype=torch.float64, device="cuda")
+    assert abs(float(v @ G @ v) / float(((Xt.t() @ v) ** 2).sum()) - 1.0) < 1e-12
+    # centred + row-weighted variant (the oem_fit_dense / logistic X'WX modes)
+    mean = Xt.mean(dim=1)
+    w = torch.rand(n, dtype=torch.float64, device="cuda")
+    Gc, _ = _gram(lib, torch, Xt, 0, n, mean=mean, w=w)
+    blk = ((Xt[0:64] - mean[0:64, None]) * w) @ (Xt[900:964] - mean[900:964, None]).t()
+    assert torch.allclose(Gc[0:64, 900:964], blk, rtol=1e-10, atol=1e-7)
+    tflops = n * p * (p + 1.0) / (ms / 1e3) / 1e12
+    assert tflops > 15.0, f"Gram kernel far below its roofline: {tflops:.1f} TFLOP/s"
+
+
+def test_big_fit_kkt_at_scale(lib):
+    import torch
+    n, p = 1_000_000, 500
+    rng = np.random.default_rng(105)
+    Xt, y = _gen(torch, n, p, 105, list(rng.uniform(-0.5, 0.5, 25)))
+    X = Xt.t()
+    out = lib.oem_fit_big(X, y, "gaussian", ["lasso"], [], [], [], [], [], 30, 1e-3, 1.0, 3.0, 0.5, np.ones(p), True, True,
+                          False, dict(maxit=2000, tol=1e-10))
+    B, lam = out["beta"][0], out["lambda_"][0]
+    w = 1.0 / torch.sqrt((Xt * Xt).sum(dim=1) / (n - 1.0))               # uncentred big.oem scaling
+    assert np.all(B[1:, 0] == 0.0)                                        # lambda_max: null model
+    for i in (5, 15, 29):
+        beta = torch.from_numpy(np.ascontiguousarray(B[1:, i])).cuda()
+        resid = y - B[0, i] - X @ beta
+        grad = (Xt @ resid) * w / n                                       # gradient w.r.t. the standardised coefficients
+        act = beta != 0
+        assert float((grad[act] - lam[i] * torch.sign(beta[act])).abs().max()) < 1e-6 * lam[0]
+        assert float(grad[~act].abs().max()) <= lam[i] * (1 + 1e-6)
+        assert abs(float(resid.sum())) / n < 1e-7                         # unpenalised intercept: zero mean residual
+    assert out["d"] > 0 and np.all(out["niter"][0] <= 2000)
+
+
+def test_xval_closed_form_at_lambda_max(lib):
+    import torch
+    n, p, F = 2_000_000, 200, 10
+    Xt, y = _gen(torch, n, p, 103, [0.5, 0.5, -0.5, -0.5, 1.0], noise=4.0)
+    rng = np.random.default_rng(103)
+    foldid = (1 + rng.permutation(n) % F).astype(np.int32)
+    out = lib.oem_xval_dense(Xt.t(), y, "gaussian", ["lasso"], [], [], [], [], [], 20, 1e-3, 1.0, 3.0, 0.5, np.ones(p), True,
+                             True, F, foldid, False, "mse", dict(maxit=500, tol=1e-7))
+    # at lambda_max every fold's model is the intercept-only fit on the other folds: pred_i = mean(y not in fold(i))
+    f = torch.from_numpy(foldid).cuda().long() - 1
+    s = torch.zeros(F, dtype=torch.float64, device="cuda").index_add_(0, f, y)
+    c = torch.bincount(f, minlength=F).double()
+    mu = (s.sum() - s) / (c.sum() - c)
+    t = (y - mu[f]) ** 2
+    cvm0 = float(t.mean())
+    cvsd0 = float(torch.sqrt(((t - t.mean()) ** 2).sum() / (n - 1.0)) / np.sqrt(n))
+    # lambda_max is computed from the full data; a left-out-fold model may keep a coefficient barely alive there
+    assert abs(out["cvm"][0][0] / cvm0 - 1.0) < 1e-4
+    assert abs(out["cvsd"][0][0] / cvsd0 - 1.0) < 1e-3
+    assert np.all(np.diff(out["lambda_"][0]) < 0) and np.argmin(out["cvm"][0]) > 0
