@@ -69,7 +69,7 @@ typedef struct oemb200_opts {
     double gigs;           /* big.oem `gigs`: here = host->device streaming chunk size in GB (<=0: 1 GB) */
     /* ---- runtime (not in the reference) ---- */
     int    device;         /* CUDA device ordinal; -1 = current device */
-    void  *stream;         /* cudaStream_t to run on; NULL = a private stream */
+    void  *stream;         /* cudaStream_t to run on; NULL = the legacy default stream */
     oemb200_allreduce_fn allreduce;  /* row-sharded multi-process runs; NULL = single process */
     void  *allreduce_ctx;
     int    rank, world;    /* informational (world<=1: single process) */

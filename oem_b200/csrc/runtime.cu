@@ -26,13 +26,10 @@ Ctx::Ctx(const oemb200_opts *o) {
         fail(OEMB200_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, major, minor);
     num_sms = sms;
     smem_optin = (size_t)optin;
-    if (o && o->stream) {
-        stream = static_cast<cudaStream_t>(o->stream);
-        own_stream = false;
-    } else {
-        OEM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        own_stream = true;
-    }
+    // NULL means the legacy default stream (like any CUDA library call without a stream argument): work is then
+    // ordered after whatever the host program queued there (e.g. torch kernels that produced a device-resident X).
+    stream = (o && o->stream) ? static_cast<cudaStream_t>(o->stream) : cudaStreamLegacy;
+    own_stream = false;
     if (o) { allreduce = o->allreduce; allreduce_ctx = o->allreduce_ctx; }
     tm = new PhaseTimers(stream);
 }
