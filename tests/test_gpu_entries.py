@@ -186,3 +186,43 @@ def test_golden_on_gpu(lib):
         if "cvm_checksum" in ref:
             assert np.allclose(got["cvm_checksum"], ref["cvm_checksum"], rtol=1e-9), name
             assert np.allclose(got["cvsd_checksum"], ref["cvsd_checksum"], rtol=1e-8), name
+
+
+@pytest.mark.parametrize("n,p", [(40, 1), (50, 3), (200, 7), (300, 129), (77, 8)])
+def test_ragged_shapes(lib, oracle, n, p):
+    # columns not a multiple of the 8-wide MMA atom / 128-wide panel, odd and tiny row counts
+    X, y = gaussian_problem(n + p, n, p)
+    a = args_xy(X, y, "gaussian", ["lasso", "ols"], nlambda=8, opts=dict(tol=1e-9))
+    assert_same_fit(lib.oem_fit_dense(*a), oracle.oem_fit_dense(*a))
+    assert_same_fit(lib.oem_fit_big(*a), oracle.oem_fit_big(*a))
+
+
+def test_constant_column_and_single_lambda(lib, oracle):
+    X, y = gaussian_problem(31, 500, 6)
+    X[:, 2] = 0.0                       # zero column: scale 0 -> 1 in every standardisation convention
+    X[:, 4] = 3.0                       # constant column: centred norm 0 -> scale 1 (DataStd), non-zero uncentred norm
+    a = args_xy(X, y, "gaussian", ["lasso"], lambda_=[np.array([0.05])], opts=dict(tol=1e-9))
+    got, ref = lib.oem_fit_dense(*a), oracle.oem_fit_dense(*a)
+    assert got["beta"][0].shape == (7, 1)
+    assert_same_fit(got, ref)
+    assert_same_fit(lib.oem_fit_big(*a), oracle.oem_fit_big(*a))
+
+
+def test_maxit_exhausted_reports_maxit_plus_one(lib, oracle):
+    X, y = gaussian_problem(32, 400, 30, mean_x=2.0)      # large mean + intercept column: slow convergence
+    a = args_xy(X, y, "gaussian", ["lasso"], nlambda=6, standardize=False, opts=dict(maxit=5, tol=1e-12))
+    got, ref = lib.oem_fit_big(*a), oracle.oem_fit_big(*a)
+    assert np.array_equal(got["niter"][0], ref["niter"][0]) and got["niter"][0].max() == 6     # src/oem_base.h:94-109
+    assert_same_fit(got, ref)
+
+
+def test_unsupported_paths_fail_loudly(lib):
+    X, y = gaussian_problem(1, 20, 30)           # n <= p: XX' branch is outside the hot path
+    with pytest.raises(lib.OemB200Error) as ei:
+        lib.oem_fit_dense(*args_xy(X, y, "gaussian", ["lasso"]))
+    assert ei.value.code == 4
+    Xs, ys = gaussian_problem(1, 200, 5)
+    a = args_xy(Xs, ys, "gaussian", ["lasso"])
+    bad = a[:17] + [3, np.array([0] * 200), False, "mse", a[18]]
+    with pytest.raises(lib.OemB200Error, match="foldid"):
+        lib.oem_xval_dense(*bad)
