@@ -42,7 +42,9 @@ class Comm:
             import torch
             self.calls += 1
             self.doubles += int(count)
-            ext = torch.cuda.ExternalStream(int(stream)) if stream else torch.cuda.current_stream()
+            # 0 / 1 / 2 are the CUDA handles of the null, legacy-default and per-thread default streams
+            sid = int(stream) if stream else 0
+            ext = torch.cuda.default_stream() if sid in (0, 1) else torch.cuda.ExternalStream(sid)
             with torch.cuda.stream(ext):
                 t = _wrap_device_f64(buf, int(count))
                 self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)

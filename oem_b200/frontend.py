@@ -1,0 +1,261 @@
+"""R front-end mirrors: oem(), oem_xtx(), xval_oem(), big_oem() with the reference's
+argument names, defaults, validation and post-processing, on top of the C-ABI entries of oem_b200.api.
+
+    R/oem.R:162-507        oem()        -> oem_fit_dense / oem_fit_logistic_dense
+    R/oem_xtx.R:109-455    oem.xtx()    -> oem_xtx
+    R/oem_xval.R:107-460   xval.oem()   -> oem_xval_dense  (+ getmin, cvup / cvlo: R/utils.R:3-26)
+    R/big_oem.R:121-543    big.oem()    -> oem_fit_big     (x: ndarray, np.memmap of a big.matrix .bk file, or a
+                                                            column-major CUDA tensor)
+
+What the R functions do around .Call and this module reproduces: argument checks and their error messages,
+defaults (tol 1e-7, maxit 500, nlambda 100, lambda.min.ratio 1e-4 if n >= p else 0.01, gamma 3, alpha 1, tau 0.5,
+irls.tol 1e-3, irls.maxit 100), the group bookkeeping (sorted unique groups, group 0 = unpenalised, the extra
+group-0 entry for an explicit intercept column), lambda list normalisation (sorted decreasing, one vector per
+penalty), `nzero` per lambda, and for xval.oem lambda.min / lambda.1se / cvup / cvlo / best.model.
+Dots in R argument names become underscores.  Results are dicts keyed like the R lists.
+"""
+import numpy as np
+
+from . import api
+
+PENALTIES = ["elastic.net", "lasso", "ols", "mcp", "scad", "mcp.net", "scad.net", "grp.lasso", "grp.lasso.net",
+             "grp.mcp", "grp.scad", "grp.mcp.net", "grp.scad.net", "sparse.grp.lasso"]
+
+
+def _match_penalty(penalty):
+    if penalty is None:
+        return ["elastic.net"]          # match.arg(several.ok = FALSE) on the default vector picks the first
+    pens = [penalty] if isinstance(penalty, str) else list(penalty)
+    for p in pens:
+        if p not in PENALTIES:
+            raise ValueError(f"'arg' should be one of {PENALTIES}")
+    return pens
+
+
+def _shape(x):
+    if hasattr(x, "shape") and len(x.shape) == 2:
+        return int(x.shape[0]), int(x.shape[1])
+    raise ValueError("x must have at least two columns")
+
+
+def _groups(penalty, groups, group_weights, p, explicit_intercept):
+    """R/oem.R:282-345 (and the same block in R/big_oem.R:208-264, R/oem_xval.R)."""
+    if not any("grp" in pen for pen in penalty):
+        return np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0)
+    groups = np.asarray(groups).ravel()
+    if groups.size != p:
+        raise ValueError("If any group penalty is used groups must have same length as number of columns in x")
+    unique_groups = np.sort(np.unique(groups))
+    has_zero = bool(np.any(unique_groups == 0))
+    if group_weights is not None:
+        gw = np.asarray(group_weights, dtype=np.float64).ravel().copy()
+        if has_zero:
+            gw[np.nonzero(unique_groups == 0)[0]] = 0.0
+        elif explicit_intercept:
+            unique_groups = np.concatenate([[0], unique_groups])
+            gw = np.concatenate([[0.0], gw])
+        if gw.size != unique_groups.size:
+            raise ValueError("group.weights must have same length as the number of groups")
+    else:
+        gw = np.zeros(0)
+        if not has_zero and explicit_intercept:
+            unique_groups = np.sort(np.concatenate([[0], unique_groups]))
+    if explicit_intercept:
+        groups = np.concatenate([[0], groups])
+    return groups.astype(np.int32), unique_groups.astype(np.int32), gw
+
+
+def _lambda_list(lambda_, npen):
+    """R/oem.R:366-404."""
+    if isinstance(lambda_, (list, tuple)) and len(lambda_) and np.ndim(lambda_[0]) >= 1:
+        if len(lambda_) != npen:
+            raise ValueError("If list of lambda vectors is provided, it must be the same length as the number of penalties fit")
+        n0 = np.asarray(lambda_[0]).size
+        out = []
+        for lv in lambda_:
+            lv = np.asarray(lv, dtype=np.float64).ravel()
+            if lv.size < 1:
+                raise ValueError("Provided lambda vector must have at least one value")
+            if lv.size != n0:
+                raise ValueError("All provided lambda vectors must have same length")
+            out.append(np.sort(lv)[::-1].copy())
+        return out
+    lv = np.sort(np.asarray(lambda_ if lambda_ is not None else [], dtype=np.float64).ravel())[::-1].copy()
+    return [lv.copy() for _ in range(npen)]
+
+
+def _common_checks(n, p, y_len, penalty_factor, lambda_min_ratio, nlambda, maxit, irls_maxit, tol, irls_tol):
+    if p < 2:
+        raise ValueError("x must have at least two columns")
+    if y_len != n:
+        raise ValueError("x and y lengths do not match")
+    pf = np.ones(p) if penalty_factor is None else np.asarray(penalty_factor, dtype=np.float64).ravel()
+    if pf.size != p:
+        raise ValueError("penalty.factor must have same length as number of columns in x")
+    if lambda_min_ratio is None:
+        lambda_min_ratio = 0.01 if n < p else 0.0001
+    lambda_min_ratio = float(lambda_min_ratio)
+    if lambda_min_ratio >= 1 or lambda_min_ratio <= 0:
+        raise ValueError("lambda.min.ratio must be between 0 and 1")
+    if int(nlambda) <= 0:
+        raise ValueError("nlambda must be a positive integer")
+    if maxit <= 0 or irls_maxit <= 0:
+        raise ValueError("maxit and irls.maxit should be positive")
+    if tol < 0 or irls_tol < 0:
+        raise ValueError("tol and irls.tol should be nonnegative")
+    return pf, lambda_min_ratio
+
+
+def nonzero_counts(beta):
+    """`nzero`: number of non-zero non-intercept coefficients per lambda (predict.oem(type = "nonzero"),
+    R/methods.R:48-119 as used at R/oem.R:495-497)."""
+    b = np.asarray(beta)
+    return np.count_nonzero(b[1:, :] if b.ndim == 2 else b[1:, None], axis=0)
+
+
+def getmin(lambda_, cvm, cvsd):
+    """R/utils.R:3-26 (modified from glmnet)."""
+    M = len(cvm)
+    lam_min, lam_1se, cv_models = np.zeros(M), np.zeros(M), np.zeros(M)
+    for m in range(M):
+        lam, c, s = np.asarray(lambda_[m])[:len(cvm[m])], np.asarray(cvm[m]), np.asarray(cvsd[m])
+        cvmin = c.min()
+        idmin = c <= cvmin
+        lam_min[m] = lam[idmin].max()
+        cv_models[m] = c[idmin].min()
+        first = int(np.nonzero(lam == lam_min[m])[0][0])
+        semin = (c + s)[first]
+        lam_1se[m] = lam[c < semin].max()
+    mmin = int(np.argmin(cv_models))
+    return dict(lambda_min=float(lam_min[mmin]), model_min=mmin + 1, lambda_1se=float(lam_1se[mmin]),
+                lambda_min_models=lam_min, lambda_1se_models=lam_1se)
+
+
+def _decorate(res, penalty, n, p, family, varnames):
+    out = dict(res)
+    out["lambda"] = out.pop("lambda_")
+    out["beta"] = {pen: b for pen, b in zip(penalty, res["beta"])}
+    out["nzero"] = [nonzero_counts(b) for b in res["beta"]]
+    out.update(nobs=n, nvars=p, penalty=list(penalty), family=family,
+               varnames=varnames or [f"V{i + 1}" for i in range(p)], rownames=["(Intercept)"] + (varnames or [f"V{i + 1}" for i in range(p)]))
+    return out
+
+
+def oem(x, y, family="gaussian", penalty=None, weights=(), lambda_=(), nlambda=100, lambda_min_ratio=None, alpha=1.0,
+        gamma=3.0, tau=0.5, groups=(), penalty_factor=None, group_weights=None, standardize=True, intercept=True,
+        maxit=500, tol=1e-7, irls_maxit=100, irls_tol=1e-3, accelerate=False, ncores=-1, compute_loss=False,
+        hessian_type="upper.bound", varnames=None, comm=None):
+    """R/oem.R:162-507.  `gamma` may also be one value per penalty (extension)."""
+    if family not in ("gaussian", "binomial"):
+        raise ValueError("'arg' should be one of 'gaussian', 'binomial'")
+    if hessian_type not in ("upper.bound", "full"):
+        raise ValueError("'arg' should be one of 'upper.bound', 'full'")
+    penalty = _match_penalty(penalty)
+    n, p = _shape(x)
+    if len(weights) > 0:
+        raise ValueError("weights not implemented yet.")
+    ylen = int(y.shape[0]) if hasattr(y, "shape") else len(y)
+    pf, lmr = _common_checks(n, p, ylen, penalty_factor, lambda_min_ratio, nlambda, maxit, irls_maxit, tol, irls_tol)
+    if family == "binomial" and not hasattr(y, "is_cuda"):
+        if np.unique(np.asarray(y)).size > 2:
+            raise ValueError("y must be a binary outcome")
+    g, ug, gw = _groups(penalty, groups, group_weights, p, explicit_intercept=(intercept and family != "gaussian"))
+    lam = _lambda_list(lambda_, len(penalty))
+    opts = dict(maxit=int(maxit), tol=float(tol), irls_maxit=int(irls_maxit), irls_tol=float(irls_tol), ncores=int(ncores),
+                hessian_type=hessian_type, accelerate=bool(accelerate))
+    fn = api.oem_fit_dense if family == "gaussian" else api.oem_fit_logistic_dense
+    res = fn(x, y, family, penalty, [], g, ug, gw, lam, int(nlambda), lmr, float(alpha), gamma, float(tau), pf,
+             bool(standardize), bool(intercept), bool(compute_loss), opts, comm=comm)
+    return _decorate(res, penalty, n, p, family, varnames)
+
+
+def big_oem(x, y, family="gaussian", penalty=None, weights=(), lambda_=(), nlambda=100, lambda_min_ratio=None,
+            alpha=1.0, gamma=3.0, tau=0.5, groups=(), penalty_factor=None, group_weights=None, standardize=True,
+            intercept=True, maxit=500, tol=1e-7, irls_maxit=100, irls_tol=1e-3, compute_loss=False, gigs=4.0,
+            hessian_type="full", varnames=None, comm=None):
+    """R/big_oem.R:121-543.  `x` plays the role of the big.matrix: an ndarray / np.memmap (see
+    oem_b200.bigmatrix.attach for .bk/.desc files) or a column-major CUDA tensor.  Only the gaussian family is
+    on the hot path (the reference's big.oem binomial branch is not)."""
+    if family != "gaussian":
+        raise NotImplementedError("big.oem family = 'binomial' is outside the hot path (SURVEY.md 8a)")
+    penalty = _match_penalty(penalty)
+    n, p = _shape(x)
+    if len(weights) > 0:
+        raise ValueError("weights not implemented yet.")
+    if getattr(x, "dtype", np.dtype("float64")) not in (np.dtype("float64"),) and not hasattr(x, "is_cuda"):
+        raise ValueError("big.matrix type must be double")                 # src/oem_big.cpp:57-62
+    ylen = int(y.shape[0]) if hasattr(y, "shape") else len(y)
+    pf, lmr = _common_checks(n, p, ylen, penalty_factor, lambda_min_ratio, nlambda, maxit, irls_maxit, tol, irls_tol)
+    g, ug, gw = _groups(penalty, groups, group_weights, p, explicit_intercept=bool(intercept))
+    lam = _lambda_list(lambda_, len(penalty))
+    opts = dict(maxit=int(maxit), tol=float(tol), irls_maxit=int(irls_maxit), irls_tol=float(irls_tol), gigs=float(gigs))
+    res = api.oem_fit_big(x, y, family, penalty, [], g, ug, gw, lam, int(nlambda), lmr, float(alpha), gamma, float(tau),
+                          pf, bool(standardize), bool(intercept), bool(compute_loss), opts, comm=comm)
+    return _decorate(res, penalty, n, p, family, varnames)
+
+
+def oem_xtx(xtx, xty, family="gaussian", penalty=None, lambda_=(), nlambda=100, lambda_min_ratio=None, alpha=1.0,
+            gamma=3.0, tau=0.5, groups=(), scale_factor=(), penalty_factor=None, group_weights=None, maxit=500,
+            tol=1e-7, irls_maxit=100, irls_tol=1e-3):
+    """R/oem_xtx.R:109-455.  xtx, xty must already be divided by n; beta has no intercept row."""
+    if family != "gaussian":
+        raise ValueError("only the gaussian family is available for oem.xtx")
+    penalty = _match_penalty(penalty)
+    n, p = _shape(xtx)
+    if n != p:
+        raise ValueError("xtx must be a square matrix")
+    xty = np.asarray(xty, dtype=np.float64).ravel() if not hasattr(xty, "is_cuda") else xty
+    # R/oem_xtx.R:225-233: lambda.min.ratio defaults to 1e-4 (n is unknown here)
+    pf, lmr = _common_checks(p + 1, p, p + 1, penalty_factor, 1e-4 if lambda_min_ratio is None else lambda_min_ratio,
+                             nlambda, maxit, irls_maxit, tol, irls_tol)
+    sf = np.asarray(scale_factor, dtype=np.float64).ravel()
+    if sf.size and sf.size != p:
+        raise ValueError("scale.factor must be same length as xty (nvars)")
+    g, ug, gw = _groups(penalty, groups, group_weights, p, explicit_intercept=False)
+    lam = _lambda_list(lambda_, len(penalty))
+    res = api.oem_xtx(xtx, xty, family, penalty, g, ug, gw, lam, int(nlambda), lmr, float(alpha), gamma, float(tau), sf, pf,
+                      dict(maxit=int(maxit), tol=float(tol), irls_maxit=int(irls_maxit), irls_tol=float(irls_tol)))
+    out = dict(res)
+    out["lambda"] = out.pop("lambda_")
+    out["beta"] = {pen: b for pen, b in zip(penalty, res["beta"])}
+    out["nzero"] = [np.count_nonzero(b, axis=0) for b in res["beta"]]
+    out.update(nvars=p, penalty=list(penalty), family=family)
+    return out
+
+
+def xval_oem(x, y, nfolds=10, foldid=None, type_measure="mse", ncores=-1, family="gaussian", penalty=None, weights=(),
+             lambda_=(), nlambda=100, lambda_min_ratio=None, alpha=1.0, gamma=3.0, tau=0.5, groups=(),
+             penalty_factor=None, group_weights=None, standardize=True, intercept=True, maxit=500, tol=1e-7,
+             irls_maxit=100, irls_tol=1e-3, compute_loss=False, varnames=None, seed=None, comm=None):
+    """R/oem_xval.R:107-460: fit + fast cross-validation in one call; adds lambda.min / lambda.1se / cvup / cvlo."""
+    if family != "gaussian":
+        raise NotImplementedError("xval.oem family = 'binomial' is outside the hot path (SURVEY.md 8a)")
+    if type_measure not in ("mse", "deviance", "mae"):
+        raise ValueError("type.measure must be 'mse', 'deviance' or 'mae' for the gaussian family")
+    penalty = _match_penalty(penalty)
+    n, p = _shape(x)
+    if len(weights) > 0:
+        raise NotImplementedError("xval.oem weights are outside the hot path (SURVEY.md 8a a9)")
+    if foldid is None:
+        rng = np.random.default_rng(seed)
+        foldid = rng.permutation(np.resize(np.arange(1, int(nfolds) + 1), n))     # sample(rep(seq(nfolds), length = n))
+    else:
+        foldid = np.asarray(foldid).ravel()
+        nfolds = int(foldid.max())
+    if nfolds < 3:
+        raise ValueError("nfolds must be bigger than 3; nfolds=10 recommended")
+    ylen = int(y.shape[0]) if hasattr(y, "shape") else len(y)
+    pf, lmr = _common_checks(n, p, ylen, penalty_factor, lambda_min_ratio, nlambda, maxit, irls_maxit, tol, irls_tol)
+    g, ug, gw = _groups(penalty, groups, group_weights, p, explicit_intercept=bool(intercept))
+    lam = _lambda_list(lambda_, len(penalty))
+    opts = dict(maxit=int(maxit), tol=float(tol), irls_maxit=int(irls_maxit), irls_tol=float(irls_tol), ncores=int(ncores))
+    res = api.oem_xval_dense(x, y, family, penalty, [], g, ug, gw, lam, int(nlambda), lmr, float(alpha), gamma, float(tau), pf,
+                             bool(standardize), bool(intercept), int(nfolds), foldid.astype(np.int32), bool(compute_loss),
+                             "mse" if type_measure == "deviance" else type_measure, opts, comm=comm)
+    out = _decorate(res, penalty, n, p, family, varnames)
+    out.update(getmin(out["lambda"], out["cvm"], out["cvsd"]))
+    out["cvup"] = [m + s for m, s in zip(out["cvm"], out["cvsd"])]
+    out["cvlo"] = [m - s for m, s in zip(out["cvm"], out["cvsd"])]
+    out["best_model"] = penalty[out["model_min"] - 1]
+    out["foldid"] = foldid
+    return out

@@ -1,0 +1,104 @@
+"""R front-end mirrors (oem_b200.frontend) and the bigmemory ingest (oem_b200.bigmatrix): host logic on CPU,
+end-to-end parity with the oracle on the GPU."""
+import numpy as np
+import pytest
+
+from cases import gaussian_problem, binomial_problem
+
+
+def test_getmin_known_answer():
+    from oem_b200.frontend import getmin
+    lam = [np.array([1.0, 0.5, 0.25, 0.125]), np.array([1.0, 0.5, 0.25, 0.125])]
+    cvm = [np.array([4.0, 2.0, 1.0, 1.5]), np.array([3.0, 0.9, 0.95, 2.0])]
+    cvsd = [np.array([0.5, 0.5, 0.6, 0.5]), np.array([0.1, 0.2, 0.1, 0.1])]
+    r = getmin(lam, cvm, cvsd)
+    # model 2 has the smaller minimum (0.9 at lambda 0.5); 1se rule: largest lambda with cvm < 0.9 + 0.2
+    assert r["model_min"] == 2 and r["lambda_min"] == 0.5 and r["lambda_1se"] == 0.5
+    assert r["lambda_min_models"].tolist() == [0.25, 0.5]
+    assert r["lambda_1se_models"].tolist() == [0.25, 0.5]       # model 1: cvm < 1.0 + 0.6 -> {1.0, 1.5} -> lambda 0.25
+
+
+def test_group_bookkeeping_and_validation():
+    from oem_b200 import frontend as fe
+    g, ug, gw = fe._groups(["grp.lasso"], [2, 2, 1, 1, 3], None, 5, explicit_intercept=False)
+    assert g.tolist() == [2, 2, 1, 1, 3] and ug.tolist() == [1, 2, 3] and gw.size == 0
+    g, ug, gw = fe._groups(["grp.lasso"], [2, 2, 1, 1, 3], None, 5, explicit_intercept=True)     # R/oem.R:318-345
+    assert g.tolist() == [0, 2, 2, 1, 1, 3] and ug.tolist() == [0, 1, 2, 3]
+    g, ug, gw = fe._groups(["grp.lasso"], [0, 2, 1, 1, 3], [9.0, 1.0, 2.0, 3.0], 5, explicit_intercept=True)
+    assert ug.tolist() == [0, 1, 2, 3] and gw.tolist() == [0.0, 1.0, 2.0, 3.0]                  # group 0 weight forced to 0
+    assert fe._groups(["lasso"], [], None, 5, True)[0].size == 0
+    with pytest.raises(ValueError, match="groups must have same length"):
+        fe._groups(["grp.lasso"], [1, 2], None, 5, False)
+    lam = fe._lambda_list([0.1, 1.0, 0.5], 2)
+    assert [l.tolist() for l in lam] == [[1.0, 0.5, 0.1]] * 2                                   # sorted decreasing
+    with pytest.raises(ValueError, match="same length as the number of penalties"):
+        fe._lambda_list([np.array([1.0])], 2)
+    X, y = gaussian_problem(1, 30, 4)
+    with pytest.raises(ValueError, match="lengths do not match"):
+        fe.oem(X, y[:-1], penalty="lasso")
+    with pytest.raises(ValueError, match="lambda.min.ratio"):
+        fe.oem(X, y, penalty="lasso", lambda_min_ratio=1.5)
+    with pytest.raises(ValueError, match="weights not implemented"):
+        fe.oem(X, y, penalty="lasso", weights=np.ones(30))
+    with pytest.raises(ValueError, match="nfolds must be bigger than 3"):
+        fe.xval_oem(X, y, nfolds=2, penalty="lasso")
+
+
+def test_bigmatrix_roundtrip(tmp_path):
+    from oem_b200 import bigmatrix
+    X, _ = gaussian_problem(3, 101, 7)
+    bk, desc = str(tmp_path / "bigmat.bk"), str(tmp_path / "bigmatk.desc")
+    bigmatrix.write(X, bk, desc)
+    d = bigmatrix.read_descriptor(desc)
+    assert (d["nrow"], d["ncol"], d["type"], d["filename"]) == (101, 7, "double", "bigmat.bk")
+    mm = bigmatrix.attach(desc)
+    assert mm.shape == (101, 7) and mm.flags["F_CONTIGUOUS"] and np.array_equal(np.asarray(mm), X)
+    assert np.array_equal(np.fromfile(bk, dtype=np.float64), X.ravel(order="F"))     # raw column-major payload
+
+
+@pytest.mark.gpu
+def test_frontends_match_oracle(lib, oracle):
+    from oem_b200 import frontend as fe
+    X, y = gaussian_problem(41, 3000, 40)
+    groups = np.repeat(np.arange(1, 9), 5)
+    r = fe.oem(X, y, penalty=["lasso", "grp.lasso"], groups=groups, nlambda=25, tol=1e-9)
+    ref = oracle.oem_fit_dense(X, y, "gaussian", ["lasso", "grp.lasso"], [], groups, np.unique(groups), [], [[], []], 25,
+                               1e-4, 1.0, 3.0, 0.5, np.ones(40), True, True, False, dict(maxit=500, tol=1e-9))
+    for i, pen in enumerate(["lasso", "grp.lasso"]):
+        assert np.max(np.abs(r["beta"][pen] - ref["beta"][i])) <= 1e-8
+        # lambda_max sits exactly on the threshold of the largest |X'y| entry (strict inequality, src/oem_dense.h:87-90):
+        # whether that coefficient is 0 or ~1e-17 depends on the last bit of lmax * scaleY / scaleY, so skip column 0
+        assert np.array_equal(r["nzero"][i][1:], np.count_nonzero(ref["beta"][i][1:], axis=0)[1:])
+        assert np.array_equal(r["nzero"][i], np.count_nonzero(r["beta"][pen][1:], axis=0))
+    assert r["nobs"] == 3000 and r["nvars"] == 40 and r["rownames"][0] == "(Intercept)"
+    # binomial: explicit intercept -> group 0 prepended by the front-end like R/oem.R:318-345
+    Xb, yb = binomial_problem(42, 3000, 20)
+    gb = np.repeat(np.arange(1, 5), 5)
+    rb = fe.oem(Xb, yb, family="binomial", penalty="grp.lasso", groups=gb, nlambda=8, lambda_min_ratio=1e-2)
+    refb = oracle.oem_fit_logistic_dense(Xb, yb, "binomial", ["grp.lasso"], [], np.concatenate([[0], gb]), np.arange(0, 5), [],
+                                         [[]], 8, 1e-2, 1.0, 3.0, 0.5, np.ones(20), True, True, False, dict(maxit=500, tol=1e-7))
+    assert np.max(np.abs(rb["beta"]["grp.lasso"] - refb["beta"][0])) <= 1e-8
+    # xval.oem: cvm / lambda.min / best model
+    rng = np.random.default_rng(7)
+    foldid = 1 + rng.permutation(3000) % 5
+    rx = fe.xval_oem(X, y, foldid=foldid, penalty=["lasso", "mcp"], nlambda=20)
+    refx = oracle.oem_xval_dense(X, y, "gaussian", ["lasso", "mcp"], [], [], [], [], [[], []], 20, 1e-4, 1.0, 3.0, 0.5,
+                                 np.ones(40), True, True, 5, foldid, False, "mse", dict(maxit=500, tol=1e-7))
+    gm = fe.getmin(refx["lambda_"], refx["cvm"], refx["cvsd"])
+    assert rx["model_min"] == gm["model_min"] and abs(rx["lambda_min"] / gm["lambda_min"] - 1) < 1e-12
+    assert rx["best_model"] in ("lasso", "mcp") and np.allclose(rx["cvup"][0], refx["cvm"][0] + refx["cvsd"][0], rtol=1e-8)
+
+
+@pytest.mark.gpu
+def test_big_oem_from_file_backed_matrix(lib, oracle, tmp_path):
+    from oem_b200 import bigmatrix, frontend as fe
+    X, y = gaussian_problem(43, 20000, 30)
+    bk, desc = str(tmp_path / "bigmat.bk"), str(tmp_path / "bigmatk.desc")
+    bigmatrix.write(X, bk, desc)
+    bigmat = bigmatrix.attach(desc)                                   # mmap'd, like attach.big.matrix()
+    r = fe.big_oem(bigmat, y, penalty=["lasso", "scad"], gamma=[3.0, 3.7], nlambda=20, gigs=0.001)   # several row chunks
+    ref = oracle.oem_fit_big(X, y, "gaussian", ["lasso", "scad"], [], [], [], [], [[], []], 20, 1e-4, 1.0, [3.0, 3.7], 0.5,
+                             np.ones(30), True, True, False, dict(maxit=500, tol=1e-7))
+    assert np.max(np.abs(r["beta"]["lasso"] - ref["beta"][0])) <= 1e-8
+    assert np.max(np.abs(r["beta"]["scad"] - ref["beta"][1])) <= 1e-8
+    assert r["stats"]["h2d_bytes"] >= X.nbytes
