@@ -38,25 +38,150 @@ struct CvItem {
     long long valid_end;  // rows >= valid_end are padding
 };
 
-// scatter rows into fold-sorted order: Xs[dest[i], j] = X[i, j]
+// Rows into fold-sorted order: Xs[dest[i], j] = X[i, j].  A CTA stages a tile of 1024 source rows x 4 columns in
+// shared memory with coalesced loads, then writes it out in the tile's fold-grouped order (`order`, built on the host
+// by a per-tile counting sort): rows of one fold are consecutive in the destination, so the stores are coalesced runs
+// of ~1024/nfolds doubles instead of isolated 8-byte writes.
+constexpr int FG_ROWS = 1024;
+constexpr int FG_COLS = 4;
+
 __global__ void __launch_bounds__(256)
 fold_gather_kernel(const double *__restrict__ X, long long n, int p, long long ld, const int *__restrict__ dest,
-                   double *__restrict__ Xs, long long lds, const double *__restrict__ y, double *__restrict__ ys) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const long long d = dest[i];
-    const int j0 = blockIdx.y * 32;
-    const int j1 = min(p, j0 + 32);
-    for (int j = j0; j < j1; ++j) Xs[(size_t)j * lds + d] = X[(size_t)j * ld + i];
-    if (blockIdx.y == 0 && y) ys[d] = y[i];
+                   const int *__restrict__ order, double *__restrict__ Xs, long long lds, const double *__restrict__ y,
+                   double *__restrict__ ys) {
+    __shared__ double tile[FG_COLS][FG_ROWS];
+    const long long r0 = (long long)blockIdx.x * FG_ROWS;
+    const int j0 = blockIdx.y * FG_COLS;
+    const int nr = (int)min((long long)FG_ROWS, n - r0);
+    const int nc = min(FG_COLS, p - j0);
+    for (int c = 0; c < nc; ++c)
+        for (int r = threadIdx.x; r < nr; r += 256) tile[c][r] = X[(size_t)(j0 + c) * ld + r0 + r];
+    __syncthreads();
+    for (int t = threadIdx.x; t < nr; t += 256) {
+        const int rl = order[r0 + t];                 // tile-local source row, fold-grouped
+        const long long d = dest[r0 + rl];
+        for (int c = 0; c < nc; ++c) Xs[(size_t)(j0 + c) * lds + d] = tile[c][rl];
+        if (blockIdx.y == 0 && y) ys[d] = y[r0 + rl];
+    }
 }
 
-void fold_gather_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const int *dest, double *Xs,
-                        int64_t lds, const double *y, double *ys) {
-    dim3 grid((unsigned)((n + 255) / 256), (p + 31) / 32);
-    fold_gather_kernel<<<grid, 256, 0, cx.stream>>>(X, n, p, ld, dest, Xs, lds, y, ys);
+void fold_gather_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const int *dest, const int *order,
+                        double *Xs, int64_t lds, const double *y, double *ys) {
+    dim3 grid((unsigned)((n + FG_ROWS - 1) / FG_ROWS), (p + FG_COLS - 1) / FG_COLS);
+    fold_gather_kernel<<<grid, 256, 0, cx.stream>>>(X, n, p, ld, dest, order, Xs, lds, y, ys);
     OEM_CUDA(cudaGetLastError());
     cx.st.kernel_launches += 1;
+}
+
+int fold_gather_tile_rows() { return FG_ROWS; }
+
+// ---- fold bucketing on the device (stable counting sort of the rows by fold, nfolds <= 64) ----
+constexpr int FB_MAXF = 64;
+
+// per-tile histogram of foldid (1-based); bad ids raise *err
+__global__ void __launch_bounds__(256)
+fold_count_kernel(const int *__restrict__ foldid, long long n, int F, int *__restrict__ tcount, int *__restrict__ err) {
+    __shared__ int hist[FB_MAXF];
+    if (threadIdx.x < FB_MAXF) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long long r0 = (long long)blockIdx.x * FG_ROWS;
+    for (int r = threadIdx.x; r < FG_ROWS && r0 + r < n; r += 256) {
+        const int f = foldid[r0 + r];
+        if (f < 1 || f > F) atomicExch(err, 1);
+        else atomicAdd(&hist[f - 1], 1);            // integer counts: order-independent, deterministic
+    }
+    __syncthreads();
+    if (threadIdx.x < F) tcount[(size_t)blockIdx.x * F + threadIdx.x] = hist[threadIdx.x];
+}
+
+// exclusive scan over tiles, one thread per fold; total[f] = rows of fold f
+__global__ void fold_scan_kernel(int *__restrict__ tcount, int ntiles, int F, long long *__restrict__ total) {
+    const int f = threadIdx.x;
+    if (f >= F) return;
+    long long run = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int c = tcount[(size_t)t * F + f];
+        tcount[(size_t)t * F + f] = (int)run;
+        run += c;
+    }
+    total[f] = run;
+}
+
+// dest[i] = foldbase[f] + (rows of fold f before i); order = tile-local rows grouped by fold (stable)
+__global__ void __launch_bounds__(256)
+fold_rank_kernel(const int *__restrict__ foldid, long long n, int F, const int *__restrict__ tprefix,
+                 const long long *__restrict__ foldbase, int *__restrict__ dest, int *__restrict__ order) {
+    __shared__ int seg[32][FB_MAXF];      // rows of fold f in 32-row segment s, then exclusive prefix over s
+    __shared__ int fstart[FB_MAXF];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r0 = (long long)blockIdx.x * FG_ROWS;
+    int myf[4], lrank[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = k * 256 + threadIdx.x;
+        const int f = (r0 + r < n) ? foldid[r0 + r] - 1 : -1;
+        myf[k] = f;
+        lrank[k] = 0;
+        for (int ff = 0; ff < F; ++ff) {
+            const unsigned m = __ballot_sync(0xffffffffu, f == ff);
+            if (f == ff) lrank[k] = __popc(m & ((1u << lane) - 1u));
+            if (lane == 0) seg[k * 8 + warp][ff] = __popc(m);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < F) {
+        int run = 0;
+        for (int sgi = 0; sgi < 32; ++sgi) { const int c = seg[sgi][threadIdx.x]; seg[sgi][threadIdx.x] = run; run += c; }
+        fstart[threadIdx.x] = run;        // tile count of this fold
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int ff = 0; ff < F; ++ff) { const int c = fstart[ff]; fstart[ff] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = k * 256 + threadIdx.x, f = myf[k];
+        if (f < 0) continue;
+        const int within = seg[k * 8 + warp][f] + lrank[k];
+        dest[r0 + r] = (int)(foldbase[f] + tprefix[(size_t)blockIdx.x * F + f] + within);
+        order[r0 + fstart[f] + within] = r;
+    }
+}
+
+// Device-side bucketing: fills dest / order (device) and counts (host).  Returns false if nfolds is too large for
+// this path (the caller then buckets on the host).
+bool fold_bucket_device(Ctx &cx, const int *foldid_dev, int64_t n, int F, int64_t align, int *dest, int *order,
+                        std::vector<int64_t> &cnt, std::vector<int64_t> &off) {
+    if (F > FB_MAXF) return false;
+    const int ntiles = (int)((n + FG_ROWS - 1) / FG_ROWS);
+    DBuf<int> tcount((size_t)ntiles * F), err(1);
+    DBuf<long long> total(F), base(F);
+    err.zero(cx.stream);
+    fold_count_kernel<<<ntiles, 256, 0, cx.stream>>>(foldid_dev, n, F, tcount.p, err.p);
+    fold_scan_kernel<<<1, FB_MAXF, 0, cx.stream>>>(tcount.p, ntiles, F, total.p);
+    OEM_CUDA(cudaGetLastError());
+    std::vector<long long> ht(F);
+    int herr = 0;
+    total.download(ht.data(), F, cx.stream);
+    err.download(&herr, 1, cx.stream);
+    cx.sync();
+    if (herr) fail(OEMB200_EINVAL, "foldid has entries outside 1..%d", F);
+    cnt.assign(F, 0);
+    off.assign(F + 1, 0);
+    std::vector<long long> hb(F);
+    for (int k = 0; k < F; ++k) {
+        cnt[k] = ht[k];
+        off[k + 1] = off[k] + (cnt[k] + align - 1) / align * align;
+        hb[k] = off[k];
+    }
+    base.upload(hb.data(), F, cx.stream);
+    fold_rank_kernel<<<ntiles, 256, 0, cx.stream>>>(foldid_dev, n, F, tcount.p, base.p, dest, order);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 3;
+    cx.sync();      // tcount / base go back to the pool
+    return true;
 }
 
 template <bool MAE>

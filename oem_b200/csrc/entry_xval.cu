@@ -38,34 +38,60 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
     Setup su;
     su.parse(s, q, q, false);
 
-    // ---- 1. fold buckets ----
+    // ---- 1. fold buckets: stable counting sort of the rows by fold (device kernels; host loops only for > 64 folds) ----
     const int64_t align = 2 * gram_kt();
     std::vector<int64_t> cnt(F, 0), off(F + 1, 0);
-    for (int64_t i = 0; i < n; ++i) {
-        const int f = foldid[i];
-        if (f < 1 || f > F) fail(OEMB200_EINVAL, "foldid[%lld] = %d outside 1..%d", (long long)i, f, F);
-        cnt[f - 1]++;
-    }
-    for (int k = 0; k < F; ++k) off[k + 1] = off[k] + (cnt[k] + align - 1) / align * align;
-    const int64_t npad = std::max<int64_t>(off[F], align);
-    if (npad >= (1ll << 31)) fail(OEMB200_EUNSUPPORTED, "xval: more than 2^31 rows per rank; shard the rows");
-    std::vector<int> dest(n);
-    {
-        std::vector<int64_t> cur(off.begin(), off.end() - 1);
-        for (int64_t i = 0; i < n; ++i) dest[i] = (int)cur[foldid[i] - 1]++;
-    }
     const size_t t_h = tm.start(&cx.st.ms_h2d);
     DevMatrix X;
     to_device_matrix(cx, x, n, p, ldx, X);
     DevVector yv;
     to_device_vector(cx, y, n, yv);
-    DBuf<int> d_dest(n);
-    d_dest.upload(dest.data(), n, cx.stream);
+    DBuf<int> d_dest(n), d_order(n), d_fold;
+    const int *fold_dev = foldid;
+    if (!is_device_ptr(foldid)) {
+        d_fold.alloc(n);
+        d_fold.upload(foldid, n, cx.stream);
+        fold_dev = d_fold.p;
+    }
     tm.stop(t_h);
+    if (!fold_bucket_device(cx, fold_dev, n, F, align, d_dest.p, d_order.p, cnt, off)) {
+        if (is_device_ptr(foldid)) fail(OEMB200_EUNSUPPORTED, "xval: more than 64 folds needs foldid on the host");
+        std::vector<int> dest(n), order(n);
+        for (int64_t i = 0; i < n; ++i) {
+            const int f = foldid[i];
+            if (f < 1 || f > F) fail(OEMB200_EINVAL, "foldid[%lld] = %d outside 1..%d", (long long)i, f, F);
+            cnt[f - 1]++;
+        }
+        for (int k = 0; k < F; ++k) off[k + 1] = off[k] + (cnt[k] + align - 1) / align * align;
+        std::vector<int64_t> cur(off.begin(), off.end() - 1);
+        for (int64_t i = 0; i < n; ++i) dest[i] = (int)cur[foldid[i] - 1]++;
+        const int64_t TR = fold_gather_tile_rows();
+        std::vector<int> c2(F + 1);
+        for (int64_t t0 = 0; t0 < n; t0 += TR) {
+            const int64_t t1 = std::min(n, t0 + TR);
+            std::fill(c2.begin(), c2.end(), 0);
+            for (int64_t i = t0; i < t1; ++i) c2[foldid[i]]++;
+            int run = 0;
+            for (int f = 1; f <= F; ++f) { const int c = c2[f]; c2[f] = run; run += c; }
+            for (int64_t i = t0; i < t1; ++i) order[t0 + c2[foldid[i]]++] = (int)(i - t0);
+        }
+        d_dest.upload(dest.data(), n, cx.stream);
+        d_order.upload(order.data(), n, cx.stream);
+        cx.sync();
+    }
+    const int64_t npad = std::max<int64_t>(off[F], align);
+    if (npad >= (1ll << 31)) fail(OEMB200_EUNSUPPORTED, "xval: more than 2^31 rows per rank; shard the rows");
     DBuf<double> Xs((size_t)npad * p), ys(npad);
-    Xs.zero(cx.stream);
+    // only the (< 72) padding rows at the end of each fold segment need zeros; the gather writes every other row
     ys.zero(cx.stream);
-    fold_gather_launch(cx, X.p, n, p, X.ld, d_dest.p, Xs.p, npad, yv.p, ys.p);
+    for (int k = 0; k < F; ++k) {
+        const int64_t pad0 = off[k] + cnt[k], npadrows = off[k + 1] - pad0;
+        if (npadrows > 0)
+            OEM_CUDA(cudaMemset2DAsync(Xs.p + pad0, (size_t)npad * 8, 0, (size_t)npadrows * 8, p, cx.stream));
+    }
+    if (off[F] < npad)
+        OEM_CUDA(cudaMemset2DAsync(Xs.p + off[F], (size_t)npad * 8, 0, (size_t)(npad - off[F]) * 8, p, cx.stream));
+    fold_gather_launch(cx, X.p, n, p, X.ld, d_dest.p, d_order.p, Xs.p, npad, yv.p, ys.p);
     X.own.release();          // the fold-sorted copy replaces the uploaded one
 
     // ---- 2. per-fold sums: bundle = [G F*p*p | stats F*3p | ysum F*2 | nobs F] ----
