@@ -69,6 +69,7 @@ struct PathArgs {
     int *niter_out, *lanczos_steps;
     double *ubuf;            // ngram x 2 x max_ct x q
     unsigned *barriers;      // ngram counters, zero-initialised
+    int *gflags;             // ngram x 2 x team_size violation masks (global mode)
     long long *prof;         // optional (debug): cycle counters of CTA 0 / thread 0
 };
 
@@ -355,28 +356,58 @@ __device__ __forceinline__ void st_cluster_f64(double *local_smem_ptr, unsigned 
 }
 
 
-// ---- mat-vec on the FP64 tensor pipe (kept out of line: the persistent loop must stay I-cache resident) ----
+// slow path of the coordinate-wise prox (non-zero result), out of line: the persistent loop must stay small
+__device__ __noinline__ double prox_coord_nonzero(int kind, double u, double tp, const double *cp, double gamma) {
+    const double dp = cp[1], rdp = cp[4], gammad = cp[5], den2 = cp[6], rden2 = cp[7];
+    if (kind == 2) return st_scad_r(u, tp, dp, rdp, gamma, gammad, den2, rden2);
+    if (kind == 1) return st_mcp_r(u, tp, dp, rdp, gammad, den2, rden2);
+    return st_lasso_r(u, tp, dp, rdp);
+}
+
+// ---- mat-vec on the FP64 tensor pipe with the prox / stop rule fused into its epilogue ----
 struct MvCtx {
-    const double *Amine, *xy;
-    double *part, *us0, *ub;
-    int q, qs, c0, c1, natm, nvec, max_ct, team_size, nbuf;
+    const double *Amine, *xy, *pf, *cpar, *gam;
+    const int *kind;          // per chain: 0 lasso-type, 1 mcp, 2 scad, 3 ols
+    double *part, *ub;
+    int *violw;               // shared word: bit c set when chain c's stop rule is violated somewhere in my slice
+    int q, qs, c0, c1, natm, max_ct, team_size;
+    double tol;
 };
 
 template <int MODE>
-__device__ __forceinline__ void mv_publish(const MvCtx &m, int par, int c, int j, double val) {
-    double *dst = m.us0 + ((size_t)(par & (m.nbuf - 1)) * m.nvec + c) * m.qs + j;
+__device__ __forceinline__ void mv_publish(const MvCtx &m, double *dst_local, int par, int c, int j, double val) {
+    double *dst = dst_local + (size_t)c * m.qs + j;
     if (MODE == MODE_SINGLE) *dst = val;
     else if (MODE == MODE_CLUSTER) {
         for (int r = 0; r < m.team_size; ++r) st_cluster_f64(dst, (unsigned)r, val);
     } else m.ub[((size_t)par * m.max_ct + c) * m.q + j] = val;
 }
 
-// u[c][j] = sum_i S[i][j] vec_c[i] (+ xy[j]) for my columns j and nv vectors.
+// Chains in `fastmask` get their coordinate-wise prox (src/oem_dense.h:527-629) and stop rule (src/utils.cpp:537-549)
+// right here, on the one member that owns column j: the published value is then the NEXT BETA, not u.
+__device__ __forceinline__ double mv_finish(const MvCtx &m, unsigned fastmask, const double *prev, int c, int j, double u) {
+    if (!((fastmask >> c) & 1u)) return u;
+    const double *cp = m.cpar + c * 8;
+    const int kind = m.kind[c];
+    const double tp = m.pf[j] * cp[0];
+    double r = 0.0;
+    if (kind == 3) r = div_r(u, cp[1], cp[4]);
+    else if (abs_gt(u, tp * cp[2])) r = prox_coord_nonzero(kind, u, tp, cp, m.gam[c]);   // else every rule returns 0
+    const double pv = prev[(size_t)c * m.qs + j];
+    if (__double_as_longlong(r) != __double_as_longlong(pv)) {      // identical bit patterns (0 -> 0) need no arithmetic
+        const bool bc = abs_gt(r, 1e-13), bp = abs_gt(pv, 1e-13);
+        if (bc != bp || (bc && abs_gt(r - pv, m.tol * fabs(pv)))) atomicOr(m.violw, 1 << c);   // |(cur-prev)/prev| > tol
+    }
+    return r;
+}
+
+// out[c][j] = finish( sum_i S[i][j] vec_c[i] (+ xy[j]) ) for my columns j and nv vectors (vec = prev for the stop rule).
 // D(8 columns x 8 vectors) += A(8 columns x 4 rows) * B(4 rows x 8 vectors) per DMMA; a work unit is one
 // 8-column x 8-vector tile; with fewer than 8 units the K range is split across warps and the partial
 // tiles are summed in fixed order through shared memory.
 template <int MODE>
-__device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, int nv, const int *inactive, int add_xy, int par) {
+__device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, double *dst_local, int nv, const int *inactive,
+                                         int add_xy, unsigned fastmask, int par) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int qs = m.qs;
@@ -419,8 +450,10 @@ __device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, int 
             const int cv = an * 8 + 2 * t;
             if (j < m.c1) {
                 const double add = add_xy ? m.xy[j] : 0.0;
-                if (cv < nv && !(inactive && inactive[cv])) mv_publish<MODE>(m, par, cv, j, r0 + add);
-                if (cv + 1 < nv && !(inactive && inactive[cv + 1])) mv_publish<MODE>(m, par, cv + 1, j, r1 + add);
+                if (cv < nv && !(inactive && inactive[cv]))
+                    mv_publish<MODE>(m, dst_local, par, cv, j, mv_finish(m, fastmask, vec, cv, j, r0 + add));
+                if (cv + 1 < nv && !(inactive && inactive[cv + 1]))
+                    mv_publish<MODE>(m, dst_local, par, cv + 1, j, mv_finish(m, fastmask, vec, cv + 1, j, r1 + add));
             }
         } else {
             m.part[task * 64 + lane * 2] = r0;
@@ -438,17 +471,9 @@ __device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, int 
             const int j = m.c0 + am * 8 + (ln >> 2);
             const int cv = an * 8 + 2 * (ln & 3) + h;
             if (j < m.c1 && cv < nv && !(inactive && inactive[cv]))
-                mv_publish<MODE>(m, par, cv, j, sacc + (add_xy ? m.xy[j] : 0.0));
+                mv_publish<MODE>(m, dst_local, par, cv, j, mv_finish(m, fastmask, vec, cv, j, sacc + (add_xy ? m.xy[j] : 0.0)));
         }
     }
-}
-
-// slow path of the coordinate-wise prox (non-zero result), out of line for the same reason
-__device__ __noinline__ double prox_coord_nonzero(int kind, double u, double tp, const double *cp, double gamma) {
-    const double dp = cp[1], rdp = cp[4], gammad = cp[5], den2 = cp[6], rden2 = cp[7];
-    if (kind == 2) return st_scad_r(u, tp, dp, rdp, gamma, gammad, den2, rden2);
-    if (kind == 1) return st_mcp_r(u, tp, dp, rdp, gammad, den2, rden2);
-    return st_lasso_r(u, tp, dp, rdp);
 }
 
 template <int MODE>
@@ -464,10 +489,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
 
     // ---- shared-memory carve-up (doubles, then ints) ----
     double *Asl = sm;                                      // cpc_pad x qs (slice of XX, then of A)
-    double *beta = sm + (a.a_in_smem ? (size_t)a.cpc_pad * qs : 0);   // nvec x qs, zero padded
-    constexpr int NBUF = (MODE == MODE_CLUSTER) ? 2 : 1;   // remote DSMEM stores need a second (parity) buffer
-    double *us0 = beta + (size_t)nvec * qs;                // exchange buffer(s), nvec x qs each
-    double *xy = us0 + (size_t)NBUF * nvec * qs;           // q
+    double *B0 = sm + (a.a_in_smem ? (size_t)a.cpc_pad * qs : 0);   // ping-pong iterate buffers, nvec x qs each,
+    double *B1 = B0 + (size_t)nvec * qs;                   //   zero padded: beta lives in one, the other receives the next
+    double *xy = B1 + (size_t)nvec * qs;                   // q
     double *pf = xy + q;                                   // q
     double *lam_sm = pf + q;                               // max_ct * Lmax
     double *gw = lam_sm + (size_t)a.max_ct * a.Lmax;       // ngroups
@@ -479,12 +503,15 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     double *ak = lz_ib + LZ_MAX;                           // PK_MAXCT
     double *chd = ak + PK_MAXCT;                           // 3 * PK_MAXCT: alpha, gamma, tau
     double *misc = chd + 3 * PK_MAXCT;                     // 8
-    double *cpar = misc + 8;                               // 8 * PK_MAXCT: per-iteration derived constants
+    double *cpar = misc + 8;                               // 8 * PK_MAXCT: per-lambda derived constants
     int *lam_idx = reinterpret_cast<int *>(cpar + 8 * PK_MAXCT);   // PK_MAXCT each
     int *iter = lam_idx + PK_MAXCT;
     int *done = iter + PK_MAXCT;
     int *chi = done + PK_MAXCT;                            // 3 * PK_MAXCT: penalty, nlam, out_off
-    int *grp_ptr = chi + 3 * PK_MAXCT;                     // ngroups + 1
+    int *kind = chi + 3 * PK_MAXCT;                        // PK_MAXCT: 0 lasso-type, 1 mcp, 2 scad, 3 ols, 4 replicated (group)
+    int *cflag = kind + PK_MAXCT;                          // 2 x 8: violation masks of the cluster members (by parity)
+    int *violw = cflag + 16;                               // 4 ints: my violation mask (+ padding)
+    int *grp_ptr = violw + 4;                              // ngroups + 1
     int *grp_unique = grp_ptr + a.ngroups + 1;             // ngroups
     int *grp_idx = grp_unique + a.ngroups;                 // ngidx
     int *cover = grp_idx + a.ngidx;                        // q (only with groups)
@@ -492,6 +519,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     unsigned *bar = a.barriers + team;
     unsigned bar_target = 0;
     double *ub = a.ubuf ? a.ubuf + (size_t)team * 2 * a.max_ct * q : nullptr;
+    int *gflag = a.gflags ? a.gflags + (size_t)team * 2 * a.team_size : nullptr;
     const double *XXg = a.XX + (size_t)team * q * q;
     double *Amine = a.a_in_smem ? Asl : a.Abuf + ((size_t)team * a.team_size + rank) * a.cpc_pad * qs;
 
@@ -502,7 +530,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         const double *src = XXg + (size_t)j * q;
         for (int i = lane; i < qs; i += 32) dst[i] = (j < c1 && i < q) ? src[i] : 0.0;
     }
-    for (int e = threadIdx.x; e < (1 + NBUF) * nvec * qs; e += PK_THREADS) beta[e] = 0.0;   // beta + exchange buffer(s)
+    for (int e = threadIdx.x; e < 2 * nvec * qs; e += PK_THREADS) B0[e] = 0.0;
     for (int j = threadIdx.x; j < q; j += PK_THREADS) {
         xy[j] = a.XY[(size_t)team * q + j];
         pf[j] = a.pen_fact ? a.pen_fact[j] : 1.0;
@@ -520,24 +548,30 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         chd[c] = ch.alpha; chd[PK_MAXCT + c] = ch.gamma; chd[2 * PK_MAXCT + c] = ch.tau;
         lam_idx[c] = 0; iter[c] = 0; ak[c] = 1.0;
         done[c] = (ch.nlam <= 0) ? 1 : 0;
+        const int pen = ch.penalty;
+        kind[c] = (pen >= OEMB200_PEN_GRP_LASSO || a.accelerate) ? 4
+                : pen == OEMB200_PEN_OLS ? 3
+                : (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET) ? 2
+                : (pen == OEMB200_PEN_MCP || pen == OEMB200_PEN_MCP_NET) ? 1 : 0;
     }
     for (int e = threadIdx.x; e < nct * a.Lmax; e += PK_THREADS) {
         const int c = e / a.Lmax, l = e - c * a.Lmax;
         const ChainDev ch = a.chains[a.team_idx[ct0 + c]];
         lam_sm[e] = l < ch.nlam ? a.lambdas[ch.lam_off + l] : 0.0;
     }
-    if (MODE == MODE_CLUSTER) cluster_sync_all();   // peers may start storing into my exchange buffers
+    if (threadIdx.x < 16) cflag[threadIdx.x] = 0;
+    if (threadIdx.x == 0) violw[0] = 0;
+    if (MODE == MODE_CLUSTER) cluster_sync_all();   // peers may start storing into my buffers
     else __syncthreads();
     SmemTabs tb{pf, gw, grp_ptr, grp_unique, grp_idx, cover, a.ngroups};
 
-    // ---- exchange primitives ----
-    auto exchange = [&](int par, int nv, const int *inactive) {
+    // ---- exchange: barrier (+ in global mode the copy of the published vectors into my shared memory) ----
+    auto exchange = [&](int par, double *dst, int nv, const int *inactive) {
         if (MODE == MODE_SINGLE) __syncthreads();
         else if (MODE == MODE_CLUSTER) cluster_sync_all();
         else {
             team_barrier(bar, bar_target, a.team_size);
             const double *src = ub + (size_t)par * a.max_ct * q;
-            double *dst = us0;
             // per chain, 4 loads in flight per thread before the first use (one L2 round trip per batch)
             for (int c = 0; c < nv; ++c) {
                 if (inactive && inactive[c]) continue;
@@ -556,18 +590,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     };
 
     MvCtx mv;
-    mv.Amine = Amine; mv.xy = xy; mv.part = part; mv.us0 = us0; mv.ub = ub;
-    mv.q = q; mv.qs = qs; mv.c0 = c0; mv.c1 = c1; mv.natm = a.cpc_pad >> 3; mv.nvec = nvec; mv.max_ct = a.max_ct;
-    mv.team_size = a.team_size; mv.nbuf = NBUF;
-    auto matvec = [&](const double *vec, int nv, const int *inactive, bool add_xy, int par_) {
-        matvec_dmma<MODE>(mv, vec, nv, inactive, add_xy ? 1 : 0, par_);
-    };
+    mv.Amine = Amine; mv.xy = xy; mv.pf = pf; mv.cpar = cpar; mv.gam = chd + PK_MAXCT; mv.kind = kind;
+    mv.part = part; mv.ub = ub; mv.violw = violw;
+    mv.q = q; mv.qs = qs; mv.c0 = c0; mv.c1 = c1; mv.natm = a.cpc_pad >> 3; mv.max_ct = a.max_ct;
+    mv.team_size = a.team_size; mv.tol = a.tol;
 
     // =========================== phase 0: top eigenvalue ===========================
     double dval;
     int par = 0;
     if (a.compute_eig) {
-        double *v = beta, *vprev = beta + qs;
+        double *v = B0, *vprev = B0 + qs;      // w alternates between the two rows of B1 (remote stores need the parity)
         // deterministic pseudo-random start vector (fixed seed), normalised
         double ss = 0.0;
         for (int i = threadIdx.x; i < q; i += PK_THREADS) {
@@ -588,9 +620,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         const int kmax = min(LZ_MAX, max(q, 1));
         bool conv = false;
         while (!conv) {
-            matvec(v, 1, nullptr, false, par);
-            exchange(par, 1, nullptr);
-            double *w = us0 + (size_t)(par & (NBUF - 1)) * nvec * qs;
+            double *w = B1 + (size_t)par * qs;
+            matvec_dmma<MODE>(mv, v, w, 1, nullptr, 0, 0u, par);
+            exchange(par, w, 1, nullptr);
             par ^= 1;
             double dot = 0.0;
             for (int i = threadIdx.x; i < q; i += PK_THREADS) dot = fma(v[i], w[i], dot);
@@ -639,7 +671,25 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     }
 
     if (nct > 0) {
-        // ---- A = d I - XX on my slice ----
+        // per-lambda derived constants of chain c (thread c): thresholds, denominators and their reciprocals
+        auto set_cpar = [&](int c) {
+            const int pen = chi[c];
+            const double alpha = chd[c], gamma = chd[PK_MAXCT + c];
+            const double lambda = lam_sm[(size_t)c * a.Lmax + min(lam_idx[c], a.Lmax - 1)];
+            double denom = dval + (1.0 - alpha) * lambda, lam = lambda * alpha;
+            if (pen == OEMB200_PEN_SCAD_NET && alpha == 0.0) { lam = 0.0; denom = dval + lambda; }
+            const bool net = (pen == OEMB200_PEN_ENET || pen == OEMB200_PEN_SCAD_NET || pen == OEMB200_PEN_MCP_NET);
+            const double lp = net ? lam : lambda, dp = net ? denom : dval;
+            const bool is_scad = (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET);
+            const bool is_mcp = (pen == OEMB200_PEN_MCP || pen == OEMB200_PEN_MCP_NET);
+            const double gammad = gamma * dp;
+            const double den2 = is_mcp ? dp - 1.0 / gamma : (gamma - 1.0) * dp - 1.0;   // second denominator
+            double *cp = cpar + c * 8;
+            cp[0] = lp; cp[1] = dp; cp[2] = (is_scad || is_mcp) ? fmin(1.0, gammad) : 1.0; cp[3] = lambda;
+            cp[4] = 1.0 / dp; cp[5] = gammad; cp[6] = den2; cp[7] = 1.0 / den2;
+        };
+        __syncthreads();      // the Lanczos scratch aliases cpar
+        // ---- A = d I - XX on my slice; iterate buffers; first-lambda constants ----
         for (int jl = warp; jl < a.cpc_pad; jl += PK_WARPS) {
             const int j = c0 + jl;
             double *col = Amine + (size_t)jl * qs;
@@ -651,99 +701,61 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         }
         for (int e = threadIdx.x; e < nvec * qs; e += PK_THREADS) {
             const int c = e / qs, j = e - c * qs;
-            beta[e] = (c < nct && j < q && a.beta_init) ? a.beta_init[(size_t)chi[2 * PK_MAXCT + c] * q + j] : 0.0;
+            B0[e] = (c < nct && j < q && a.beta_init) ? a.beta_init[(size_t)chi[2 * PK_MAXCT + c] * q + j] : 0.0;
+            B1[e] = 0.0;
         }
-        __syncthreads();
+        if (threadIdx.x < nct) set_cpar(threadIdx.x);
+        unsigned fastmask = 0u;
+        bool any_slow = false;
+        for (int c = 0; c < nct; ++c) {
+            if (kind[c] < 4) fastmask |= 1u << c;
+            else any_slow = true;
+        }
+        if (MODE == MODE_CLUSTER) cluster_sync_all();
+        else __syncthreads();
 
         // =========================== phase 1: lambda paths ===========================
-        // Per iteration: mat-vec -> exchange -> one pass each for prox / stop rule / commit over ALL active
-        // chains (no block-wide sync between chains; 4 independent elements per thread in flight because
-        // with 8 warps per SM these passes are latency-, not throughput-bound).
-        int *flagw = reinterpret_cast<int *>(red);      // 8 words: per-warp "violated" bit masks
+        // beta lives in Bc; the next iterate is assembled in Bn by the members that own its coordinates (the
+        // coordinate-wise prox + stop rule run in the mat-vec epilogue), exchanged with ONE barrier, and the buffers
+        // swap.  Group penalties / Nesterov publish u instead and every member applies the prox redundantly.
+        int cur = 0;
+        int *flagw = reinterpret_cast<int *>(red);      // 8 words: per-warp masks
         for (;;) {
             int nactive = 0;
             for (int c = 0; c < nct; ++c) nactive += done[c] ? 0 : 1;
             if (nactive == 0) break;
             long long t0 = clock64();
-            // derived per-chain constants for this iteration's lambda (read after the exchange's sync); done by
-            // the last warp, which has the lightest mat-vec share
-            if (warp == PK_WARPS - 1 && lane < nct && !done[lane]) {
-                const int c = lane, pen = chi[c];
-                const double alpha = chd[c], gamma = chd[PK_MAXCT + c];
-                const double lambda = lam_sm[(size_t)c * a.Lmax + lam_idx[c]];
-                double denom = dval + (1.0 - alpha) * lambda, lam = lambda * alpha;
-                if (pen == OEMB200_PEN_SCAD_NET && alpha == 0.0) { lam = 0.0; denom = dval + lambda; }
-                const bool net = (pen == OEMB200_PEN_ENET || pen == OEMB200_PEN_SCAD_NET || pen == OEMB200_PEN_MCP_NET);
-                const double lp = net ? lam : lambda, dp = net ? denom : dval;
-                const bool is_scad = (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET);
-                const bool is_mcp = (pen == OEMB200_PEN_MCP || pen == OEMB200_PEN_MCP_NET);
-                const double gammad = gamma * dp;
-                const double den2 = is_mcp ? dp - 1.0 / gamma : (gamma - 1.0) * dp - 1.0;   // second denominator
-                double *cp = cpar + c * 8;
-                cp[0] = lp; cp[1] = dp; cp[2] = (is_scad || is_mcp) ? fmin(1.0, gammad) : 1.0; cp[3] = lambda;
-                cp[4] = 1.0 / dp; cp[5] = gammad; cp[6] = den2; cp[7] = 1.0 / den2;
+            double *Bc = cur ? B1 : B0, *Bn = cur ? B0 : B1;
+            matvec_dmma<MODE>(mv, Bc, Bn, nct, done, 1, fastmask, cur);
+            __syncthreads();
+            // my violation mask -> every member (same parity slot scheme as the vectors)
+            if (threadIdx.x == 0) {
+                const int vm = violw[0];
+                violw[0] = 0;
+                if (MODE == MODE_SINGLE) cflag[cur * 8] = vm;
+                else if (MODE == MODE_CLUSTER) {
+                    for (int r = 0; r < a.team_size; ++r) {
+                        unsigned remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&cflag[cur * 8 + rank])), "r"(r));
+                        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(vm) : "memory");
+                    }
+                } else gflag[(size_t)cur * a.team_size + rank] = vm;
             }
-            matvec(beta, nct, done, true, par);
             long long t1 = clock64();
-            exchange(par, nct, done);
+            exchange(cur, Bn, nct, done);
             long long t2 = clock64();
-            double *us = us0 + (size_t)(par & (NBUF - 1)) * nvec * qs;
-            par ^= 1;
-            // ---- coordinate-wise chains: prox (src/oem_dense.h:527-629), stop rule (src/utils.cpp:537-549) and
-            // commit fused in ONE pass: u -> next beta, compared with and written over the old beta.  Identical
-            // bit patterns (0 -> 0 above all) cost no arithmetic; |(cur-prev)/prev| > tol is evaluated as
-            // |cur-prev| > tol |prev|.  Group penalties and the Nesterov option take the three-pass route below.
             unsigned bad = 0u;
-            bool any_slow = false;
-            for (int c = 0; c < nct; ++c) {
-                if (done[c]) continue;
-                const int pen = chi[c];
-                if (pen >= OEMB200_PEN_GRP_LASSO || a.accelerate) { any_slow = true; continue; }
-                const double *bn = us + (size_t)c * qs;
-                double *bo = beta + (size_t)c * qs;
-                const double *cp = cpar + c * 8;
-                const double lp = cp[0], zf = cp[2], rdp = cp[4];
-                const double gamma = chd[PK_MAXCT + c];
-                const bool is_ols = pen == OEMB200_PEN_OLS;
-                const int kind = (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET) ? 2
-                               : (pen == OEMB200_PEN_MCP || pen == OEMB200_PEN_MCP_NET) ? 1 : 0;
-                bool viol = false;
-                for (int j0 = threadIdx.x; j0 < q; j0 += 4 * PK_THREADS) {
-                    double u[4], tp[4], prev[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int j = j0 + k * PK_THREADS;
-                        u[k] = j < q ? bn[j] : 0.0;
-                        tp[k] = j < q ? pf[j] * lp : 0.0;
-                        prev[k] = j < q ? bo[j] : 0.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int j = j0 + k * PK_THREADS;
-                        double r = 0.0;
-                        if (is_ols) r = div_r(u[k], dval, rdp);        // ols: dp == d
-                        else if (abs_gt(u[k], tp[k] * zf))      // else: every rule returns 0, no further FP64 work
-                            r = prox_coord_nonzero(kind, u[k], tp[k], cp, gamma);
-                        if (j < q && __double_as_longlong(r) != __double_as_longlong(prev[k])) {
-                            const bool bc = abs_gt(r, 1e-13), bp = abs_gt(prev[k], 1e-13);
-                            if (bc != bp) viol = true;
-                            else if (bc && abs_gt(r - prev[k], a.tol * fabs(prev[k]))) viol = true;
-                            bo[j] = r;
-                        }
-                    }
-                }
-                if (viol) bad |= 1u << c;
-            }
+            if (MODE == MODE_GLOBAL) {
+                for (int r = threadIdx.x; r < a.team_size; r += PK_THREADS)
+                    bad |= (unsigned)__ldcg(gflag + (size_t)cur * a.team_size + r);
+            } else if (threadIdx.x < a.team_size) bad = (unsigned)cflag[cur * 8 + threadIdx.x];
             const long long tA = clock64();
             if (any_slow) {
-                __syncthreads();
                 for (int c = 0; c < nct; ++c) {
-                    if (done[c]) continue;
-                    const int pen = chi[c];
-                    if (!(pen >= OEMB200_PEN_GRP_LASSO || a.accelerate)) continue;
-                    double *bn = us + (size_t)c * qs;
-                    double *bo = beta + (size_t)c * qs;
-                    prox_inplace(q, tb, pen, chd[c], chd[PK_MAXCT + c], chd[2 * PK_MAXCT + c], cpar[c * 8 + 3], dval, bn);
+                    if (done[c] || kind[c] < 4) continue;
+                    double *bn = Bn + (size_t)c * qs;
+                    const double *bo = Bc + (size_t)c * qs;
+                    prox_inplace(q, tb, chi[c], chd[c], chd[PK_MAXCT + c], chd[2 * PK_MAXCT + c], cpar[c * 8 + 3], dval, bn);
                     if (a.accelerate) {     // Nesterov step, src/oem_dense.h:633-651
                         const double ak_prev = ak[c];
                         const double ak_new = 0.5 * (1.0 + sqrt(1.0 + 4.0 * ak_prev * ak_prev));
@@ -759,14 +771,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                         adv = block_sum(adv, red);
                         if (threadIdx.x == 0) ak[c] = (adv > 0.0) ? 1.0 : ak_new;
                     }
-                    bool viol = false;
+                    bool viol = false;      // stop rule, src/utils.cpp:537-549
                     for (int j = threadIdx.x; j < q; j += PK_THREADS) {
-                        const double cur = bn[j], prev = bo[j];
-                        if (__double_as_longlong(cur) == __double_as_longlong(prev)) continue;
-                        const bool bc = abs_gt(cur, 1e-13), bp = abs_gt(prev, 1e-13);
-                        if (bc != bp) viol = true;
-                        else if (bc && abs_gt(cur - prev, a.tol * fabs(prev))) viol = true;
-                        bo[j] = cur;
+                        const double cv = bn[j], pv = bo[j];
+                        if (__double_as_longlong(cv) == __double_as_longlong(pv)) continue;
+                        const bool bc = abs_gt(cv, 1e-13), bp = abs_gt(pv, 1e-13);
+                        if (bc != bp || (bc && abs_gt(cv - pv, a.tol * fabs(pv)))) viol = true;
                     }
                     if (viol) bad |= 1u << c;
                 }
@@ -784,11 +794,14 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                 if (done[c]) continue;
                 const bool conv = !((bad >> c) & 1u);
                 if (!(conv || iter[c] + 1 >= a.maxit)) continue;
-                double *bo = beta + (size_t)c * qs;
+                double *bn = Bn + (size_t)c * qs;
+                double *bo = Bc + (size_t)c * qs;
+                const bool last = lam_idx[c] + 1 >= chi[PK_MAXCT + c];
                 double *gout = a.beta_out + ((size_t)chi[2 * PK_MAXCT + c] * a.Lmax + lam_idx[c]) * q;
                 for (int j = threadIdx.x; j < q; j += PK_THREADS) {
-                    double x = bo[j];
-                    if (a.post_scale) { x *= a.post_scale[j]; bo[j] = x; }   // get_beta() mutates the iterate: src/oem_xtx.h:576-581
+                    double x = bn[j];
+                    if (a.post_scale) { x *= a.post_scale[j]; bn[j] = x; }   // get_beta() mutates the iterate: src/oem_xtx.h:576-581
+                    if (last) bo[j] = x;                                       // a finished chain keeps its beta in both buffers
                     if (rank == 0) gout[j] = x;
                 }
             }
@@ -803,11 +816,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                     iter[c] = 0;
                     lam_idx[c] = li + 1;
                     if (li + 1 >= chi[PK_MAXCT + c]) done[c] = 1;
+                    else set_cpar(c);
                 } else {
                     iter[c] = it;
                 }
             }
-            __syncthreads();
+            cur ^= 1;
+            // with replicated (group / Nesterov) chains a member still reads the old buffer after the exchange: keep the
+            // cluster in step before peers overwrite it remotely
+            if (MODE == MODE_CLUSTER && any_slow) cluster_sync_all();
+            else __syncthreads();
             if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
                 const long long t3 = clock64();
                 a.prof[0] += t1 - t0; a.prof[1] += t2 - t1; a.prof[2] += t3 - t2; a.prof[3] += 1;
@@ -815,9 +833,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
             }
         }
         if (a.beta_final && rank == 0) {
+            const double *Bc = cur ? B1 : B0;
             for (int e = threadIdx.x; e < nct * q; e += PK_THREADS) {
                 const int c = e / q, j = e - c * q;
-                a.beta_final[(size_t)chi[2 * PK_MAXCT + c] * q + j] = beta[(size_t)c * qs + j];
+                a.beta_final[(size_t)chi[2 * PK_MAXCT + c] * q + j] = Bc[(size_t)c * qs + j];
             }
         }
     }
@@ -854,9 +873,10 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     const int qs = q4 + (((4 - q4) % 16) + 16) % 16;      // smallest value >= roundup(q,4) that is 4 (mod 16)
     const int ng = pp.ngroups, ngidx = ng ? pp.ngidx : 0;
     auto fixed_for = [&](int nbuf) {
-        return ((size_t)(1 + nbuf) * nvec * qs + 2 * (size_t)q + (size_t)max_ct * std::max(pp.Lmax, 1) + ng + PK_PART * 64 + 16 +
+        (void)nbuf;     // two ping-pong buffers in every mode
+        return ((size_t)2 * nvec * qs + 2 * (size_t)q + (size_t)max_ct * std::max(pp.Lmax, 1) + ng + PK_PART * 64 + 16 +
                 3 * LZ_MAX + PK_MAXCT + 3 * PK_MAXCT + 8 + 8 * PK_MAXCT) * 8 +
-               ((size_t)6 * PK_MAXCT + (ng ? 2 * (size_t)ng + 1 + ngidx + q : 0)) * 4 + 16;
+               ((size_t)7 * PK_MAXCT + 20 + (ng ? 2 * (size_t)ng + 1 + ngidx + q : 0)) * 4 + 16;
     };
     size_t fixed_bytes = fixed_for(1);
     const size_t smem_cap = cx.smem_optin;
@@ -899,7 +919,8 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     DBuf<double> d_ubuf;
     DBuf<unsigned> d_bar(G);
     DBuf<double> d_A;
-    if (mode == MODE_GLOBAL) d_ubuf.alloc((size_t)G * 2 * max_ct * q);
+    DBuf<int> d_gflags;
+    if (mode == MODE_GLOBAL) { d_ubuf.alloc((size_t)G * 2 * max_ct * q); d_gflags.alloc((size_t)G * 2 * team); d_gflags.zero(cx.stream); }
     if (!a_in_smem) d_A.alloc((size_t)G * team * cpc_pad * qs);
     if (!cd.empty()) d_chains.upload(cd.data(), cd.size(), cx.stream);
     d_tptr.upload(tptr.data(), tptr.size(), cx.stream);
@@ -919,7 +940,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     a.unique_groups = pp.unique_groups; a.grp_ptr = pp.grp_ptr; a.grp_idx = pp.grp_idx; a.grp_cover = pp.grp_cover;
     a.group_weights = pp.group_weights; a.post_scale = pp.post_scale; a.beta_init = pp.beta_init;
     a.beta_final = pp.beta_final; a.beta_out = pp.beta_out; a.niter_out = pp.niter_out;
-    a.lanczos_steps = pp.lanczos_steps; a.ubuf = d_ubuf.p; a.barriers = d_bar.p;
+    a.lanczos_steps = pp.lanczos_steps; a.ubuf = d_ubuf.p; a.barriers = d_bar.p; a.gflags = d_gflags.p;
 
     DBuf<long long> d_prof;
     const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;
@@ -945,7 +966,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         fprintf(stderr, "[path prof] mode=%d team=%d cpc=%d q=%d nct=%d | iters=%lld cyc/iter: matvec=%.0f exchange=%.0f prox+update=%.0f | "
                 "lanczos: steps=%lld total=%lld cyc (tridiag %lld)\n", mode, team, cpc, q, max_ct, h[3],
                 h[3] ? (double)h[0] / h[3] : 0.0, h[3] ? (double)h[1] / h[3] : 0.0, h[3] ? (double)h[2] / h[3] : 0.0, h[6], h[4], h[5]);
-        if (h[3]) fprintf(stderr, "[path prof]   prox=%.0f group/accel=%.0f stop=%.0f commit=%.0f state=%.0f\n", (double)h[8] / h[3],
+        if (h[3]) fprintf(stderr, "[path prof]   flags=%.0f replicated=%.0f reduce=%.0f finished=%.0f state=%.0f\n", (double)h[8] / h[3],
                           (double)h[9] / h[3], (double)h[10] / h[3], (double)h[11] / h[3], (double)h[12] / h[3]);
     }
 }
