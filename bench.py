@@ -258,6 +258,14 @@ def run_ours(args):
     gram_flops = st["gram_flops"] / max(1, st["gram_launches"])
     achieved = gram_flops / (gram_ms / 1e3) / 1e12
 
+    traffic, traffic_note = None, None
+    try:       # per-launch DRAM bytes of the Gram kernel from the committed ncu capture of this exact launch shape
+        tj = json.load(open(os.path.join(ROOT, "profiles", "gram_traffic.json")))
+        if tj["rows"] == rows and tj["p"] == P:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu capture in profiles/gram_traffic.json"
+    except Exception:
+        pass
     line = {"metric": "full lambda-path fit time", "value": ms_step / 1e3, "unit": "s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -269,7 +277,8 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "roofline": {"bound": "tensor", "kernel": "gram_syrk_kernel (FP64 DMMA.8x8x4, TMA-staged)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": None,
+                         "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_note,
+                         "algorithmic_bytes_per_launch": 8.0 * rows * P,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_launch": gram_flops, "ms_per_launch": gram_ms}}
 
