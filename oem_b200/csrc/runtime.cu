@@ -12,6 +12,7 @@ Ctx::Ctx(const oemb200_opts *o) {
     if (e != cudaSuccess || ndev < 1)
         fail(OEMB200_ENODEVICE, "no CUDA device available (%s); liboem_b200 has no CPU fallback",
              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    OEM_CUDA(cudaGetDevice(&prev_device));
     if (o && o->device >= 0) {
         if (o->device >= ndev) fail(OEMB200_EINVAL, "device %d out of range (%d devices)", o->device, ndev);
         OEM_CUDA(cudaSetDevice(o->device));
@@ -38,6 +39,7 @@ Ctx::~Ctx() {
     if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();   // unwinding: let queued kernels drain before buffers recycle
     delete tm;
     if (own_stream && stream) cudaStreamDestroy(stream);
+    if (prev_device >= 0 && prev_device != device) cudaSetDevice(prev_device);   // leave the caller's device as we found it
 }
 
 void Ctx::finish() {
@@ -55,16 +57,26 @@ struct Pool {
     std::multimap<size_t, void *> free_blocks;
     std::map<void *, size_t> live;
 };
-thread_local Pool g_pool;
+thread_local std::map<int, Pool> g_pools;      // one cache per device
+thread_local std::map<void *, int> g_owner;    // live block -> device
+Pool &cur_pool(int *dev_out = nullptr) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_out) *dev_out = dev;
+    return g_pools[dev];
+}
 }  // namespace
 
 void *pool_alloc(size_t bytes) {
+    int dev = 0;
+    Pool &g_pool = cur_pool(&dev);
     const size_t sz = (bytes + 511) & ~size_t(511);
     auto it = g_pool.free_blocks.lower_bound(sz);
     if (it != g_pool.free_blocks.end() && it->first <= sz + sz / 8) {   // reuse a block at most 12.5% larger
         void *p = it->second;
         g_pool.live[p] = it->first;
         g_pool.free_blocks.erase(it);
+        g_owner[p] = dev;
         return p;
     }
     void *p = nullptr;
@@ -76,10 +88,15 @@ void *pool_alloc(size_t bytes) {
         if (e != cudaSuccess) fail(OEMB200_ECUDA, "cudaMalloc of %.3f GB failed: %s", sz / 1e9, cudaGetErrorString(e));
     }
     g_pool.live[p] = sz;
+    g_owner[p] = dev;
     return p;
 }
 
 void pool_free(void *p) {
+    auto ow = g_owner.find(p);
+    if (ow == g_owner.end()) { cudaFree(p); return; }
+    Pool &g_pool = g_pools[ow->second];
+    g_owner.erase(ow);
     auto it = g_pool.live.find(p);
     if (it == g_pool.live.end()) { cudaFree(p); return; }
     // very large blocks (the uploaded copy of X) are not worth caching
@@ -89,8 +106,10 @@ void pool_free(void *p) {
 }
 
 void pool_release_all() {
-    for (auto &kv : g_pool.free_blocks) cudaFree(kv.second);
-    g_pool.free_blocks.clear();
+    for (auto &dp : g_pools) {
+        for (auto &kv : dp.second.free_blocks) cudaFree(kv.second);
+        dp.second.free_blocks.clear();
+    }
 }
 
 void Ctx::all_reduce(double *dev_buf, int64_t count) {

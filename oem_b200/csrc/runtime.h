@@ -39,6 +39,7 @@ struct PhaseTimers {
 
 struct Ctx {
     int device = 0;
+    int prev_device = -1;
     int num_sms = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;

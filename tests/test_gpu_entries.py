@@ -226,3 +226,13 @@ def test_unsupported_paths_fail_loudly(lib):
     bad = a[:17] + [3, np.array([0] * 200), False, "mse", a[18]]
     with pytest.raises(lib.OemB200Error, match="foldid"):
         lib.oem_xval_dense(*bad)
+
+
+def test_wide_problem_streams_A_from_l2(lib, oracle):
+    # q = 2400: a member's column slice of A (24 x 2404 doubles) no longer fits shared memory next to the iterate
+    # buffers, so the path kernel streams its slice from L2 (a_in_smem = false) -- same answers
+    X, y = gaussian_problem(77, 6000, 2400, nnz=10)
+    lam = [np.geomspace(0.3, 0.05, 4)]
+    a = args_xy(X, y, "gaussian", ["lasso"], lambda_=lam, opts=dict(maxit=40, tol=1e-7))
+    got, ref = lib.oem_fit_big(*a), oracle.oem_fit_big(*a)
+    assert_same_fit(got, ref)
