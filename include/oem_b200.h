@@ -37,7 +37,7 @@ extern "C" {
 #define OEMB200_EINVAL      1   /* bad argument (message says which) */
 #define OEMB200_ENODEVICE   2   /* no CUDA device / driver */
 #define OEMB200_ECUDA       3   /* a CUDA call or kernel failed */
-#define OEMB200_EUNSUPPORTED 4  /* reference feature outside the hot path (weights, n<=p, sparse) */
+#define OEMB200_EUNSUPPORTED 4  /* reference feature outside the hot path (n<=p, sparse, weights outside xval) */
 #define OEMB200_ECOMM       5   /* the all-reduce callback failed */
 
 /* Penalty ids, in the order the oracle uses (oracle/oem_oracle.c). Names are the R strings. */
@@ -80,7 +80,7 @@ typedef struct oemb200_spec {
     const char          *family;            /* "gaussian" | "binomial" */
     int                  n_penalty;
     const char  *const  *penalty;           /* R penalty names */
-    const double        *weights;  int64_t n_weights;        /* must be empty (R/oem.R:244) */
+    const double        *weights;  int64_t n_weights;        /* observation weights: xval only (R/oem_xval.R:215); else empty (R/oem.R:244) */
     const int           *groups;   int n_groups;             /* length p, or 0 */
     const int           *unique_groups; int n_unique_groups;
     const double        *group_weights; int n_group_weights; /* 0 => sqrt(|g|) */

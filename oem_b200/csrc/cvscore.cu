@@ -29,7 +29,7 @@ constexpr int CV_THREADS = 256;
 constexpr int CV_X_BYTES = CV_KC * CV_XBOX * 8;                 // 10880
 constexpr int CV_B_BYTES = CV_KC * CV_BBOX * 8;                 // 26240
 constexpr int CV_STAGE_BYTES = CV_X_BYTES + 2 * CV_B_BYTES;     // 63360
-constexpr int CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 128 + (2 * 2 * CV_COLS + 2 * CV_COLS + CV_ROWS + 8) * 8;
+constexpr int CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 128 + (2 * 2 * CV_COLS + 2 * CV_COLS + 2 * CV_ROWS + 8) * 8;
 
 struct CvItem {
     int fold, colblock, pad0, pad1;
@@ -48,7 +48,8 @@ constexpr int FG_COLS = 4;
 __global__ void __launch_bounds__(256)
 fold_gather_kernel(const double *__restrict__ X, long long n, int p, long long ld, const int *__restrict__ dest,
                    const int *__restrict__ order, double *__restrict__ Xs, long long lds, const double *__restrict__ y,
-                   double *__restrict__ ys) {
+                   double *__restrict__ ys, const double *__restrict__ w, double *__restrict__ ws,
+                   double *__restrict__ yws) {
     __shared__ double tile[FG_COLS][FG_ROWS];
     const long long r0 = (long long)blockIdx.x * FG_ROWS;
     const int j0 = blockIdx.y * FG_COLS;
@@ -61,14 +62,23 @@ fold_gather_kernel(const double *__restrict__ X, long long n, int p, long long l
         const int rl = order[r0 + t];                 // tile-local source row, fold-grouped
         const long long d = dest[r0 + rl];
         for (int c = 0; c < nc; ++c) Xs[(size_t)(j0 + c) * lds + d] = tile[c][rl];
-        if (blockIdx.y == 0 && y) ys[d] = y[r0 + rl];
+        if (blockIdx.y == 0 && y) {
+            const double yv = y[r0 + rl];
+            ys[d] = yv;
+            if (w) {                                  // observation weights: w and y*w in fold-sorted order
+                const double wv = w[r0 + rl];
+                ws[d] = wv;
+                yws[d] = yv * wv;
+            }
+        }
     }
 }
 
 void fold_gather_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const int *dest, const int *order,
-                        double *Xs, int64_t lds, const double *y, double *ys) {
+                        double *Xs, int64_t lds, const double *y, double *ys, const double *w, double *ws,
+                        double *yws) {
     dim3 grid((unsigned)((n + FG_ROWS - 1) / FG_ROWS), (p + FG_COLS - 1) / FG_COLS);
-    fold_gather_kernel<<<grid, 256, 0, cx.stream>>>(X, n, p, ld, dest, order, Xs, lds, y, ys);
+    fold_gather_kernel<<<grid, 256, 0, cx.stream>>>(X, n, p, ld, dest, order, Xs, lds, y, ys, w, ws, yws);
     OEM_CUDA(cudaGetLastError());
     cx.st.kernel_launches += 1;
 }
@@ -187,8 +197,8 @@ bool fold_bucket_device(Ctx &cx, const int *foldid_dev, int64_t n, int F, int64_
 template <bool MAE>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, int p, int ncld,
-               const CvItem *__restrict__ items, const double *__restrict__ ys, const double *__restrict__ b0,
-               double *__restrict__ partial, int part_stride) {
+               const CvItem *__restrict__ items, const double *__restrict__ ys, const double *__restrict__ ws,
+               const double *__restrict__ b0, double *__restrict__ partial, int part_stride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + CV_STAGES * CV_STAGE_BYTES);
     uint64_t *empty = full + CV_STAGES;
@@ -196,6 +206,7 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     double *run_mean = red + 2 * 2 * CV_COLS;     // [CV_COLS]
     double *run_m2 = run_mean + CV_COLS;          // [CV_COLS]
     double *ytile = run_m2 + CV_COLS;             // [CV_ROWS]
+    double *wtile = ytile + CV_ROWS;              // [CV_ROWS] observation weights (1 when none)
 
     const CvItem it = items[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -242,6 +253,7 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (threadIdx.x < CV_ROWS) {
             const long long r = trow0 + threadIdx.x;
             ytile[threadIdx.x] = r < it.valid_end ? ys[r] : 0.0;
+            wtile[threadIdx.x] = (ws && r < it.valid_end) ? ws[r] : 1.0;
         }
         for (int kt = 0; kt < nkt; ++kt, ++idx) {
             const int s = (int)(idx % CV_STAGES);
@@ -279,14 +291,14 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         for (int ma = 0; ma < 4; ++ma) {
             const int rl = wm * 32 + ma * 8 + g;
             const bool valid = (trow0 + rl) < it.valid_end;
-            const double yv = ytile[rl];
+            const double yv = ytile[rl], wv = wtile[rl];
 #pragma unroll
             for (int na = 0; na < 10; ++na)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int c = cbase + na * 8 + h;
                     const double r = yv - (acc[ma][na][h] + __ldg(b0 + (size_t)it.fold * ncld + col0 + c));
-                    const double tv = valid ? (MAE ? fabs(r) : r * r) : 0.0;
+                    const double tv = valid ? (MAE ? fabs(r) : r * r) * wv : 0.0;   // oem_xval_dense.cpp:389-401
                     acc[ma][na][h] = tv;
                     s1[na * 2 + h] += tv;
                 }
@@ -401,10 +413,11 @@ static EncodeTiledFn encode_fn() {
 int cv_ncld(int nc) { return (nc + CV_COLS - 1) / CV_COLS * CV_COLS + 8; }
 
 // Xs: fold-sorted, column-major, leading dimension lds (even), nrows_total rows.  B: nfolds x p x ncld (column index
-// contiguous), b0: nfolds x ncld.  segs[k] = {row0, padded end, valid end}.  out3: 3 x nc (count, mean, M2).
-void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys, int nfolds,
-                    const std::vector<std::array<int64_t, 3>> &segs, const double *B, const double *b0, int nc,
-                    bool mae, double *out3) {
+// contiguous), b0: nfolds x ncld.  segs[k] = {row0, padded end, valid end}.  ws: optional observation weights in
+// fold-sorted order.  out3: 3 x nc (count, mean, M2).
+void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys,
+                    const double *ws, int nfolds, const std::vector<std::array<int64_t, 3>> &segs, const double *B,
+                    const double *b0, int nc, bool mae, double *out3) {
     const int ncld = cv_ncld(nc);
     const int ncb = (nc + CV_COLS - 1) / CV_COLS;
     if ((lds & 1) || (reinterpret_cast<uintptr_t>(Xs) & 15))
@@ -459,11 +472,11 @@ void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64
     if (mae) {
         OEM_CUDA(cudaFuncSetAttribute(cvscore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
         cvscore_kernel<true><<<(unsigned)items.size(), CV_THREADS, CV_SMEM_BYTES, cx.stream>>>(
-            tmX, tmB, p, ncld, d_items.p, ys, b0, partial.p, part_stride);
+            tmX, tmB, p, ncld, d_items.p, ys, ws, b0, partial.p, part_stride);
     } else {
         OEM_CUDA(cudaFuncSetAttribute(cvscore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
         cvscore_kernel<false><<<(unsigned)items.size(), CV_THREADS, CV_SMEM_BYTES, cx.stream>>>(
-            tmX, tmB, p, ncld, d_items.p, ys, b0, partial.p, part_stride);
+            tmX, tmB, p, ncld, d_items.p, ys, ws, b0, partial.p, part_stride);
     }
     OEM_CUDA(cudaGetLastError());
     cv_merge_kernel<<<(nc + 127) / 128, 128, 0, cx.stream>>>(partial.p, part_stride, d_items.p, (int)items.size(), nc, out3);

@@ -18,14 +18,16 @@ namespace oemb200 {
 
 thread_local std::string g_last_error;
 
-void check_common(const oemb200_spec *s, const oemb200_opts *o, const oemb200_result *r, const char *want_family) {
+void check_common(const oemb200_spec *s, const oemb200_opts *o, const oemb200_result *r, const char *want_family,
+                  bool allow_weights) {
     if (!s || !o || !r) fail(OEMB200_EINVAL, "spec / opts / result must not be NULL");
     if (!s->family || strcmp(s->family, want_family) != 0) {
         if (strcmp(want_family, "gaussian") == 0)
             fail(OEMB200_EINVAL, "binomial not available for oem_fit_dense, use oem_fit_logistic_dense");
         fail(OEMB200_EINVAL, "family must be \"%s\"", want_family);
     }
-    if (s->n_weights > 0) fail(OEMB200_EUNSUPPORTED, "weights not implemented yet.");   // R/oem.R:244
+    if (s->n_weights > 0 && !allow_weights) fail(OEMB200_EUNSUPPORTED, "weights not implemented yet.");   // R/oem.R:244
+    if (s->n_weights > 0 && !s->weights) fail(OEMB200_EINVAL, "n_weights > 0 but weights is NULL");
     if (!r->beta || !r->lambda || !r->niter || !r->d) fail(OEMB200_EINVAL, "result buffers beta/lambda/niter/d are required");
     if (o->maxit < 1) fail(OEMB200_EINVAL, "maxit must be >= 1");
 }

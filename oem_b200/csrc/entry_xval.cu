@@ -22,8 +22,12 @@ namespace oemb200 {
 
 void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s, int nfolds,
               const int *foldid, const char *type_measure, const oemb200_opts *o, oemb200_result *res) {
-    check_common(s, o, res, "gaussian");
+    check_common(s, o, res, "gaussian", /*allow_weights=*/true);
     if (n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
+    // observation weights (xval.oem(weights=), R/oem_xval.R:215-222): XtWX_xval[_int], oem_xval_dense.h:489-627
+    const bool weighted = s->n_weights > 0;
+    if (weighted && s->n_weights != n)
+        fail(OEMB200_EINVAL, "length of weights not same as number of observations in x");      // R/oem_xval.R:218-221
     if (nfolds < 2 || !foldid) fail(OEMB200_EINVAL, "xval needs nfolds >= 2 and foldid");
     if (!res->cvm || !res->cvsd) fail(OEMB200_EINVAL, "xval needs cvm / cvsd result buffers");
     bool mae = false;
@@ -44,8 +48,9 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
     const size_t t_h = tm.start(&cx.st.ms_h2d);
     DevMatrix X;
     to_device_matrix(cx, x, n, p, ldx, X);
-    DevVector yv;
+    DevVector yv, wv;
     to_device_vector(cx, y, n, yv);
+    if (weighted) to_device_vector(cx, s->weights, n, wv);
     DBuf<int> d_dest(n), d_order(n), d_fold;
     const int *fold_dev = foldid;
     if (!is_device_ptr(foldid)) {
@@ -81,9 +86,15 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
     }
     const int64_t npad = std::max<int64_t>(off[F], align);
     if (npad >= (1ll << 31)) fail(OEMB200_EUNSUPPORTED, "xval: more than 2^31 rows per rank; shard the rows");
-    DBuf<double> Xs((size_t)npad * p), ys(npad);
+    DBuf<double> Xs((size_t)npad * p), ys(npad), ws, yws;
     // only the (< 72) padding rows at the end of each fold segment need zeros; the gather writes every other row
     ys.zero(cx.stream);
+    if (weighted) {
+        ws.alloc(npad);
+        yws.alloc(npad);
+        ws.zero(cx.stream);
+        yws.zero(cx.stream);
+    }
     for (int k = 0; k < F; ++k) {
         const int64_t pad0 = off[k] + cnt[k], npadrows = off[k + 1] - pad0;
         if (npadrows > 0)
@@ -91,22 +102,28 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
     }
     if (off[F] < npad)
         OEM_CUDA(cudaMemset2DAsync(Xs.p + off[F], (size_t)npad * 8, 0, (size_t)(npad - off[F]) * 8, p, cx.stream));
-    fold_gather_launch(cx, X.p, n, p, X.ld, d_dest.p, d_order.p, Xs.p, npad, yv.p, ys.p);
+    fold_gather_launch(cx, X.p, n, p, X.ld, d_dest.p, d_order.p, Xs.p, npad, yv.p, ys.p, weighted ? wv.p : nullptr,
+                       ws.p, yws.p);
     X.own.release();          // the fold-sorted copy replaces the uploaded one
 
-    // ---- 2. per-fold sums: bundle = [G F*p*p | stats F*3p | ysum F*2 | nobs F] ----
-    const size_t nb = (size_t)F * p * p + (size_t)F * 3 * p + (size_t)F * 2 + F;
+    // ---- 2. per-fold sums: bundle = [G F*p*p | stats F*3p | ysum F*2 | nobs F | corner F] ----
+    // unweighted: G_k = X_k'X_k, stats = (colsums, X_k'y, sum x^2), ysum = sum y, corner = n_k.
+    // weighted:   G_k = X_k'W X_k, stats = (sum w x, X_k'(y*w), UNWEIGHTED sum x^2), ysum = sum y*w, corner = sum w;
+    //             nobs stays the row count (oem_xval_dense.h:528-545, 596-624).
+    const size_t nb = (size_t)F * p * p + (size_t)F * 3 * p + (size_t)F * 2 + 2 * (size_t)F;
     DBuf<double> bundle(nb);
     double *G = bundle.p, *stats = G + (size_t)F * p * p, *ysum = stats + (size_t)F * 3 * p, *nobs = ysum + (size_t)F * 2;
+    double *corner = nobs + F;
     std::vector<RowSegment> segs;
     for (int k = 0; k < F; ++k) segs.push_back(RowSegment{off[k], off[k + 1], k});
-    gram_launch(cx, Xs.p, npad, p, npad, segs, F, nullptr, nullptr, G, false);
+    gram_launch(cx, Xs.p, npad, p, npad, segs, F, nullptr, weighted ? ws.p : nullptr, G, false);
     const size_t t_c = tm.start(&cx.st.ms_colstats);
     for (int k = 0; k < F; ++k) {
         const int64_t len = off[k + 1] - off[k];
         if (len > 0) {
-            colstats_launch(cx, Xs.p + off[k], len, p, npad, nullptr, ys.p + off[k], nullptr, stats + (size_t)k * 3 * p, false);
-            vecsum_launch(cx, ys.p + off[k], len, 0.0, ysum + (size_t)k * 2, false);
+            colstats_launch(cx, Xs.p + off[k], len, p, npad, weighted ? ws.p + off[k] : nullptr,
+                            (weighted ? yws.p : ys.p) + off[k], nullptr, stats + (size_t)k * 3 * p, false);
+            vecsum_launch(cx, (weighted ? yws.p : ys.p) + off[k], len, 0.0, ysum + (size_t)k * 2, false);
         } else {
             OEM_CUDA(cudaMemsetAsync(stats + (size_t)k * 3 * p, 0, 3 * (size_t)p * 8, cx.stream));
             OEM_CUDA(cudaMemsetAsync(ysum + (size_t)k * 2, 0, 16, cx.stream));
@@ -117,6 +134,16 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
         std::vector<double> hc(F);
         for (int k = 0; k < F; ++k) hc[k] = (double)cnt[k];
         OEM_CUDA(cudaMemcpyAsync(nobs, hc.data(), F * sizeof(double), cudaMemcpyHostToDevice, cx.stream));
+        if (!weighted)
+            OEM_CUDA(cudaMemcpyAsync(corner, hc.data(), F * sizeof(double), cudaMemcpyHostToDevice, cx.stream));
+    }
+    DBuf<double> wsum2;
+    if (weighted) {           // corner_k = sum of the fold's weights (vecsum writes [sum, sum of squares])
+        wsum2.alloc(2 * (size_t)F);
+        wsum2.zero(cx.stream);
+        for (int k = 0; k < F; ++k)
+            if (off[k + 1] > off[k]) vecsum_launch(cx, ws.p + off[k], off[k + 1] - off[k], 0.0, wsum2.p + 2 * (size_t)k, false);
+        OEM_CUDA(cudaMemcpy2DAsync(corner, 8, wsum2.p, 16, 8, F, cudaMemcpyDeviceToDevice, cx.stream));
     }
     const size_t t_ar = tm.start(&cx.st.ms_allreduce);
     cx.all_reduce(bundle.p, (int64_t)nb);
@@ -126,7 +153,7 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
     const int NG = F + 1;
     const size_t t_as = tm.start(&cx.st.ms_assemble);
     DBuf<double> XX((size_t)NG * q * q), XY((size_t)NG * q), cinv((size_t)NG * p), nout(NG);
-    assemble_aug_launch(cx, p, icpt, s->standardize ? 1 : 0, F, NG, G, stats, ysum, 2, nobs, nobs, XX.p, XY.p, cinv.p, nout.p);
+    assemble_aug_launch(cx, p, icpt, s->standardize ? 1 : 0, F, NG, G, stats, ysum, 2, corner, nobs, XX.p, XY.p, cinv.p, nout.p);
     std::vector<double> hXY(q), hcinv((size_t)NG * p), hn(NG);
     XY.download(hXY.data(), q, cx.stream);
     cinv.download(hcinv.data(), hcinv.size(), cx.stream);
@@ -180,7 +207,7 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
     db0.upload(hb0.data(), hb0.size(), cx.stream);
     std::vector<std::array<int64_t, 3>> cs;
     for (int k = 0; k < F; ++k) cs.push_back({off[k], off[k + 1], off[k] + cnt[k]});
-    cvscore_launch(cx, Xs.p, npad, p, npad, ys.p, F, cs, dB.p, db0.p, nc, mae, out3.p);
+    cvscore_launch(cx, Xs.p, npad, p, npad, ys.p, weighted ? ws.p : nullptr, F, cs, dB.p, db0.p, nc, mae, out3.p);
     std::vector<double> h3(3 * (size_t)nc);
     out3.download(h3.data(), h3.size(), cx.stream);
     cx.sync();
@@ -226,7 +253,7 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
                 }
         dB.upload(hB2.data(), hB2.size(), cx.stream);
         db0.upload(hb2.data(), hb2.size(), cx.stream);
-        cvscore_launch(cx, Xs.p, npad, p, npad, ys.p, F, cs, dB.p, db0.p, nc, false, out3.p);
+        cvscore_launch(cx, Xs.p, npad, p, npad, ys.p, nullptr, F, cs, dB.p, db0.p, nc, false, out3.p);   // loss is unweighted (.h:1122-1145)
         out3.download(h3.data(), h3.size(), cx.stream);
         cx.sync();
         std::vector<double> tot(nc);

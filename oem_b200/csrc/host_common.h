@@ -59,7 +59,8 @@ void run_paths(Ctx &cx, const Setup &su, const oemb200_opts *o, int q, int ngram
                const double *post_scale_dev, PathBuffers &pb);
 
 // ---- shared by the entry drivers (entries.cu) ----
-void check_common(const oemb200_spec *s, const oemb200_opts *o, const oemb200_result *r, const char *want_family);
+void check_common(const oemb200_spec *s, const oemb200_opts *o, const oemb200_result *r, const char *want_family,
+                  bool allow_weights = false);
 struct DevMatrix { const double *p = nullptr; int64_t ld = 0; DBuf<double> own; };
 struct DevVector { const double *p = nullptr; DBuf<double> own; };
 void to_device_matrix(Ctx &cx, const double *x, int64_t n, int p, int64_t ldx, DevMatrix &m);

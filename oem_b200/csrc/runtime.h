@@ -191,15 +191,17 @@ void logit_fused_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, 
 // ---------------- cvscore.cu ----------------
 // order[i]: for every tile of fold_gather_tile_rows() source rows, the tile-local row indices grouped by fold
 void fold_gather_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const int *dest, const int *order,
-                        double *Xs, int64_t lds, const double *y, double *ys);
+                        double *Xs, int64_t lds, const double *y, double *ys, const double *w = nullptr,
+                        double *ws = nullptr, double *yws = nullptr);
 int fold_gather_tile_rows();
 // stable counting sort of the rows by fold on the device (nfolds <= 64): dest, order (device), cnt / off (host)
 bool fold_bucket_device(Ctx &cx, const int *foldid_dev, int64_t n, int F, int64_t align, int *dest, int *order,
                         std::vector<int64_t> &cnt, std::vector<int64_t> &off);
 int cv_ncld(int nc);     // leading dimension (columns) of the coefficient matrices handed to cvscore_launch
 // out3 = 3 x nc: (count, mean, M2) of t = (y - pred)^2 | |y - pred| over all valid rows, per column
-void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys, int nfolds,
-                    const std::vector<std::array<int64_t, 3>> &segs, const double *B, const double *b0, int nc,
-                    bool mae, double *out3);
+// ws: optional observation weights (fold-sorted like ys): t is multiplied by w_i
+void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys,
+                    const double *ws, int nfolds, const std::vector<std::array<int64_t, 3>> &segs, const double *B,
+                    const double *b0, int nc, bool mae, double *out3);
 
 }  // namespace oemb200

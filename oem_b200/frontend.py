@@ -234,8 +234,9 @@ def xval_oem(x, y, nfolds=10, foldid=None, type_measure="mse", ncores=-1, family
         raise ValueError("type.measure must be 'mse', 'deviance' or 'mae' for the gaussian family")
     penalty = _match_penalty(penalty)
     n, p = _shape(x)
-    if len(weights) > 0:
-        raise NotImplementedError("xval.oem weights are outside the hot path (SURVEY.md 8a a9)")
+    weights = np.asarray(weights, dtype=np.float64).ravel() if len(weights) > 0 else np.zeros(0)
+    if weights.size and weights.size != n:
+        raise ValueError("length of weights not same as number of observations in x")      # R/oem_xval.R:216-221
     if foldid is None:
         rng = np.random.default_rng(seed)
         foldid = rng.permutation(np.resize(np.arange(1, int(nfolds) + 1), n))     # sample(rep(seq(nfolds), length = n))
@@ -249,7 +250,7 @@ def xval_oem(x, y, nfolds=10, foldid=None, type_measure="mse", ncores=-1, family
     g, ug, gw = _groups(penalty, groups, group_weights, p, explicit_intercept=bool(intercept))
     lam = _lambda_list(lambda_, len(penalty))
     opts = dict(maxit=int(maxit), tol=float(tol), irls_maxit=int(irls_maxit), irls_tol=float(irls_tol), ncores=int(ncores))
-    res = api.oem_xval_dense(x, y, family, penalty, [], g, ug, gw, lam, int(nlambda), lmr, float(alpha), gamma, float(tau), pf,
+    res = api.oem_xval_dense(x, y, family, penalty, weights, g, ug, gw, lam, int(nlambda), lmr, float(alpha), gamma, float(tau), pf,
                              bool(standardize), bool(intercept), int(nfolds), foldid.astype(np.int32), bool(compute_loss),
                              "mse" if type_measure == "deviance" else type_measure, opts, comm=comm)
     out = _decorate(res, penalty, n, p, family, varnames)

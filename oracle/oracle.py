@@ -349,24 +349,39 @@ def oem_xtx(xtx, xty, family, penalty, groups, unique_groups, group_weights, lam
 # ------------------------------------------------------------------------------------------
 # oem_xval_dense
 # ------------------------------------------------------------------------------------------
-def fold_parts(X, Y, foldid, nfolds, intercept):
-    """XtX_xval / XtX_xval_int (src/oem_xval_dense.h:358-484): per-fold Gram pieces."""
+def fold_parts(X, Y, foldid, nfolds, intercept, weights=None):
+    """XtX_xval / XtX_xval_int (src/oem_xval_dense.h:358-484): per-fold Gram pieces; with observation
+    weights the twins XtWX_xval / XtWX_xval_int (:489-627): G = sub' W sub, b = sub' (y*w), border
+    sum_i w_i x_i, corner sum w, b(0) = sum y*w, while nobs stays the row COUNT and colsq stays the
+    UNWEIGHTED sum of squares (:533-535 "we do not standardize with respect to weights").
+    The reference's intercept twin writes rankUpdate(sqrt(W).asDiagonal() * sub.adjoint()) (:596-597),
+    a numelem x numelem diagonal times an nvars x numelem matrix -- dimensionally invalid (undefined
+    behaviour under NDEBUG); its no-intercept twin (:528-529) and every other weighted term define the
+    intent sub' W sub, which is what is restated here for both."""
     p = X.shape[1]
     parts = []
     for k in range(1, nfolds + 1):
         idx = np.nonzero(foldid == k)[0]
         sub, sub_y = X[idx, :], Y[idx]
-        G = sub.T @ sub
-        b = sub.T @ sub_y
+        if weights is None:
+            G = sub.T @ sub
+            b = sub.T @ sub_y
+            cs, corner, b0 = sub.sum(axis=0), float(idx.size), sub_y.sum()
+        else:
+            w = weights[idx]
+            sw = np.sqrt(w)[:, None] * sub
+            G = sw.T @ sw
+            yw = sub_y * w
+            b = sub.T @ yw
+            cs, corner, b0 = (w[:, None] * sub).sum(axis=0), w.sum(), yw.sum()
         if intercept:
-            cs = sub.sum(axis=0)
             Gi = np.zeros((p + 1, p + 1))
             Gi[1:, 1:] = G
             Gi[0, 1:] = cs
             Gi[1:, 0] = cs
-            Gi[0, 0] = idx.size
+            Gi[0, 0] = corner
             G = Gi
-            b = np.concatenate([[sub_y.sum()], b])
+            b = np.concatenate([[b0], b])
         parts.append(dict(xtx=G, xty=b, nobs=idx.size, colsq=(sub ** 2).sum(axis=0)))
     return parts
 
@@ -407,15 +422,21 @@ def assemble(parts, skip_fold, p, standardize_, intercept):
 def oem_xval_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_,
                    nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize_, intercept,
                    nfolds, foldid, compute_loss, type_measure, opts):
-    """src/oem_xval_dense.cpp:31-477; unweighted branch, ncores=1 semantics."""
+    """src/oem_xval_dense.cpp:31-477, ncores=1 semantics; observation weights
+    (reachable through xval.oem(weights=), R/oem_xval.R:215-222) enter the fold Grams (fold_parts)
+    and the CV score t*w_i (oem_xval_dense.cpp:389-392, 398-401); the loss stays unweighted
+    (oem_xval_dense.h:1122-1145)."""
     o = _as_opts(opts)
     if family != "gaussian":
         raise ValueError("binomial not available for oem_xval_dense, use oem_xval_logistic_dense")
-    if np.asarray(weights).size:
-        raise NotImplementedError("xval weights: out of scope (SURVEY.md 8a a9)")
     X = np.asarray(x, dtype=np.float64)
     Y = np.asarray(y, dtype=np.float64).ravel()
     n, p = X.shape
+    W = np.asarray(weights, dtype=np.float64).ravel()
+    if W.size == 0:
+        W = None
+    elif W.size != n:
+        raise ValueError("length of weights not same as number of observations in x")   # R/oem_xval.R:218-221
     foldid = np.asarray(foldid, dtype=np.int32).ravel()
     q = p + int(intercept)
     pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
@@ -423,7 +444,7 @@ def oem_xval_dense(x, y, family, penalty, weights, groups, unique_groups, group_
         pf = np.concatenate([[0.0], pf])
     if not n > p:
         raise ValueError("dimension of x larger than number of observations")
-    parts = fold_parts(X, Y, foldid, nfolds, intercept)
+    parts = fold_parts(X, Y, foldid, nfolds, intercept, W)
     grp = _Groups(groups, unique_groups, group_weights, scan=q)
     s = _Solver(q, pf, grp, o["maxit"], o["tol"])
     out = dict(beta=[None] * len(penalty), lambda_=[None] * len(penalty), niter=[None] * len(penalty),
@@ -472,6 +493,8 @@ def oem_xval_dense(x, y, family, penalty, weights, groups, unique_groups, group_
             B = beta_folds[pp][k - 1]
             r = Y[idx, None] - (X[idx, :] @ B[1:, :] + B[0:1, :])
             T[idx, :] = r ** 2 if type_measure == "mse" else np.abs(r)
+            if W is not None:
+                T[idx, :] *= W[idx, None]
         m = T.mean(axis=0)
         M2 = ((T - m[None, :]) ** 2).sum(axis=0)
         out["cvm"].append(m)

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from cases import args_xy, binomial_problem, gaussian_problem   # noqa: E402
 
-CASES = ["dense_c1", "dense_c2", "big_c5", "logistic_c4", "xtx", "xval_c3"]
+CASES = ["dense_c1", "dense_c2", "big_c5", "logistic_c4", "xtx", "xval_c3", "xval_weighted"]
 
 
 def inputs(name):
@@ -45,6 +45,13 @@ def inputs(name):
         groups = np.concatenate([[0], np.repeat(np.arange(1, 9), 5)])
         a = args_xy(X, y, "gaussian", ["lasso", "grp.lasso", "mcp"], groups=groups, unique_groups=np.unique(groups), nlambda=25)
         return "oem_xval_dense", a[:17] + [5, foldid, False, "mse", a[18]]
+    if name == "xval_weighted":     # xval.oem(weights=): X'WX fold Grams, weighted mae score
+        X, y = gaussian_problem(77, 2000, 20, noise=2.0)
+        rng = np.random.default_rng(77)
+        foldid = 1 + rng.permutation(2000) % 4
+        a = args_xy(X, y, "gaussian", ["lasso", "scad"], nlambda=20)
+        a[4] = rng.uniform(0.25, 3.0, size=2000)
+        return "oem_xval_dense", a[:17] + [4, foldid, False, "mae", a[18]]
     raise KeyError(name)
 
 

@@ -161,6 +161,35 @@ def test_xval(lib, oracle, standardize, intercept, measure):
         assert np.allclose(got["loss"][pp], ref["loss"][pp], rtol=1e-9)
 
 
+@pytest.mark.parametrize("standardize,intercept,measure", [(True, True, "mse"), (True, False, "mae"), (False, False, "mse")])
+def test_xval_observation_weights(lib, oracle, standardize, intercept, measure):
+    # xval.oem(weights=): X'WX fold Grams (XtWX_xval[_int], oem_xval_dense.h:489-627), weighted CV score
+    X, y = gaussian_problem(31, 3001, 30, coef="vignette", noise=2.0)
+    rng = np.random.default_rng(31)
+    foldid = 1 + rng.permutation(3001) % 5
+    w = rng.uniform(0.25, 3.0, size=3001)
+    a = xval_args(X, y, ["lasso", "mcp", "elastic.net"], foldid, 5, nlambda=25, alpha=0.7, standardize=standardize,
+                  intercept=intercept, type_measure=measure, compute_loss=True)
+    a[4] = w
+    got, ref = lib.oem_xval_dense(*a), oracle.oem_xval_dense(*a)
+    assert_same_fit(got, ref)
+    for pp in range(3):
+        assert np.allclose(got["cvm"][pp], ref["cvm"][pp], rtol=1e-9, atol=0)
+        assert np.allclose(got["cvsd"][pp], ref["cvsd"][pp], rtol=1e-8, atol=0)
+        assert np.allclose(got["loss"][pp], ref["loss"][pp], rtol=1e-9)
+    # unit weights are the unweighted fit, bit for bit
+    a[4] = np.ones(3001)
+    one = lib.oem_xval_dense(*a)
+    a[4] = []
+    none = lib.oem_xval_dense(*a)
+    for pp in range(3):
+        assert np.array_equal(one["beta"][pp], none["beta"][pp])
+        assert np.array_equal(one["cvm"][pp], none["cvm"][pp])
+    with pytest.raises(Exception):
+        a[4] = np.ones(17)
+        lib.oem_xval_dense(*a)
+
+
 def test_xval_many_columns_uneven_folds(lib, oracle):
     # more than 320 (penalty x lambda) columns -> two column blocks in the scoring GEMM; ragged folds; odd n
     X, y = gaussian_problem(9, 2501, 23, noise=2.0)
