@@ -25,6 +25,7 @@
 // workspace slot; gram_reduce_kernel sums the slots of a tile in a fixed order (deterministic,
 // no atomics) and mirrors the lower triangle.
 #include <algorithm>
+#include <type_traits>
 #include <mutex>
 #include "runtime.h"
 
@@ -136,6 +137,12 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
 #pragma unroll
         for (int na = 0; na < 4; ++na) acc[ma][na][0] = acc[ma][na][1] = 0.0;
 
+    // Row atoms of the last panel beyond q are padding: a warp skips them (warp-uniform), which frees issue slots on
+    // its scheduler for the other warp that shares it (warps w and w+4 = the two row halves of one column quarter).
+    const int mav = max(0, min(8, (q - it.pi * G_TILE - wm * 64 + 7) >> 3));
+    auto run = [&](auto full_tag) {
+    constexpr int MAV = decltype(full_tag)::value;      // row atoms this warp computes (compile-time: keeps the
+                                                        // straight-line LDS / DMMA schedule of the full tile)
     for (int kt = 0; kt < nk; ++kt) {
         const int s = kt % G_STAGES;
         const uint32_t ph = (kt / G_STAGES) & 1;
@@ -156,12 +163,14 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
         for (int ks = 0; ks < G_KSTEPS; ++ks) {
             double a[8], b[4];
 #pragma unroll
-            for (int ma = 0; ma < 8; ++ma) a[ma] = pA[offA[ma] + ks * 4];
+            for (int ma = 0; ma < 8; ++ma)
+                if (ma < MAV) a[ma] = pA[offA[ma] + ks * 4];
 #pragma unroll
             for (int na = 0; na < 4; ++na) b[na] = pB[offB[na] + ks * 4];
             if (CENTER) {
 #pragma unroll
-                for (int ma = 0; ma < 8; ++ma) a[ma] -= mA[ma];
+                for (int ma = 0; ma < 8; ++ma)
+                    if (ma < MAV) a[ma] -= mA[ma];
                 const bool valid = !tail || (rbase + ks * 4 < nrows);
 #pragma unroll
                 for (int na = 0; na < 4; ++na) b[na] = valid ? b[na] - mB[na] : 0.0;
@@ -172,8 +181,10 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
             }
 #pragma unroll
             for (int ma = 0; ma < 8; ++ma)
+                if (ma < MAV) {
 #pragma unroll
-                for (int na = 0; na < 4; ++na) dmma884(acc[ma][na][0], acc[ma][na][1], a[ma], b[na]);
+                    for (int na = 0; na < 4; ++na) dmma884(acc[ma][na][0], acc[ma][na][1], a[ma], b[na]);
+                }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -189,6 +200,18 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
                 load_tile(kt + G_STAGES);
             }
         }
+    }
+    };
+    switch (mav) {
+        case 8: run(std::integral_constant<int, 8>{}); break;
+        case 7: run(std::integral_constant<int, 7>{}); break;
+        case 6: run(std::integral_constant<int, 6>{}); break;
+        case 5: run(std::integral_constant<int, 5>{}); break;
+        case 4: run(std::integral_constant<int, 4>{}); break;
+        case 3: run(std::integral_constant<int, 3>{}); break;
+        case 2: run(std::integral_constant<int, 2>{}); break;
+        case 1: run(std::integral_constant<int, 1>{}); break;
+        default: run(std::integral_constant<int, 0>{}); break;      // all padding: only keeps the barriers moving
     }
 
     // epilogue: partial tile -> workspace slot, [j][i] with i (panel pi column) contiguous

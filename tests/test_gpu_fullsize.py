@@ -58,6 +58,8 @@ def test_gram_properties_at_shard_scale(lib):
     Gc, _ = _gram(lib, torch, Xt, 0, n, mean=mean, w=w)
     blk = ((Xt[0:64] - mean[0:64, None]) * w) @ (Xt[900:964] - mean[900:964, None]).t()
     assert torch.allclose(Gc[0:64, 900:964], blk, rtol=1e-10, atol=1e-7)
+    # the event-timed region of the first call holds one-off host work (module load, workspace cudaMalloc): time a warm one
+    _, ms = _gram(lib, torch, Xt, 0, n)
     tflops = n * p * (p + 1.0) / (ms / 1e3) / 1e12
     assert tflops > 15.0, f"Gram kernel far below its roofline: {tflops:.1f} TFLOP/s"
 
