@@ -127,3 +127,43 @@ def test_fuzz_xtx(lib, oracle, seed):
             kw["lmin_ratio"], kw["alpha"], kw["gamma"], kw["tau"], sf, kw["penalty_factor"], dict(maxit=3000, tol=1e-10)]
     got, ref = lib.oem_xtx(xtx, xty, *args), oracle.oem_xtx(xtx, xty, *args)
     assert_same_fit(got, ref, check_niter=False, lam_ulps=4)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_wide_path_modes(lib, oracle, seed):
+    """q = 100..900: the path kernel's cluster (DSMEM) and cooperative (global exchange) modes, fast (fused prox) and
+    replicated (group penalty) routes mixed in one launch, with and without a scale factor."""
+    rng = np.random.default_rng(11000 + seed)
+    p = int(rng.integers(100, 900))
+    n = 2 * p + 50
+    X, y = gaussian_problem(11500 + seed, n, p, nnz=12)
+    xtx, xty = X.T @ X / n, X.T @ y / n
+    k = int(rng.integers(1, 5))
+    pens = [str(x) for x in rng.choice(COORD + GROUP, size=k, replace=False)]
+    g = np.sort(rng.integers(1, p // 4 + 1, size=p)).astype(np.int32)
+    sf = np.sqrt(np.diag(xtx)) if seed % 2 else []
+    args = ["gaussian", pens, g, np.unique(g), [], [], int(rng.integers(4, 9)), 0.05, float(rng.choice([0.5, 1.0])),
+            float(rng.uniform(2.5, 4.0)), 0.5, sf, np.ones(p), dict(maxit=400, tol=1e-9)]
+    got, ref = lib.oem_xtx(xtx, xty, *args), oracle.oem_xtx(xtx, xty, *args)
+    assert_same_fit(got, ref, check_niter=False, lam_ulps=4)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_xval_wide(lib, oracle, seed):
+    """several Grams (folds + full data) of q = 120..400 sharing one persistent launch"""
+    rng = np.random.default_rng(12000 + seed)
+    p = int(rng.integers(120, 400))
+    F = int(rng.integers(3, 6))
+    n = (F + 1) * (p + 40)
+    X, y = gaussian_problem(12500 + seed, n, p, nnz=10, noise=2.0)
+    foldid = (1 + rng.permutation(n) % F).astype(np.int32)
+    pens = [str(x) for x in rng.choice(["lasso", "mcp", "scad", "grp.lasso", "elastic.net"], size=2, replace=False)]
+    g = np.concatenate([[0], np.sort(rng.integers(1, p // 5 + 1, size=p))]).astype(np.int32)
+    a = args_xy(X, y, "gaussian", pens, groups=g, unique_groups=np.unique(g), nlambda=6, lmin_ratio=0.05, alpha=0.8,
+                opts=dict(tol=1e-9, maxit=400))
+    a = a[:17] + [F, foldid, False, "mse", a[18]]
+    got, ref = lib.oem_xval_dense(*a), oracle.oem_xval_dense(*a)
+    assert_same_fit(got, ref, check_niter=False)
+    for pp in range(2):
+        assert np.allclose(got["cvm"][pp], ref["cvm"][pp], rtol=1e-8)
+        assert np.allclose(got["cvsd"][pp], ref["cvsd"][pp], rtol=1e-7)
