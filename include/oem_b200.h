@@ -159,6 +159,15 @@ int oemb200_fit_logistic_dense(const double *x, int64_t n, int p, int64_t ldx, c
 int oemb200_fit_big(const double *x, int64_t n, int p, int64_t ldx, const double *y,
                     const oemb200_spec *spec, const oemb200_opts *opts, oemb200_result *res);
 
+/* predict.oem (R/methods.R:48-119; logistic response R/methods.R:346-366): out (n x nlambda, column-major,
+ * ldo >= n, host or device) = newx (n x p) * beta[intercept rows dropped] + beta[0, :].  beta is the host
+ * coefficient matrix of one model as the fit entries return it: beta_rows x nlambda column-major with
+ * beta_rows = p + 1 (row 0 = intercept) or p (oem_xtx).  type 0 = "link", 1 = "response" of the binomial
+ * family, 1 / (1 + exp(-link)).  One FP64 DMMA GEMM launch (the CV-scoring kernel with a store epilogue). */
+int oemb200_predict(const double *x, int64_t n, int p, int64_t ldx, const double *beta, int beta_rows,
+                    int nlambda, int type, double *out, int64_t ldo, const oemb200_opts *opts,
+                    oemb200_stats *stats);
+
 /* ------------------------------------------------------------------------------------------
  * Phase-level entries (device pointers only) used by bench.py for the roofline numbers and by
  * the Gram-level parity tests.  They are the kernels the five entries above are made of.

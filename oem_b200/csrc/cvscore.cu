@@ -9,7 +9,7 @@
 //   X box  [68 rows x 20 cols]  (64 used; the 4 extra rows make the k-stride 68 = 4 mod 16: conflict-free)
 //   B box  2 x [164 cols x 20 rows] (160 used each, stride 164 = 4 mod 16)
 // CTA tile = 64 rows x 320 columns, 8 warps as 2 x 4 with 32 x 80 warp tiles (80 accumulator doubles per
-// thread).  A CTA walks a contiguous range of row tiles of one fold and keeps (count, mean, M2) per column
+// thread); with at most 160 columns (one penalty's lambda path) 128 rows x 160 columns, 8 warps as 4 x 2.  A CTA walks a contiguous range of row tiles of one fold and keeps (count, mean, M2) per column
 // with Chan's pairwise update, so one partial per CTA reaches the fixed-order final merge.
 #include <algorithm>
 #include <array>
@@ -17,8 +17,6 @@
 
 namespace oemb200 {
 
-constexpr int CV_ROWS = 64;
-constexpr int CV_XBOX = 68;
 constexpr int CV_KC = 20;
 constexpr int CV_KSTEPS = CV_KC / 4;
 constexpr int CV_COLS = 320;
@@ -26,10 +24,12 @@ constexpr int CV_BHALF = 160;
 constexpr int CV_BBOX = 164;
 constexpr int CV_STAGES = 3;
 constexpr int CV_THREADS = 256;
-constexpr int CV_X_BYTES = CV_KC * CV_XBOX * 8;                 // 10880
 constexpr int CV_B_BYTES = CV_KC * CV_BBOX * 8;                 // 26240
-constexpr int CV_STAGE_BYTES = CV_X_BYTES + 2 * CV_B_BYTES;     // 63360
-constexpr int CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 128 + (2 * 2 * CV_COLS + 2 * CV_COLS + 2 * CV_ROWS + 8) * 8;
+// dynamic shared memory of the NH-half variant: stages + barriers + [2][rows/32][cols] reduction + running mean / M2 + y, w tiles
+constexpr int cv_smem_bytes(int nh) {
+    return CV_STAGES * (CV_KC * ((nh == 2 ? 64 : 128) + 4) * 8 + nh * CV_B_BYTES) + 128 +
+           (2 * ((nh == 2 ? 64 : 128) / 32) * (CV_BHALF * nh) + 2 * (CV_BHALF * nh) + 2 * (nh == 2 ? 64 : 128) + 8) * 8;
+}
 
 struct CvItem {
     int fold, colblock, pad0, pad1;
@@ -194,28 +194,39 @@ bool fold_bucket_device(Ctx &cx, const int *foldid_dev, int64_t n, int F, int64_
     return true;
 }
 
-template <bool MAE>
+// EPI: 0 = squared error moments, 1 = absolute error moments (the CV score), 2 = store the linear predictor
+// x_i . b + b0 (predict.oem type = "link", R/methods.R:113-118), 3 = store 1 / (1 + exp(-link)) (type = "response" of
+// predict.oemfit_binomial, R/methods.R:355-358).  The store modes write pred[c * ldo + row] for c < nc.
+constexpr int EPI_MSE = 0, EPI_MAE = 1, EPI_LINK = 2, EPI_RESPONSE = 3;
+
+template <int EPI, int NH>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, int p, int ncld,
                const CvItem *__restrict__ items, const double *__restrict__ ys, const double *__restrict__ ws,
-               const double *__restrict__ b0, double *__restrict__ partial, int part_stride) {
+               const double *__restrict__ b0, double *__restrict__ partial, int part_stride,
+               double *__restrict__ pred, long long ldo, int nc) {
+    constexpr bool MAE = (EPI == EPI_MAE);
+    // NH = 2: CTA tile 64 rows x 320 columns (8 warps as 2 x 4);  NH = 1: 128 rows x 160 columns (4 x 2) for
+    // nc <= 160 (one penalty's lambda path), which halves the padded columns.  Warp tile 32 x 80 in both.
+    constexpr int ROWS = NH == 2 ? 64 : 128, XBOX = ROWS + 4, COLS = CV_BHALF * NH, NWM = ROWS / 32;
+    constexpr int X_BYTES = CV_KC * XBOX * 8, STAGE_BYTES = X_BYTES + NH * CV_B_BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + CV_STAGES * CV_STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + CV_STAGES * STAGE_BYTES);
     uint64_t *empty = full + CV_STAGES;
-    double *red = reinterpret_cast<double *>(smem_raw + CV_STAGES * CV_STAGE_BYTES + 128);   // [2][2][CV_COLS]
-    double *run_mean = red + 2 * 2 * CV_COLS;     // [CV_COLS]
-    double *run_m2 = run_mean + CV_COLS;          // [CV_COLS]
-    double *ytile = run_m2 + CV_COLS;             // [CV_ROWS]
-    double *wtile = ytile + CV_ROWS;              // [CV_ROWS] observation weights (1 when none)
+    double *red = reinterpret_cast<double *>(smem_raw + CV_STAGES * STAGE_BYTES + 128);   // [2][NWM][COLS]
+    double *run_mean = red + 2 * NWM * COLS;     // [COLS]
+    double *run_m2 = run_mean + COLS;          // [COLS]
+    double *ytile = run_m2 + COLS;             // [ROWS]
+    double *wtile = ytile + ROWS;              // [ROWS] observation weights (1 when none)
 
     const CvItem it = items[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = NH == 2 ? warp >> 2 : warp >> 1, wn = NH == 2 ? warp & 3 : warp & 1;
     const int nkt = (p + CV_KC - 1) / CV_KC;
-    const int ntiles = (int)((it.row_end - it.row0 + CV_ROWS - 1) / CV_ROWS);
+    const int ntiles = (int)((it.row_end - it.row0 + ROWS - 1) / ROWS);
     const long long total = (long long)ntiles * nkt;
-    const int col0 = it.colblock * CV_COLS;
+    const int col0 = it.colblock * COLS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CV_THREADS / 32); }
@@ -223,22 +234,22 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmB);
     }
-    for (int c = threadIdx.x; c < CV_COLS; c += CV_THREADS) { run_mean[c] = 0.0; run_m2[c] = 0.0; }
+    for (int c = threadIdx.x; c < COLS; c += CV_THREADS) { run_mean[c] = 0.0; run_m2[c] = 0.0; }
     __syncthreads();
 
     auto issue = [&](long long idx) {      // thread 0 only
         const int s = (int)(idx % CV_STAGES);
         const int tile = (int)(idx / nkt), kt = (int)(idx - (long long)tile * nkt);
-        unsigned char *base = smem_raw + (size_t)s * CV_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], CV_STAGE_BYTES);
-        tma_load_2d(base, &tmX, &full[s], (int)(it.row0 + (long long)tile * CV_ROWS), kt * CV_KC);
-        tma_load_2d(base + CV_X_BYTES, &tmB, &full[s], col0, it.fold * p + kt * CV_KC);
-        tma_load_2d(base + CV_X_BYTES + CV_B_BYTES, &tmB, &full[s], col0 + CV_BHALF, it.fold * p + kt * CV_KC);
+        unsigned char *base = smem_raw + (size_t)s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        tma_load_2d(base, &tmX, &full[s], (int)(it.row0 + (long long)tile * ROWS), kt * CV_KC);
+        tma_load_2d(base + X_BYTES, &tmB, &full[s], col0, it.fold * p + kt * CV_KC);
+        if (NH == 2) tma_load_2d(base + X_BYTES + CV_B_BYTES, &tmB, &full[s], col0 + CV_BHALF, it.fold * p + kt * CV_KC);
     };
     if (threadIdx.x == 0)
         for (long long i = 0; i < CV_STAGES && i < total; ++i) issue(i);
 
-    const int offA = wm * 32 + g;                         // + ma*8 + (k)*CV_XBOX
+    const int offA = wm * 32 + g;                         // + ma*8 + (k)*XBOX
     const int offB = (wn & 1) * 80 + g;                   // + na*8 + (k)*CV_BBOX, box = wn >> 1
     double run_cnt = 0.0;
 
@@ -249,8 +260,8 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         for (int ma = 0; ma < 4; ++ma)
 #pragma unroll
             for (int na = 0; na < 10; ++na) acc[ma][na][0] = acc[ma][na][1] = 0.0;
-        const long long trow0 = it.row0 + (long long)tile * CV_ROWS;
-        if (threadIdx.x < CV_ROWS) {
+        const long long trow0 = it.row0 + (long long)tile * ROWS;
+        if (EPI < EPI_LINK && threadIdx.x < ROWS) {
             const long long r = trow0 + threadIdx.x;
             ytile[threadIdx.x] = r < it.valid_end ? ys[r] : 0.0;
             wtile[threadIdx.x] = (ws && r < it.valid_end) ? ws[r] : 1.0;
@@ -259,14 +270,14 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const int s = (int)(idx % CV_STAGES);
             const uint32_t ph = (uint32_t)((idx / CV_STAGES) & 1);
             mbar_wait(&full[s], ph);
-            const double *xs = reinterpret_cast<const double *>(smem_raw + (size_t)s * CV_STAGE_BYTES);
-            const double *bs = xs + CV_KC * CV_XBOX + (wn >> 1) * (CV_KC * CV_BBOX);
+            const double *xs = reinterpret_cast<const double *>(smem_raw + (size_t)s * STAGE_BYTES);
+            const double *bs = xs + CV_KC * XBOX + (wn >> 1) * (CV_KC * CV_BBOX);
 #pragma unroll
             for (int ks = 0; ks < CV_KSTEPS; ++ks) {
                 double a[4], b[10];
                 const int k = ks * 4 + t;
 #pragma unroll
-                for (int ma = 0; ma < 4; ++ma) a[ma] = xs[k * CV_XBOX + offA + ma * 8];
+                for (int ma = 0; ma < 4; ++ma) a[ma] = xs[k * XBOX + offA + ma * 8];
 #pragma unroll
                 for (int na = 0; na < 10; ++na) b[na] = bs[k * CV_BBOX + offB + na * 8];
 #pragma unroll
@@ -281,9 +292,28 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 issue(idx + CV_STAGES);
             }
         }
+        const int cbase = (wn >> 1) * CV_BHALF + (wn & 1) * 80 + 2 * t;      // + na*8 + {0,1}
+        if (EPI >= EPI_LINK) {
+            // ---------------- epilogue (predict): store link / response, rows of one atom are 64 contiguous bytes ----------------
+#pragma unroll
+            for (int ma = 0; ma < 4; ++ma) {
+                const long long row = trow0 + wm * 32 + ma * 8 + g;
+                if (row >= it.valid_end) continue;
+#pragma unroll
+                for (int na = 0; na < 10; ++na)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = col0 + cbase + na * 8 + h;
+                        if (c >= nc) continue;
+                        double v = acc[ma][na][h] + __ldg(b0 + (size_t)it.fold * ncld + c);
+                        if (EPI == EPI_RESPONSE) v = 1.0 / (1.0 + exp(-v));
+                        pred[(size_t)c * ldo + row] = v;
+                    }
+            }
+            continue;
+        }
         // ---------------- epilogue: t = measure(y - b0 - pred), tile (count, mean, M2) per column ----------------
         __syncthreads();     // ytile visible
-        const int cbase = (wn >> 1) * CV_BHALF + (wn & 1) * 80 + 2 * t;      // + na*8 + {0,1}
         double s1[20];
 #pragma unroll
         for (int c = 0; c < 20; ++c) s1[c] = 0.0;
@@ -315,10 +345,10 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int na = 0; na < 10; ++na)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) red[(0 * 2 + wm) * CV_COLS + cbase + na * 8 + h] = s1[na * 2 + h];
+                for (int h = 0; h < 2; ++h) red[(0 * NWM + wm) * COLS + cbase + na * 8 + h] = s1[na * 2 + h];
         }
         __syncthreads();
-        const double cnt = (double)max(0ll, min((long long)CV_ROWS, it.valid_end - trow0));
+        const double cnt = (double)max(0ll, min((long long)ROWS, it.valid_end - trow0));
         double m2[20];
 #pragma unroll
         for (int c = 0; c < 20; ++c) m2[c] = 0.0;
@@ -328,7 +358,10 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int c = cbase + na * 8 + h;
-                    const double mean = (red[c] + red[CV_COLS + c]) / cnt;
+                    double ssum = red[c];
+#pragma unroll
+                    for (int w2 = 1; w2 < NWM; ++w2) ssum += red[w2 * COLS + c];
+                    const double mean = ssum / cnt;
 #pragma unroll
                     for (int ma = 0; ma < 4; ++ma) {
                         const bool valid = (trow0 + wm * 32 + ma * 8 + g) < it.valid_end;
@@ -349,14 +382,16 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int na = 0; na < 10; ++na)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) red[(1 * 2 + wm) * CV_COLS + cbase + na * 8 + h] = m2[na * 2 + h];
+                for (int h = 0; h < 2; ++h) red[(1 * NWM + wm) * COLS + cbase + na * 8 + h] = m2[na * 2 + h];
         }
         __syncthreads();
         // Chan merge of the tile into the running state, one thread per column
         if (cnt > 0.0) {
-            for (int c = threadIdx.x; c < CV_COLS; c += CV_THREADS) {
-                const double tmean = (red[c] + red[CV_COLS + c]) / cnt;
-                const double tm2 = red[2 * CV_COLS + c] + red[3 * CV_COLS + c];
+            for (int c = threadIdx.x; c < COLS; c += CV_THREADS) {
+                double ssum = red[c], tm2 = red[NWM * COLS + c];
+#pragma unroll
+                for (int w2 = 1; w2 < NWM; ++w2) { ssum += red[w2 * COLS + c]; tm2 += red[(NWM + w2) * COLS + c]; }
+                const double tmean = ssum / cnt;
                 const double ntot = run_cnt + cnt;
                 const double dlt = tmean - run_mean[c];
                 run_mean[c] += dlt * (cnt / ntot);
@@ -366,9 +401,10 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         run_cnt += cnt;
         __syncthreads();
     }
+    if (EPI >= EPI_LINK) return;
     double *out = partial + (size_t)blockIdx.x * part_stride;
     if (threadIdx.x == 0) out[0] = run_cnt;
-    for (int c = threadIdx.x; c < CV_COLS; c += CV_THREADS) {
+    for (int c = threadIdx.x; c < COLS; c += CV_THREADS) {
         out[1 + 2 * c] = run_mean[c];
         out[2 + 2 * c] = run_m2[c];
     }
@@ -376,10 +412,10 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 // out[c] = (count, mean, M2) merged over this column block's items in item order
 __global__ void cv_merge_kernel(const double *__restrict__ partial, int part_stride, const CvItem *__restrict__ items,
-                                int nitems, int nc, double *__restrict__ out3) {
+                                int nitems, int nc, int cols, double *__restrict__ out3) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
-    const int cb = c / CV_COLS, cl = c - cb * CV_COLS;
+    const int cb = c / cols, cl = c - cb * cols;
     double n = 0.0, mean = 0.0, m2 = 0.0;
     for (int i = 0; i < nitems; ++i) {
         if (items[i].colblock != cb) continue;
@@ -414,36 +450,39 @@ int cv_ncld(int nc) { return (nc + CV_COLS - 1) / CV_COLS * CV_COLS + 8; }
 
 // Xs: fold-sorted, column-major, leading dimension lds (even), nrows_total rows.  B: nfolds x p x ncld (column index
 // contiguous), b0: nfolds x ncld.  segs[k] = {row0, padded end, valid end}.  ws: optional observation weights in
-// fold-sorted order.  out3: 3 x nc (count, mean, M2).
-void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys,
-                    const double *ws, int nfolds, const std::vector<std::array<int64_t, 3>> &segs, const double *B,
-                    const double *b0, int nc, bool mae, double *out3) {
+// fold-sorted order.  epi < EPI_LINK: out = 3 x nc (count, mean, M2); else out = predictions, column-major, ld ldo.
+static void cv_gemm_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys,
+                           const double *ws, int nfolds, const std::vector<std::array<int64_t, 3>> &segs,
+                           const double *B, const double *b0, int nc, int epi, double *out, int64_t ldo) {
     const int ncld = cv_ncld(nc);
-    const int ncb = (nc + CV_COLS - 1) / CV_COLS;
+    const int nh = nc <= CV_BHALF ? 1 : 2;                  // narrow problems: 128 x 160 tiles
+    const int cols = CV_BHALF * nh, rows = nh == 2 ? 64 : 128;
+    const int ncb = (nc + cols - 1) / cols;
     if ((lds & 1) || (reinterpret_cast<uintptr_t>(Xs) & 15))
-        fail(OEMB200_EINVAL, "cvscore: fold-sorted X must have an even leading dimension and a 16-byte aligned base");
+        fail(OEMB200_EINVAL, "cvscore: X must have an even leading dimension and a 16-byte aligned base");
     // items: contiguous ranges of 64-row tiles, a few waves of CTAs
     int64_t tiles_total = 0;
-    for (auto &s : segs) tiles_total += (s[2] - s[0] + CV_ROWS - 1) / CV_ROWS;
+    for (auto &s : segs) tiles_total += (s[2] - s[0] + rows - 1) / rows;
     const int64_t target = std::max<int64_t>(1, (int64_t)cx.num_sms * 4 / ncb);
     const int64_t tiles_per_item = std::max<int64_t>(1, (tiles_total + target - 1) / target);
     std::vector<CvItem> items;
     for (int cb = 0; cb < ncb; ++cb)
         for (int k = 0; k < nfolds; ++k) {
-            const int64_t nt = (segs[k][2] - segs[k][0] + CV_ROWS - 1) / CV_ROWS;
+            const int64_t nt = (segs[k][2] - segs[k][0] + rows - 1) / rows;
             for (int64_t t0 = 0; t0 < nt; t0 += tiles_per_item) {
                 CvItem it;
                 it.fold = k; it.colblock = cb; it.pad0 = it.pad1 = 0;
-                it.row0 = segs[k][0] + t0 * CV_ROWS;
-                it.row_end = segs[k][0] + std::min(nt, t0 + tiles_per_item) * CV_ROWS;
+                it.row0 = segs[k][0] + t0 * rows;
+                it.row_end = segs[k][0] + std::min(nt, t0 + tiles_per_item) * rows;
                 it.valid_end = segs[k][2];
                 items.push_back(it);
             }
         }
     if (items.empty()) fail(OEMB200_EINVAL, "cvscore: no rows");
-    const int part_stride = 1 + 2 * CV_COLS;
+    const int part_stride = 1 + 2 * cols;
+    const bool store = epi >= EPI_LINK;
     DBuf<CvItem> d_items(items.size());
-    DBuf<double> partial(items.size() * (size_t)part_stride);
+    DBuf<double> partial(store ? 1 : items.size() * (size_t)part_stride);
     d_items.upload(items.data(), items.size(), cx.stream);
 
     CUtensorMap tmX, tmB;
@@ -451,7 +490,7 @@ void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64
     {
         cuuint64_t dims[2] = {(cuuint64_t)nrows_total, (cuuint64_t)p};
         cuuint64_t strides[1] = {(cuuint64_t)lds * 8};
-        cuuint32_t box[2] = {CV_XBOX, CV_KC};
+        cuuint32_t box[2] = {(cuuint32_t)rows + 4, CV_KC};
         cuuint32_t es[2] = {1, 1};
         if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(Xs), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -469,20 +508,45 @@ void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64
             fail(OEMB200_ECUDA, "cvscore: tensor map for B failed");
     }
     const size_t t0 = cx.tm->start(&cx.st.ms_cvscore);
-    if (mae) {
-        OEM_CUDA(cudaFuncSetAttribute(cvscore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
-        cvscore_kernel<true><<<(unsigned)items.size(), CV_THREADS, CV_SMEM_BYTES, cx.stream>>>(
-            tmX, tmB, p, ncld, d_items.p, ys, ws, b0, partial.p, part_stride);
-    } else {
-        OEM_CUDA(cudaFuncSetAttribute(cvscore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
-        cvscore_kernel<false><<<(unsigned)items.size(), CV_THREADS, CV_SMEM_BYTES, cx.stream>>>(
-            tmX, tmB, p, ncld, d_items.p, ys, ws, b0, partial.p, part_stride);
+#define CV_LAUNCH(E, H)                                                                                               \
+    do {                                                                                                              \
+        OEM_CUDA(cudaFuncSetAttribute(cvscore_kernel<E, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                      cv_smem_bytes(H)));                                                             \
+        cvscore_kernel<E, H><<<(unsigned)items.size(), CV_THREADS, cv_smem_bytes(H), cx.stream>>>(                    \
+            tmX, tmB, p, ncld, d_items.p, ys, ws, b0, partial.p, part_stride, store ? out : nullptr, (long long)ldo,  \
+            nc);                                                                                                      \
+    } while (0)
+#define CV_LAUNCH_NH(E) do { if (nh == 1) CV_LAUNCH(E, 1); else CV_LAUNCH(E, 2); } while (0)
+    switch (epi) {
+        case EPI_MSE: CV_LAUNCH_NH(EPI_MSE); break;
+        case EPI_MAE: CV_LAUNCH_NH(EPI_MAE); break;
+        case EPI_LINK: CV_LAUNCH_NH(EPI_LINK); break;
+        default: CV_LAUNCH_NH(EPI_RESPONSE); break;
     }
+#undef CV_LAUNCH_NH
+#undef CV_LAUNCH
     OEM_CUDA(cudaGetLastError());
-    cv_merge_kernel<<<(nc + 127) / 128, 128, 0, cx.stream>>>(partial.p, part_stride, d_items.p, (int)items.size(), nc, out3);
-    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+    if (!store) {
+        cv_merge_kernel<<<(nc + 127) / 128, 128, 0, cx.stream>>>(partial.p, part_stride, d_items.p, (int)items.size(), nc, cols, out);
+        OEM_CUDA(cudaGetLastError());
+        cx.st.kernel_launches += 1;
+    }
     cx.tm->stop(t0);
-    cx.st.kernel_launches += 2;
+}
+
+void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys,
+                    const double *ws, int nfolds, const std::vector<std::array<int64_t, 3>> &segs, const double *B,
+                    const double *b0, int nc, bool mae, double *out3) {
+    cv_gemm_launch(cx, Xs, nrows_total, p, lds, ys, ws, nfolds, segs, B, b0, nc, mae ? EPI_MAE : EPI_MSE, out3, 0);
+}
+
+// pred (n x nc, column-major, ld ldo) = X (n x p) * B (p x ncld layout of cvscore) + b0, optionally through the logistic
+// link: the GEMM of predict.oem (R/methods.R:113-118, 355-358) on the CV-scoring kernel with a store epilogue.
+void predict_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const double *B, const double *b0, int nc,
+                    bool response, double *pred, int64_t ldo) {
+    std::vector<std::array<int64_t, 3>> segs{{0, n, n}};
+    cv_gemm_launch(cx, X, n, p, ld, nullptr, nullptr, 1, segs, B, b0, nc, response ? EPI_RESPONSE : EPI_LINK, pred, ldo);
 }
 
 }  // namespace oemb200

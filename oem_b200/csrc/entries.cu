@@ -430,6 +430,63 @@ static int guarded(F &&f) {
 
 using namespace oemb200;
 
+// ------------------------------------------------------------------------------------------------
+// predict.oem (R/methods.R:48-119, 346-366): newx %*% nbeta (+ intercept row), optional logistic response
+// ------------------------------------------------------------------------------------------------
+static void predict_entry(const double *x, int64_t n, int p, int64_t ldx, const double *beta, int nrows, int L, int type,
+                          double *out, int64_t ldo, const oemb200_opts *o, oemb200_stats *stats) {
+    if (!x || !beta || !out || !o) fail(OEMB200_EINVAL, "x / beta / out / opts must not be NULL");
+    if (n < 1 || p < 1 || ldx < n || L < 1 || ldo < n)
+        fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d ldx=%lld L=%d ldo=%lld", (long long)n, p, (long long)ldx, L, (long long)ldo);
+    if (nrows != p && nrows != p + 1)
+        fail(OEMB200_EINVAL, "beta has %d rows; newx has %d columns (expected %d or %d)", nrows, p, p, p + 1);   // R/methods.R:115-116
+    if (type != 0 && type != 1) fail(OEMB200_EINVAL, "type must be 0 (link) or 1 (response)");
+    if (is_device_ptr(beta)) fail(OEMB200_EINVAL, "beta must be a host pointer");
+    Ctx cx(o);
+    PhaseTimers &tm = *cx.tm;
+    const size_t t_total = tm.start(&cx.st.ms_total);
+    const size_t t_h = tm.start(&cx.st.ms_h2d);
+    DevMatrix X;
+    to_device_matrix(cx, x, n, p, ldx, X);
+    if ((X.ld & 1) || (reinterpret_cast<uintptr_t>(X.p) & 15)) {
+        // device-resident newx that the TMA descriptor cannot address (odd leading dimension / unaligned base): repack
+        const int64_t ld2 = n + (n & 1);
+        X.own.alloc((size_t)ld2 * p);
+        if (ld2 != n) X.own.zero(cx.stream);
+        OEM_CUDA(cudaMemcpy2DAsync(X.own.p, (size_t)ld2 * 8, X.p, (size_t)X.ld * 8, (size_t)n * 8, p, cudaMemcpyDeviceToDevice,
+                                   cx.stream));
+        X.p = X.own.p;
+        X.ld = ld2;
+    }
+    tm.stop(t_h);
+    const int icpt = nrows - p, ncld = cv_ncld(L);
+    std::vector<double> hB((size_t)p * ncld, 0.0), hb0(ncld, 0.0);
+    for (int c = 0; c < L; ++c) {
+        const double *col = beta + (size_t)c * nrows;
+        if (icpt) hb0[c] = col[0];
+        for (int j = 0; j < p; ++j) hB[(size_t)j * ncld + c] = col[icpt + j];
+    }
+    DBuf<double> dB(hB.size()), db0(hb0.size()), dout;
+    dB.upload(hB.data(), hB.size(), cx.stream);
+    db0.upload(hb0.data(), hb0.size(), cx.stream);
+    const bool out_dev = is_device_ptr(out);
+    double *po = out;
+    int64_t ldp = ldo;
+    if (!out_dev) {
+        dout.alloc((size_t)n * L);
+        po = dout.p;
+        ldp = n;
+    }
+    predict_launch(cx, X.p, n, p, X.ld, dB.p, db0.p, L, type == 1, po, ldp);
+    if (!out_dev) {
+        OEM_CUDA(cudaMemcpy2DAsync(out, (size_t)ldo * 8, po, (size_t)n * 8, (size_t)n * 8, L, cudaMemcpyDeviceToHost, cx.stream));
+        cx.st.d2h_bytes += (int64_t)n * L * 8;
+    }
+    tm.stop(t_total);
+    cx.finish();
+    if (stats) *stats = cx.st;
+}
+
 extern "C" {
 
 const char *oemb200_last_error(void) { return g_last_error.c_str(); }
@@ -485,6 +542,11 @@ int oemb200_xval_dense(const double *x, int64_t n, int p, int64_t ldx, const dou
                        int nfolds, const int *foldid, const char *type_measure, const oemb200_opts *opts,
                        oemb200_result *res) {
     return guarded([&] { fit_xval(x, n, p, ldx, y, spec, nfolds, foldid, type_measure, opts, res); });
+}
+
+int oemb200_predict(const double *x, int64_t n, int p, int64_t ldx, const double *beta, int beta_rows, int nlambda, int type,
+                    double *out, int64_t ldo, const oemb200_opts *opts, oemb200_stats *stats) {
+    return guarded([&] { predict_entry(x, n, p, ldx, beta, beta_rows, nlambda, type, out, ldo, opts, stats); });
 }
 
 // ---------------- phase-level entries ----------------

@@ -260,3 +260,81 @@ def xval_oem(x, y, nfolds=10, foldid=None, type_measure="mse", ncores=-1, family
     out["best_model"] = penalty[out["model_min"] - 1]
     out["foldid"] = foldid
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# S3 methods the front-ends' users call next (R/methods.R): predict / logLik on the fitted object
+# ------------------------------------------------------------------------------------------
+def lambda_interp(lambda_, s):
+    """R/utils.R:64-87 (copied there from glmnet): linear interpolation weights of `s` on the fitted lambda grid.
+    Returns 0-based left / right column indices and the weight of the left column."""
+    lam = np.asarray(lambda_, dtype=np.float64)
+    s = np.atleast_1d(np.asarray(s, dtype=np.float64)).copy()
+    if lam.size == 1:
+        z = np.zeros(s.size, dtype=np.int64)
+        return z, z.copy(), np.ones(s.size)
+    s = np.clip(s, lam.min(), lam.max())
+    k = lam.size
+    sfrac = (lam[0] - s) / (lam[0] - lam[k - 1])
+    t = (lam[0] - lam) / (lam[0] - lam[k - 1])
+    coord = np.interp(sfrac, t, np.arange(1, k + 1, dtype=np.float64))       # approx(lambda, seq(lambda), sfrac)$y
+    left, right = np.floor(coord).astype(np.int64), np.ceil(coord).astype(np.int64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        frac = (sfrac - t[right - 1]) / (t[left - 1] - t[right - 1])
+    frac[left == right] = 1.0
+    return left - 1, right - 1, frac
+
+
+def _which_model(fit, which_model):
+    names = list(fit["beta"].keys())
+    if isinstance(which_model, str):
+        if which_model not in names:
+            raise ValueError(f"Model {which_model} specified, but {which_model} not computed.")
+        return names.index(which_model)
+    if which_model > len(names):
+        raise ValueError(f"Model {which_model} specified, but only {len(names)} were computed.")
+    return int(which_model) - 1
+
+
+def predict(fit, newx=None, s=None, which_model=1, type="link", opts=None):
+    """predict.oem / predict.oemfit_binomial (R/methods.R:48-119, 346-366).  `type` in link / response / coefficients /
+    nonzero / class; `s` interpolates the coefficient path at new lambda values (lambda.interp).  The matrix product
+    newx %*% beta runs on the device (api.predict_matrix -> oemb200_predict)."""
+    if type not in ("link", "response", "coefficients", "nonzero", "class"):
+        raise ValueError("'arg' should be one of 'link', 'response', 'coefficients', 'nonzero', 'class'")
+    m = _which_model(fit, which_model)
+    if newx is None and type not in ("coefficients", "nonzero"):
+        raise ValueError("A value for 'newx' must be supplied")
+    nbeta = np.asarray(list(fit["beta"].values())[m], dtype=np.float64)
+    if nbeta.ndim == 1:
+        nbeta = nbeta[:, None]
+    if s is not None:
+        left, right, frac = lambda_interp(fit["lambda"][m][:nbeta.shape[1]], s)
+        nbeta = nbeta[:, left] * frac[None, :] + nbeta[:, right] * (1.0 - frac)[None, :]
+    if type == "coefficients":
+        return nbeta
+    if type == "nonzero":
+        nz = np.abs(nbeta) > 0
+        nz[0, :] = False                                      # "rem intercept" (R/methods.R:95)
+        return [np.nonzero(nz[:, j])[0] + 1 if nz[:, j].any() else None for j in range(nz.shape[1])]   # 1-based rows
+    binomial = fit.get("family") == "binomial"
+    pred = api.predict_matrix(newx, nbeta, response=(binomial and type == "response"), opts=opts)
+    if type == "class":
+        if not binomial:
+            raise ValueError("type = 'class' is only available for the binomial family")
+        return np.where(pred > 0, 2, 1)                        # index into object$classnames (R/methods.R:359-364)
+    return pred
+
+
+def logLik(fit, which_model=1):
+    """logLik.oem (R/methods.R:431-478, after ncvreg): needs compute_loss=True."""
+    m = _which_model(fit, which_model)
+    loss = np.asarray(fit["loss"][m], dtype=np.float64)
+    if np.all(loss == 1e99):
+        raise ValueError("oem object needed compute.loss set to TRUE. logLik not returned")
+    n = float(fit["nobs"])
+    if fit["family"] == "gaussian":
+        return -0.5 * n * (np.log(2 * np.pi) - np.log(n) + np.log(loss)) - 0.5 * n
+    if fit["family"] == "binomial":
+        return -1.0 * loss
+    raise ValueError(f"family {fit['family']} not available")

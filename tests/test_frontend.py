@@ -102,3 +102,83 @@ def test_big_oem_from_file_backed_matrix(lib, oracle, tmp_path):
     assert np.max(np.abs(r["beta"]["lasso"] - ref["beta"][0])) <= 1e-8
     assert np.max(np.abs(r["beta"]["scad"] - ref["beta"][1])) <= 1e-8
     assert r["stats"]["h2d_bytes"] >= X.nbytes
+
+
+def test_lambda_interp_and_host_predict_types():
+    """R/utils.R:64-87 and the host-only branches of predict.oem (R/methods.R:84-101)."""
+    from oem_b200 import frontend as fe
+    lam = np.array([1.0, 0.5, 0.25, 0.125])
+    left, right, frac = fe.lambda_interp(lam, [0.5, 0.375, 2.0, 0.01])
+    assert list(left) == [1, 1, 0, 3] and list(right) == [1, 2, 0, 3]
+    assert np.allclose(frac, [1.0, 0.5, 1.0, 1.0])
+    B = np.array([[1.0, 2.0, 3.0, 4.0], [0.0, 0.0, 1.0, 2.0], [0.0, -1.0, -1.0, 0.0]])
+    fit = dict(beta={"lasso": B}, family="gaussian", nobs=10, loss=[np.array([4.0, 3.0, 2.0, 1.0])])
+    fit["lambda"] = [lam]
+    co = fe.predict(fit, s=[0.375], type="coefficients")
+    assert np.allclose(co[:, 0], 0.5 * B[:, 1] + 0.5 * B[:, 2])
+    nz = fe.predict(fit, type="nonzero")
+    assert nz[0] is None and list(nz[1]) == [3] and list(nz[2]) == [2, 3] and list(nz[3]) == [2]
+    ll = fe.logLik(fit)
+    assert np.allclose(ll, -0.5 * 10 * (np.log(2 * np.pi) - np.log(10.0) + np.log(fit["loss"][0])) - 5.0)
+    with pytest.raises(ValueError):
+        fe.predict(fit, type="link")                      # newx missing
+    with pytest.raises(ValueError):
+        fe.predict(fit, which_model="mcp", type="coefficients")
+    with pytest.raises(ValueError):
+        fe.predict(fit, which_model=2, type="coefficients")
+    fit["loss"] = [np.full(4, 1e99)]
+    with pytest.raises(ValueError):
+        fe.logLik(fit)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p,L", [(1000, 30, 25), (4097, 57, 100), (333, 7, 1), (2500, 20, 330)])
+def test_predict_on_device(lib, n, p, L):
+    """oemb200_predict: newx %*% beta + intercept as one DMMA GEMM (ragged rows / k / more than 320 columns)"""
+    rng = np.random.default_rng(n + p)
+    X = np.asfortranarray(rng.normal(size=(n, p)))
+    B = np.asfortranarray(rng.normal(size=(p + 1, L)) * (rng.uniform(size=(p + 1, L)) < 0.4))
+    ref = X @ B[1:] + B[0:1]
+    got = lib.predict_matrix(X, B)
+    assert got.shape == (n, L) and np.max(np.abs(got - ref)) <= 1e-12 * max(1.0, np.abs(ref).max())
+    got = lib.predict_matrix(X, B, response=True)
+    assert np.allclose(got, 1.0 / (1.0 + np.exp(-ref)), rtol=1e-13, atol=1e-15)
+    got = lib.predict_matrix(X, B[1:])                    # p-row coefficient matrix (oem.xtx): no intercept row
+    assert np.max(np.abs(got - X @ B[1:])) <= 1e-12 * max(1.0, np.abs(ref).max())
+    import torch
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t()          # column-major device matrix
+    out = torch.empty((L, n), dtype=torch.float64, device="cuda").t()
+    lib.predict_matrix(Xd, B, out=out)
+    assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-12 * max(1.0, np.abs(ref).max())
+    with pytest.raises(Exception):
+        lib.predict_matrix(X, B[:-2])
+
+
+@pytest.mark.gpu
+def test_predict_and_loglik_frontends(lib, oracle):
+    from oem_b200 import frontend as fe
+    X, y = gaussian_problem(61, 3000, 25)
+    fit = fe.oem(X, y, penalty=["lasso", "mcp"], nlambda=20, compute_loss=True)
+    Xn, _ = gaussian_problem(62, 500, 25)
+    for m, pen in enumerate(["lasso", "mcp"]):
+        B = fit["beta"][pen]
+        pr = fe.predict(fit, Xn, which_model=pen)
+        assert np.max(np.abs(pr - (Xn @ B[1:] + B[0:1]))) <= 1e-12 * np.abs(pr).max()
+        lam = fit["lambda"][m]
+        s = [0.5 * (lam[3] + lam[4]), lam[7]]
+        pr = fe.predict(fit, Xn, s=s, which_model=m + 1, type="response")
+        co = fe.predict(fit, s=s, which_model=m + 1, type="coefficients")
+        assert np.allclose(co[:, 0], 0.5 * (B[:, 3] + B[:, 4]), atol=1e-12) and np.allclose(co[:, 1], B[:, 7])
+        assert np.max(np.abs(pr - (Xn @ co[1:] + co[0:1]))) <= 1e-12 * np.abs(pr).max()
+        n = float(X.shape[0])
+        assert np.allclose(fe.logLik(fit, pen), -0.5 * n * (np.log(2 * np.pi) - np.log(n) + np.log(fit["loss"][m])) - 0.5 * n)
+    # without standardisation the loss member is the raw residual sum of squares (src/oem_dense.h:759-770)
+    raw = fe.oem(X, y, penalty=["lasso"], nlambda=10, compute_loss=True, standardize=False, intercept=False)
+    rss = ((y[:, None] - fe.predict(raw, X)) ** 2).sum(axis=0)
+    assert np.allclose(raw["loss"][0], rss, rtol=1e-10)
+    Xb, yb = binomial_problem(63, 2000, 12)
+    fb = fe.oem(Xb, yb, family="binomial", penalty=["lasso"], nlambda=8, lambda_min_ratio=1e-2)
+    Bb = fb["beta"]["lasso"]
+    eta = Xb @ Bb[1:] + Bb[0:1]
+    assert np.allclose(fe.predict(fb, Xb, type="response"), 1 / (1 + np.exp(-eta)), rtol=1e-12)
+    assert np.array_equal(fe.predict(fb, Xb, type="class"), np.where(eta > 0, 2, 1))

@@ -109,6 +109,17 @@ def main():
                          "ms_per_irls_data_pass": (st["ms_irls_xb"] + st["ms_irls_xtr"]) / max(1, st["xb_launches"]),
                          "irls_iterations": int(np.sum(out["niter"][0])), "xb_launches": st["xb_launches"]})
         del X, y
+    if 5 in cfgs:      # next row: predict.oem on device, newx 4e6 x 500, 100 lambdas, output stays on the device
+        n, p, L = int(4e6 * a.scale), 500, 100
+        X, _ = gen(n, p, 106, coef=[.5])
+        rng = np.random.default_rng(106)
+        B = rng.normal(size=(p + 1, L)) * (rng.uniform(size=(p + 1, L)) < 0.1)
+        out_t = torch.empty((L, n), dtype=torch.float64, device=dev).t()
+        w, (_, st) = timed(lambda: api.predict_matrix(X, B, out=out_t, return_stats=True), a.reps)
+        print(json.dumps({"config": "predict.oem newx n=4e6 p=500 L=100 (device in, device out)", "wall_s": w,
+                          "ms_gemm": st["ms_cvscore"], "gemm_tflops": 2.0 * n * p * L / (st["ms_cvscore"] / 1e3) / 1e12,
+                          "out_gb": n * L * 8 / 1e9}), flush=True)
+        del X, out_t
     torch.cuda.empty_cache()
 
 
