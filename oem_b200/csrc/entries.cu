@@ -308,6 +308,8 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
     fill_common_outputs(su, res);
     memset(res->beta, 0, sizeof(double) * (size_t)su.P * (p + 1) * L);
     DBuf<double> d_b, d_eta, d_l2;
+    // losses of all (penalty, lambda) columns in ONE pass over X when the TMA can address it (else per-lambda sweeps)
+    const bool loss_gemm = s->compute_loss && res->loss && !(X.ld & 1) && !(reinterpret_cast<uintptr_t>(X.p) & 15);
     for (int pp = 0; pp < su.P; ++pp)
         for (int i = 0; i < su.nlam_run[pp]; ++i) {
             const double *raw = &pb.h_beta[((size_t)pp * L + i) * p];
@@ -326,9 +328,9 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
             }
             out[0] = b0;
             res->niter[(size_t)pp * L + i] = pb.h_niter[(size_t)pp * L + i];
-            if (s->compute_loss && res->loss) {
+            if (s->compute_loss && res->loss && !loss_gemm) {
                 // get_loss(): ||Y_std - X_std beta_std||^2 (src/oem_dense.h:759-770) as one more X b pass:
-                // X_std b = X (b / s) - sum_j m_j b_j / s_j
+                // X_std b = X (b / s) - sum_j m_j b_j / s_j   (sweep fallback for X the TMA cannot address)
                 std::vector<double> bs(p);
                 double off = 0.0;
                 for (int j = 0; j < p; ++j) {
@@ -349,6 +351,42 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
                 res->loss[(size_t)pp * L + i] = h[1];
             }
         }
+    if (loss_gemm) {
+        // get_loss(): ||Y_std - X_std beta_std||^2 (src/oem_dense.h:759-770).  X_std b = X (b / s) - sum_j m_j b_j / s_j, so
+        // every column is (y_std - b0' - X b')^2 summed over rows: the CV-scoring GEMM with its squared-error moments.
+        const int nc = su.P * L, ncld = cv_ncld(nc);
+        std::vector<double> hB((size_t)p * ncld, 0.0), hb0(ncld, 0.0);
+        for (int pp = 0; pp < su.P; ++pp)
+            for (int i = 0; i < su.nlam_run[pp]; ++i) {
+                const double *raw = &pb.h_beta[((size_t)pp * L + i) * p];
+                const int c = pp * L + i;
+                double off = 0.0;
+                for (int j = 0; j < p; ++j) {
+                    const double b = (flag == 1 || flag == 3) ? raw[j] / scaleX[j] : raw[j];
+                    hB[(size_t)j * ncld + c] = b;
+                    if (center_x) off -= b * meanX[j];
+                }
+                hb0[c] = off;
+            }
+        DBuf<double> dB(hB.size()), db0(hb0.size()), out3(3 * (size_t)nc);
+        dB.upload(hB.data(), hB.size(), cx.stream);
+        db0.upload(hb0.data(), hb0.size(), cx.stream);
+        std::vector<std::array<int64_t, 3>> cs{{0, n, n}};
+        cvscore_launch(cx, X.p, n, p, X.ld, yuse, nullptr, 1, cs, dB.p, db0.p, nc, false, out3.p);
+        std::vector<double> h3(3 * (size_t)nc), tot(nc);
+        out3.download(h3.data(), h3.size(), cx.stream);
+        cx.sync();
+        for (int c = 0; c < nc; ++c) tot[c] = h3[c] * h3[nc + c];          // count * mean = sum
+        if (cx.allreduce) {
+            DBuf<double> dt(nc);
+            dt.upload(tot.data(), nc, cx.stream);
+            cx.all_reduce(dt.p, nc);
+            dt.download(tot.data(), nc, cx.stream);
+            cx.sync();
+        }
+        for (int pp = 0; pp < su.P; ++pp)
+            for (int i = 0; i < su.nlam_run[pp]; ++i) res->loss[(size_t)pp * L + i] = tot[pp * L + i];
+    }
     *res->d = pb.h_d[0];
     finish_stats(cx, tm, t_total, res);
 }
