@@ -354,6 +354,34 @@ __device__ __forceinline__ void st_cluster_f64(double *local_smem_ptr, unsigned 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
 }
+// asynchronous DSMEM stores that complete a transaction count on the DESTINATION CTA's mbarrier: the receiver waits on its
+// own barrier for the expected bytes, so the sender needs neither a fence nor a cluster-wide barrier round trip
+__device__ __forceinline__ unsigned map_cluster(const void *local_smem_ptr, unsigned cta_rank) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+    return remote;
+}
+__device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_u32(unsigned remote_addr, unsigned v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "r"(v), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 
 
 // slow path of the coordinate-wise prox (non-zero result), out of line: the persistent loop must stay small
@@ -844,6 +872,276 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-resident variant for the common small problem: q <= 256, coordinate-wise penalties only
+// (lasso / ols / elastic.net / mcp / scad and their .net forms), no Nesterov, no scale.factor, cold start.
+//
+// A team is a cluster of NC <= 8 CTAs (1 CTA for q <= 128).  A CTA owns 8 * CPW columns of A = dI - XX; warp w owns
+// CPW of them and keeps its CPW x q block IN REGISTERS for the whole path (lane l holds rows l, l + 32, ...:
+// CPW * KPL <= 64 doubles per thread), so an OEM iteration reads nothing but the iterate from shared memory:
+//     b[i]     = beta_c[l + 32 i]                       KPL conflict-free LDS per chain
+//     acc[cc]  = sum_i A[cc][i] b[i]                    CPW independent DFMA chains (the FP64 CUDA-core pipe runs at
+//                                                       the same rate as DMMA on this part, and a 1..4-column B
+//                                                       operand would waste 4/8..7/8 of every DMMA)
+//     multi-value butterfly over the 32 lanes           CPW - 1 + log2(32 / CPW) shuffles, fixed order
+//     the 32 / CPW lanes that end up with column j's sum apply u = sum + XY_j, the coordinate-wise prox and the stop
+//     rule (XY_j, pf_j and the previous beta_j live in their registers) and store the new beta_j into every member's
+//     next-iterate buffer (DSMEM), each lane serving a different member
+// then ONE cluster barrier per iteration (a __syncthreads for one CTA).  The per-warp violation masks travel with
+// the same barrier; all threads keep the per-chain state (iteration count, lambda index) redundantly in registers,
+// so nothing else is synchronised until a chain moves to its next lambda.
+// sums acc[c][*] over the 32 lanes for NCT chains at once (stage-major so the chains' shuffles overlap):
+// on return tot[c] in lane l is the total of column l / (32 / CPW)
+template <int NCT, int CPW>
+__device__ __forceinline__ void reduce_cols(double (&acc)[NCT][CPW], double (&tot)[NCT], int lane) {
+#pragma unroll
+    for (int n = CPW, off = 16; n > 1; n >>= 1, off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int c = 0; c < NCT; ++c)
+#pragma unroll
+            for (int v = 0; v < n / 2; ++v) {
+                const double keep = hi ? acc[c][v + n / 2] : acc[c][v];
+                const double send = hi ? acc[c][v] : acc[c][v + n / 2];
+                acc[c][v] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < NCT; ++c) tot[c] = acc[c][0];
+#pragma unroll
+    for (int off = 16 / CPW; off >= 1; off >>= 1)
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) tot[c] += __shfl_xor_sync(0xffffffffu, tot[c], off);
+}
+
+constexpr int PR_MAXCT = 4;       // chains per Gram handled by the register variant
+
+// coordinate-wise prox with the per-lambda constants cp[0..7] (see set_cpar) -- same arithmetic as mv_finish
+__device__ __forceinline__ double prox_coord(int kind, double u, double pfj, const double *cp, double gamma) {
+    const double tp = pfj * cp[0];
+    if (kind == 3) return div_r(u, cp[1], cp[4]);
+    if (!abs_gt(u, tp * cp[2])) return 0.0;            // every rule returns 0 below its first threshold
+    const double dp = cp[1], rdp = cp[4], gammad = cp[5], den2 = cp[6], rden2 = cp[7];
+    if (kind == 2) return st_scad_r(u, tp, dp, rdp, gamma, gammad, den2, rden2);
+    if (kind == 1) return st_mcp_r(u, tp, dp, rdp, gammad, den2, rden2);
+    return st_lasso_r(u, tp, dp, rdp);
+}
+
+template <int CPW, int KPL, int NCT>
+__global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathArgs a) {
+    constexpr int LPC = 32 / CPW;             // lanes that share one column after the butterfly
+    constexpr int QP = KPL * 32;              // padded vector length
+    extern __shared__ __align__(16) double sm[];
+    const int q = a.q, NC = a.team_size;
+    const int team = blockIdx.x / NC, rank = blockIdx.x - team * NC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ct0 = a.team_ptr[team], nct = a.team_ptr[team + 1] - ct0;      // nct <= NCT (teams may have fewer chains)
+
+    double *Bsm = sm;                                         // [2][NCT][QP]
+    double *lam_sm = Bsm + 2 * NCT * QP;                      // [NCT][Lmax]
+    double *cpar = lam_sm + (size_t)NCT * a.Lmax;             // [NCT][8]
+    double *chd = cpar + NCT * 8;                             // alpha, gamma per chain: [2][NCT]
+    uint64_t *xbar = reinterpret_cast<uint64_t *>(chd + 2 * NCT);   // [2]: per-parity transaction barriers of the exchange
+    int *flags = reinterpret_cast<int *>(xbar + 2);           // [2][64]: violation masks by (parity, member, warp)
+    int *chi = flags + 128;                                   // penalty, nlam, out_off, kind: [4][NCT]
+
+    const int j = rank * (8 * CPW) + warp * CPW + lane / LPC; // the column this lane finishes
+    const int sub = lane % LPC;
+    const bool jvalid = j < q;
+    const double dval = a.d[team];
+    const double *XXg = a.XX + (size_t)team * q * q;
+
+    // ---- one-time loads ----
+    double A[CPW][KPL];
+#pragma unroll
+    for (int cc = 0; cc < CPW; ++cc) {
+        const int jj = rank * (8 * CPW) + warp * CPW + cc;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int k = lane + 32 * i;
+            double x = 0.0;
+            if (jj < q && k < q) { x = -XXg[(size_t)jj * q + k]; if (k == jj) x += dval; }
+            A[cc][i] = x;
+        }
+    }
+    const double xyj = jvalid ? a.XY[(size_t)team * q + j] : 0.0;
+    const double pfj = jvalid ? (a.pen_fact ? a.pen_fact[j] : 1.0) : 0.0;
+    for (int e = threadIdx.x; e < 2 * NCT * QP; e += PK_THREADS) Bsm[e] = 0.0;
+    for (int e = threadIdx.x; e < 128; e += PK_THREADS) flags[e] = 0;
+    if (threadIdx.x == 0) { mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1); mbar_fence_init(); }
+    if (threadIdx.x < NCT) {
+        const int c = threadIdx.x;
+        if (c < nct) {
+            const ChainDev ch = a.chains[a.team_idx[ct0 + c]];
+            const int pen = ch.penalty;
+            chi[c] = pen; chi[NCT + c] = ch.nlam; chi[2 * NCT + c] = ch.out_off;
+            chi[3 * NCT + c] = pen == OEMB200_PEN_OLS ? 3
+                             : (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET) ? 2
+                             : (pen == OEMB200_PEN_MCP || pen == OEMB200_PEN_MCP_NET) ? 1 : 0;
+            chd[c] = ch.alpha; chd[NCT + c] = ch.gamma;
+            for (int l = 0; l < a.Lmax; ++l) lam_sm[(size_t)c * a.Lmax + l] = l < ch.nlam ? a.lambdas[ch.lam_off + l] : 0.0;
+        } else {
+            chi[c] = 0; chi[NCT + c] = 0; chi[2 * NCT + c] = 0; chi[3 * NCT + c] = 0;
+            chd[c] = 1.0; chd[NCT + c] = 3.0;
+            for (int l = 0; l < a.Lmax; ++l) lam_sm[(size_t)c * a.Lmax + l] = 0.0;
+        }
+    }
+    __syncthreads();
+    // per-lambda derived constants of chain c: thresholds, denominators and their reciprocals (as in the generic kernel)
+    auto set_cpar = [&](int c, int li) {
+        const int pen = chi[c];
+        const double alpha = chd[c], gamma = chd[NCT + c];
+        const double lambda = lam_sm[(size_t)c * a.Lmax + min(li, a.Lmax - 1)];
+        double denom = dval + (1.0 - alpha) * lambda, lam = lambda * alpha;
+        if (pen == OEMB200_PEN_SCAD_NET && alpha == 0.0) { lam = 0.0; denom = dval + lambda; }
+        const bool net = (pen == OEMB200_PEN_ENET || pen == OEMB200_PEN_SCAD_NET || pen == OEMB200_PEN_MCP_NET);
+        const double lp = net ? lam : lambda, dp = net ? denom : dval;
+        const bool is_scad = (pen == OEMB200_PEN_SCAD || pen == OEMB200_PEN_SCAD_NET);
+        const bool is_mcp = (pen == OEMB200_PEN_MCP || pen == OEMB200_PEN_MCP_NET);
+        const double gammad = gamma * dp;
+        const double den2 = is_mcp ? dp - 1.0 / gamma : (gamma - 1.0) * dp - 1.0;
+        double *cp = cpar + c * 8;
+        cp[0] = lp; cp[1] = dp; cp[2] = (is_scad || is_mcp) ? fmin(1.0, gammad) : 1.0; cp[3] = lambda;
+        cp[4] = 1.0 / dp; cp[5] = gammad; cp[6] = den2; cp[7] = 1.0 / den2;
+    };
+    if (threadIdx.x < NCT) set_cpar(threadIdx.x, 0);
+
+    // replicated per-chain state (identical in every thread of the team)
+    int iter[NCT], lidx[NCT], kind[NCT];
+    double prev[NCT], gam[NCT];
+    unsigned done = 0u;
+#pragma unroll
+    for (int c = 0; c < NCT; ++c) {
+        iter[c] = 0; lidx[c] = 0; prev[c] = 0.0;
+        kind[c] = chi[3 * NCT + c];
+        gam[c] = chd[NCT + c];
+        if (c >= nct || chi[NCT + c] <= 0) done |= 1u << c;
+    }
+    if (NC > 1) cluster_sync_all();      // peers may start storing into my buffers
+    else __syncthreads();
+    // per-lambda constants of every chain live in registers; refreshed when a chain moves to its next lambda
+    double cp[NCT][8];
+#pragma unroll
+    for (int c = 0; c < NCT; ++c)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cp[c][e] = cpar[c * 8 + e];
+
+    const unsigned all = (1u << NCT) - 1u;
+    int par = 0;
+    long long niters = 0, tmv = 0, tbar = 0;
+    const bool prof = a.prof != nullptr;
+    const long long tstart = clock64();
+    while (done != all) {
+        const double *Bc = Bsm + (size_t)par * NCT * QP;
+        double *Bn = Bsm + (size_t)(par ^ 1) * NCT * QP;
+        const long long tp0 = prof ? clock64() : 0;
+        // ---- u = A' beta + XY for all chains (finished chains ride along: their results are discarded) ----
+        double acc[NCT][CPW], tot[NCT];
+        {
+            double b[NCT][KPL];
+#pragma unroll
+            for (int c = 0; c < NCT; ++c)
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) b[c][i] = Bc[c * QP + lane + 32 * i];
+#pragma unroll
+            for (int c = 0; c < NCT; ++c)
+#pragma unroll
+                for (int cc = 0; cc < CPW; ++cc) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) s = fma(A[cc][i], b[c][i], s);
+                    acc[c][cc] = s;
+                }
+        }
+        reduce_cols<NCT, CPW>(acc, tot, lane);
+        // ---- coordinate-wise prox (src/oem_dense.h:527-629) and stop rule (src/utils.cpp:537-549) on the owner lanes ----
+        unsigned viol = 0u;
+        double rnew[NCT];
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            double r = prox_coord(kind[c], tot[c] + xyj, pfj, cp[c], gam[c]);
+            if (!jvalid) r = 0.0;
+            const double pv = prev[c];
+            if (__double_as_longlong(r) != __double_as_longlong(pv)) {
+                const bool bc = abs_gt(r, 1e-13), bp = abs_gt(pv, 1e-13);
+                if (bc != bp || (bc && abs_gt(r - pv, a.tol * fabs(pv)))) viol |= 1u << c;
+            }
+            rnew[c] = r;
+        }
+        viol &= ~done;
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            if ((done >> c) & 1u) continue;
+            prev[c] = rnew[c];
+            if (jvalid) {
+                double *dst = Bn + c * QP + j;
+                if (NC == 1) { if (sub == 0) *dst = rnew[c]; }
+                else
+                    for (int rr = sub; rr < NC; rr += LPC)
+                        st_async_f64(map_cluster(dst, (unsigned)rr), rnew[c], map_cluster(&xbar[par], (unsigned)rr));
+            }
+        }
+        viol = __reduce_or_sync(0xffffffffu, viol);
+        const long long tp1 = prof ? clock64() : 0;
+        if (NC == 1) {
+            if (lane == 0) flags[par * 64 + warp] = (int)viol;
+            __syncthreads();
+        } else {
+            // every member receives q values per live chain and NC * 8 warp masks on its parity barrier
+            if (lane < NC)
+                st_async_u32(map_cluster(&flags[par * 64 + rank * 8 + warp], (unsigned)lane), viol,
+                             map_cluster(&xbar[par], (unsigned)lane));
+            if (threadIdx.x == 0)
+                mbar_arrive_expect_tx(&xbar[par], (uint32_t)(q * __popc(~done & all) * 8 + NC * 8 * 4));
+            mbar_wait_cluster(&xbar[par], (uint32_t)((niters >> 1) & 1));
+        }
+        const long long tp2 = prof ? clock64() : 0;
+        unsigned bad = 0u;
+        if (lane < NC * 8) bad = (unsigned)flags[par * 64 + lane];
+        if (lane + 32 < NC * 8) bad |= (unsigned)flags[par * 64 + lane + 32];
+        bad = __reduce_or_sync(0xffffffffu, bad);
+        // ---- chain state (every thread, identically) ----
+        unsigned advanced = 0u;
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            if ((done >> c) & 1u) continue;
+            const int it = iter[c] + 1;
+            const bool conv = !((bad >> c) & 1u);
+            if (conv || it >= a.maxit) {
+                const int li = lidx[c];
+                const size_t col = (size_t)chi[2 * NCT + c] * a.Lmax + li;
+                if (jvalid && sub == 0) a.beta_out[col * q + j] = prev[c];
+                if (blockIdx.x == team * NC && threadIdx.x == 0) a.niter_out[col] = conv ? it : a.maxit + 1;
+                iter[c] = 0;
+                lidx[c] = li + 1;
+                if (li + 1 >= chi[NCT + c]) done |= 1u << c;
+                else advanced |= 1u << c;
+            } else {
+                iter[c] = it;
+            }
+        }
+        if (advanced) {        // uniform over the whole team: new per-lambda constants before the next epilogue reads them
+#pragma unroll
+            for (int c = 0; c < NCT; ++c)
+                if (((advanced >> c) & 1u) && threadIdx.x == c) set_cpar(c, lidx[c]);
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < NCT; ++c)
+                if ((advanced >> c) & 1u) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) cp[c][e] = cpar[c * 8 + e];
+                }
+        }
+        par ^= 1;
+        ++niters;
+        if (prof) { tmv += tp1 - tp0; tbar += tp2 - tp1; }
+    }
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
+        a.prof[0] += clock64() - tstart; a.prof[3] += niters; a.prof[1] += tmv; a.prof[2] += tbar;
+    }
+    if (NC > 1) cluster_sync_all();      // no member may exit while peers can still write its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------
 void path_launch(Ctx &cx, const PathProblem &pp) {
     const int q = pp.q, G = pp.ngram;
     if (q <= 0 || G <= 0) fail(OEMB200_EINVAL, "path: empty problem");
@@ -865,6 +1163,65 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         const ChainDesc &c = pp.chains[i];
         if (c.nlam > pp.Lmax) fail(OEMB200_EINVAL, "path: chain has more lambdas than Lmax");
         cd[i] = ChainDev{c.gram, c.penalty, c.nlam, c.lam_off, c.alpha, c.gamma, c.tau, c.out_off, 0};
+    }
+
+    // ---- small coordinate-wise problems: register-resident variant (d comes from a Lanczos-only generic launch) ----
+    {
+        bool reg_ok = getenv("OEMB200_PATH_GENERIC") == nullptr && q <= 256 && !pp.accelerate && !pp.post_scale &&
+                      !pp.beta_init && !pp.beta_final && max_ct <= PR_MAXCT && !pp.chains.empty();
+        for (auto &c : pp.chains) reg_ok = reg_ok && c.penalty < OEMB200_PEN_GRP_LASSO;
+        const int NC = q <= 128 ? 1 : (q + 31) / 32;
+        const int QP = q <= 128 ? 128 : 256;
+        const int Lm = std::max(pp.Lmax, 1);
+        const int nctt = std::max(1, std::min(max_ct, PR_MAXCT));
+        const size_t smem_bytes = ((size_t)2 * nctt * QP + (size_t)nctt * Lm + nctt * 8 + 2 * nctt + 2) * 8 + (128 + 4 * nctt) * 4;
+        if (reg_ok && G * NC <= cx.num_sms && smem_bytes <= cx.smem_optin) {
+            if (pp.compute_eig) {
+                PathProblem eig = pp;
+                eig.chains.clear();
+                path_launch(cx, eig);
+            }
+            DBuf<ChainDev> d_chains(cd.size());
+            DBuf<int> d_tptr(tptr.size()), d_tidx(tidx.size());
+            d_chains.upload(cd.data(), cd.size(), cx.stream);
+            d_tptr.upload(tptr.data(), tptr.size(), cx.stream);
+            d_tidx.upload(tidx.data(), tidx.size(), cx.stream);
+            PathArgs a;
+            memset(&a, 0, sizeof a);
+            a.q = q; a.qs = QP; a.ngram = G; a.team_size = NC; a.cpc = q <= 128 ? 128 : 32; a.max_ct = max_ct; a.Lmax = Lm;
+            a.maxit = pp.maxit; a.tol = pp.tol;
+            a.XX = pp.XX; a.XY = pp.XY; a.d = pp.d;
+            a.chains = d_chains.p; a.team_ptr = d_tptr.p; a.team_idx = d_tidx.p;
+            a.lambdas = pp.lambdas; a.pen_fact = pp.pen_fact; a.beta_out = pp.beta_out; a.niter_out = pp.niter_out;
+            DBuf<long long> d_prof;
+            const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;
+            if (prof) { d_prof.alloc(16); d_prof.zero(cx.stream); a.prof = d_prof.p; }
+            void *kern = nullptr;
+#define PR_PICK(N)                                                                                                   \
+    case N: kern = q <= 128 ? (void *)oem_path_reg_kernel<16, 4, N> : (void *)oem_path_reg_kernel<4, 8, N>; break
+            switch (nctt) { PR_PICK(1); PR_PICK(2); PR_PICK(3); default: PR_PICK(4); }
+#undef PR_PICK
+            OEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            void *kargs[] = {&a};
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(G * NC); cfg.blockDim = dim3(PK_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = cx.stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            OEM_CUDA(cudaLaunchKernelExC(&cfg, kern, kargs));
+            cx.st.kernel_launches += 1;
+            if (prof) {
+                long long h[16];
+                d_prof.download(h, 16, cx.stream);
+                OEM_CUDA(cudaStreamSynchronize(cx.stream));
+                fprintf(stderr, "[path prof] register variant: team=%d q=%d nct=%d | iters=%lld cyc/iter=%.0f (matvec+prox %.0f, barrier %.0f)\n",
+                        NC, q, max_ct, h[3], h[3] ? (double)h[0] / h[3] : 0.0, h[3] ? (double)h[1] / h[3] : 0.0,
+                        h[3] ? (double)h[2] / h[3] : 0.0);
+            }
+            return;
+        }
     }
 
     // ---- geometry: mode, team size, column slice, shared memory ----
