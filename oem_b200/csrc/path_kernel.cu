@@ -17,13 +17,16 @@
 // is streamed from L2.  Each OEM iteration is
 //     u[slice] = A[:,slice]' beta + XY[slice]   for all of the team's chains at once: a skinny GEMM
 //                                               (columns x chains x q) on the FP64 TENSOR pipe
-//                                               (DMMA.8x8x4; measured on B200 the FP64 CUDA-core
-//                                               rate is ~1/4 of the DMMA rate, so even this small
-//                                               product belongs on the tensor pipe)
-//     ONE exchange of u + ONE team barrier
-//     every member redundantly applies the prox and the stop rule to the full vector
+//                                               (DMMA.8x8x4, A fragments from shared memory)
+//     coordinate-wise penalties: the member that owns coordinate j applies the prox and the stop rule in the
+//     mat-vec epilogue and publishes the NEXT BETA; group penalties / Nesterov publish u and every member
+//     applies the prox redundantly to the full vector
+//     ONE exchange + ONE team barrier
 // All members execute bit-identical arithmetic on identical inputs, so they take the same
 // convergence decisions without any further communication.  Reductions use fixed orders.
+// Small problems (q <= 256, coordinate-wise penalties) take the register-resident variant further down
+// (oem_path_reg_kernel): there a DMMA would waste 4/8..7/8 of its B operand on 1..4 chains, and the FP64
+// CUDA-core pipe (measured: same rate as DMMA on B200) runs the product from registers.
 // Three exchange modes, chosen on the host from q:
 //     MODE_SINGLE   the whole A fits one CTA: u goes straight into shared memory, __syncthreads only
 //     MODE_CLUSTER  A fits the shared memory of a thread-block cluster (<= 8 CTAs): every member stores

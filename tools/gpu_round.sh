@@ -6,7 +6,7 @@ python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/
 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 python bench.py > gpurun_out/bench_full.log 2>&1; tail -1 gpurun_out/bench_full.log | cut -c1-400
 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_reference.log 2>&1; tail -1 gpurun_out/bench_reference.log | cut -c1-300
-python tools/bench_configs.py > gpurun_out/bench_configs.log 2>&1; cut -c1-300 gpurun_out/bench_configs.log
+python tools/bench_configs.py --configs 1,2,3,4,5 > gpurun_out/bench_configs.log 2>&1; cut -c1-300 gpurun_out/bench_configs.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
     python bench.py --rows 2000000 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gram_syrk -s 1 -c 1 -o gpurun_out/prof_gram \
@@ -21,4 +21,7 @@ ncu --set full --clock-control none -k regex:xb_kernel -s 2 -c 1 -o gpurun_out/p
     python tools/bench_configs.py --configs 4 --scale 0.5 --reps 1 > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_xval.csv \
     python tools/bench_configs.py --configs 3 --scale 0.2 --reps 1 > /dev/null 2>&1
+ncu --set full --clock-control none -k regex:oem_path_reg -c 1 -o gpurun_out/prof_pathreg \
+    python tools/bench_configs.py --configs 2 --reps 1 > /dev/null 2>&1
+OEMB200_PATH_PROF=1 python tools/bench_configs.py --configs 1,2 --reps 1 2>&1 | grep 'path prof' > gpurun_out/path_prof.log
 ls -la gpurun_out
