@@ -11,6 +11,7 @@
 // arithmetic on X, on the Gram and on beta runs in the CUDA kernels.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "host_common.h"
 
@@ -102,11 +103,18 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
     vecsum_launch(cx, yv.p, n, 0.0, ysum, false);
     tm.stop(t_y);
 
+    // column sums, X'y and sum x^2 ride in the Gram launch (diagonal-tile CTAs); OEMB200_SEPARATE_COLSTATS=1 keeps the
+    // separate HBM sweep (colstats_kernel) for A/B measurements
+    const bool fused_stats = getenv("OEMB200_SEPARATE_COLSTATS") == nullptr;
     if (is_device_ptr(x)) {
-        const size_t t1 = tm.start(&cx.st.ms_colstats);
-        colstats_launch(cx, x, n, p, ldx, nullptr, yv.p, nullptr, stats, false);
-        tm.stop(t1);
-        gram_launch(cx, x, n, p, ldx, {RowSegment{0, n, 0}}, 1, nullptr, nullptr, G, false);
+        if (fused_stats) {
+            gram_launch(cx, x, n, p, ldx, {RowSegment{0, n, 0}}, 1, nullptr, nullptr, G, false, yv.p, stats);
+        } else {
+            const size_t t1 = tm.start(&cx.st.ms_colstats);
+            colstats_launch(cx, x, n, p, ldx, nullptr, yv.p, nullptr, stats, false);
+            tm.stop(t1);
+            gram_launch(cx, x, n, p, ldx, {RowSegment{0, n, 0}}, 1, nullptr, nullptr, G, false);
+        }
     } else {
         // host X: double-buffered row chunks; H2D of chunk c+1 overlaps the kernels of chunk c
         const double gigs = o->gigs > 0 ? o->gigs : 1.0;
@@ -141,8 +149,12 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
             const int64_t r0 = c * rows, nr = std::min(rows, n - r0);
             if (c + 1 < nchunks) issue_copy(c + 1);
             OEM_CUDA(cudaStreamWaitEvent(cx.stream, ready[b], 0));
-            colstats_launch(cx, stage[b].p, nr, p, rows, nullptr, yv.p + r0, nullptr, stats, c > 0);
-            gram_launch(cx, stage[b].p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, nullptr, G, c > 0);
+            if (fused_stats) {
+                gram_launch(cx, stage[b].p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, nullptr, G, c > 0, yv.p + r0, stats);
+            } else {
+                colstats_launch(cx, stage[b].p, nr, p, rows, nullptr, yv.p + r0, nullptr, stats, c > 0);
+                gram_launch(cx, stage[b].p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, nullptr, G, c > 0);
+            }
             OEM_CUDA(cudaEventRecord(freed[b], cx.stream));
         }
         tm.stop(t_h);

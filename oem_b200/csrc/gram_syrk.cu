@@ -52,11 +52,16 @@ struct GramTile {
     int pi, pj, slot0, nslots, out, pad;
 };
 
-template <bool CENTER, bool WEIGHT, bool USE_TMA>
+// STATS: the diagonal-tile CTAs also accumulate, for the 128 columns of their panel, sum x, sum x*y and sum x^2 over the
+// item's rows (the column sweeps of src/oem_big.h:743-837) from the A fragments they load anyway: warp w owns atom rows
+// w and 15-w, so the 8 warps cover the panel's 16 column atoms exactly once.  The DFMAs run on the FP64 CUDA-core pipe
+// next to the DMMA stream; a separate HBM sweep of X (colstats_kernel) is no longer needed.
+template <bool CENTER, bool WEIGHT, bool USE_TMA, bool STATS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restrict__ X, long long ld,
                  long long nrows, int q, const GramItem *__restrict__ items, const double *__restrict__ mean,
-                 const double *__restrict__ roww, double *__restrict__ ws) {
+                 const double *__restrict__ roww, double *__restrict__ ws, const double *__restrict__ yvec,
+                 double *__restrict__ stats_ws, int npanels) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *panels = reinterpret_cast<double *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + G_STAGES * G_STAGE_BYTES);
@@ -257,6 +262,7 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
         double acc[17][2];
 #pragma unroll
         for (int sl = 0; sl < 17; ++sl) acc[sl][0] = acc[sl][1] = 0.0;
+        double st_lo[3] = {0.0, 0.0, 0.0}, st_hi[3] = {0.0, 0.0, 0.0};      // sum x, sum x*y, sum x^2 of my two columns
 
         for (int kt = 0; kt < nk; ++kt) {
             const int s = kt % G_STAGES;
@@ -270,6 +276,14 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
                     wv[ks] = r < nrows ? __ldg(roww + r) : 0.0;
                 }
             }
+            double yv[G_KSTEPS];
+            if (STATS) {
+#pragma unroll
+                for (int ks = 0; ks < G_KSTEPS; ++ks) {
+                    const long long r = rbase + ks * 4;
+                    yv[ks] = (yvec && r < it.row1) ? __ldg(yvec + r) : 0.0;
+                }
+            }
             const bool tail = CENTER && (it.row0 + (long long)(kt + 1) * G_KT > nrows);
             mbar_wait(&full[s], ph);
             const double *pA = panels + (size_t)s * 2 * G_PANEL;
@@ -277,6 +291,11 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
             for (int ks = 0; ks < G_KSTEPS; ++ks) {
                 double alo = pA[offAlo + ks * 4], ahi = pA[offAhi + ks * 4];
                 const bool valid = !tail || (rbase + ks * 4 < nrows);
+                if (STATS) {
+                    // rows past the item's end only occur in the matrix's last k-tile, where the loader zero-fills them
+                    st_lo[0] += alo; st_lo[1] = fma(alo, yv[ks], st_lo[1]); st_lo[2] = fma(alo, alo, st_lo[2]);
+                    st_hi[0] += ahi; st_hi[1] = fma(ahi, yv[ks], st_hi[1]); st_hi[2] = fma(ahi, ahi, st_hi[2]);
+                }
                 if (CENTER) { alo -= mlo; ahi -= mhi; }
                 if (WEIGHT) { alo *= wv[ks]; ahi *= wv[ks]; }
 #pragma unroll
@@ -297,6 +316,24 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
                 } else {
                     mbar_wait(&empty[s], ph);
                     load_tile(kt + G_STAGES);
+                }
+            }
+        }
+        if (STATS) {
+            // fixed-order sum over the 4 row lanes t of each column, then one partial per (row chunk, panel)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                st_lo[e] += __shfl_xor_sync(0xffffffffu, st_lo[e], 1);
+                st_lo[e] += __shfl_xor_sync(0xffffffffu, st_lo[e], 2);
+                st_hi[e] += __shfl_xor_sync(0xffffffffu, st_hi[e], 1);
+                st_hi[e] += __shfl_xor_sync(0xffffffffu, st_hi[e], 2);
+            }
+            if (t == 0) {
+                double *so = stats_ws + ((size_t)it.pad * npanels + it.pi) * (3 * G_TILE);
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    so[e * G_TILE + rlo * 8 + g] = st_lo[e];
+                    so[e * G_TILE + rhi * 8 + g] = st_hi[e];
                 }
             }
         }
@@ -330,6 +367,25 @@ gram_reduce_kernel(const double *__restrict__ ws, const GramTile *__restrict__ t
     Go[(size_t)gi * q + gj] = s;
 }
 
+// stats_out[o][e][j] (+)= sum over the row chunks of output o (in chunk order) of the diagonal CTAs' partial sums
+__global__ void gram_stats_reduce_kernel(const double *__restrict__ stats_ws, const int *__restrict__ chunk_out, int nchunks,
+                                         int npanels, int q, int nout, double *__restrict__ stats_out, int accumulate) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y;
+    if (j >= q) return;
+    const int pi = j / G_TILE, jl = j - pi * G_TILE;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int c = 0; c < nchunks; ++c) {
+        if (chunk_out[c] != o) continue;
+        const double *so = stats_ws + ((size_t)c * npanels + pi) * (3 * G_TILE) + jl;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) s[e] += so[e * G_TILE];
+    }
+    double *out = stats_out + (size_t)o * 3 * q;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) out[(size_t)e * q + j] = accumulate ? out[(size_t)e * q + j] + s[e] : s[e];
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -350,17 +406,20 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <bool C, bool W, bool T>
+template <bool C, bool W, bool T, bool S>
 static void launch_variant(Ctx &cx, const CUtensorMap &tm, const double *X, int64_t ld, int64_t n, int q,
-                           const GramItem *d_items, int nitems, const double *mean, const double *roww, double *ws) {
-    auto kern = gram_syrk_kernel<C, W, T>;
+                           const GramItem *d_items, int nitems, const double *mean, const double *roww, double *ws,
+                           const double *yvec, double *stats_ws, int npanels) {
+    auto kern = gram_syrk_kernel<C, W, T, S>;
     OEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
-    kern<<<nitems, G_THREADS, G_SMEM_BYTES, cx.stream>>>(tm, X, ld, n, q, d_items, mean, roww, ws);
+    kern<<<nitems, G_THREADS, G_SMEM_BYTES, cx.stream>>>(tm, X, ld, n, q, d_items, mean, roww, ws, yvec, stats_ws, npanels);
     OEM_CUDA(cudaGetLastError());
 }
 
 void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const std::vector<RowSegment> &segs,
-                 int nout, const double *mean, const double *roww, double *G, bool accumulate) {
+                 int nout, const double *mean, const double *roww, double *G, bool accumulate, const double *stats_y,
+                 double *stats_out) {
+    if (stats_out && (mean || roww)) fail(OEMB200_EINVAL, "gram: fused column statistics need the plain (uncentred, unweighted) mode");
     if (n <= 0 || q <= 0) fail(OEMB200_EINVAL, "gram: empty matrix (n=%lld, p=%d)", (long long)n, q);
     if (n >= (1ll << 31)) fail(OEMB200_EINVAL, "gram: more than 2^31-1 rows per call; shard or chunk the rows");
     const int P = (q + G_TILE - 1) / G_TILE;
@@ -395,7 +454,7 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     // slots of one (segment-out, tile) must be contiguous: slot = tilebase + chunk index
     // first count chunks per out
     std::vector<int> chunks_per_out(nout, 0);
-    struct Chunk { int64_t r0, r1; int out, idx; };
+    struct Chunk { int64_t r0, r1; int out, idx; };      // position in `chunks` = global chunk index (stats slot)
     std::vector<Chunk> chunks;
     for (auto &s : segs) {
         const int64_t len = s.row1 - s.row0;
@@ -411,12 +470,13 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     std::vector<int> out_base(nout + 1, 0);
     for (int o = 0; o < nout; ++o) out_base[o + 1] = out_base[o] + chunks_per_out[o] * ntile_pairs;
     const int nslots = out_base[nout];
-    for (auto &c : chunks) {
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk &c = chunks[ci];
         int tp = 0;
         for (int pi = 0; pi < P; ++pi)
             for (int pj = 0; pj <= pi; ++pj, ++tp) {
                 GramItem it;
-                it.pi = pi; it.pj = pj; it.pad = 0;
+                it.pi = pi; it.pj = pj; it.pad = (int)ci;
                 it.slot = out_base[c.out] + tp * chunks_per_out[c.out] + c.idx;
                 it.row0 = c.r0; it.row1 = c.r1;
                 items.push_back(it);
@@ -435,7 +495,10 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
             }
     }
     if (items.empty()) {
-        if (!accumulate) OEM_CUDA(cudaMemsetAsync(G, 0, (size_t)nout * q * q * 8, cx.stream));
+        if (!accumulate) {
+            OEM_CUDA(cudaMemsetAsync(G, 0, (size_t)nout * q * q * 8, cx.stream));
+            if (stats_out) OEM_CUDA(cudaMemsetAsync(stats_out, 0, (size_t)nout * 3 * q * 8, cx.stream));
+        }
         return;
     }
 
@@ -444,6 +507,15 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     DBuf<double> ws((size_t)nslots * G_TILE * G_TILE);
     d_items.upload(items.data(), items.size(), cx.stream);
     d_tiles.upload(tiles.data(), tiles.size(), cx.stream);
+    DBuf<double> stats_ws;
+    DBuf<int> d_chunk_out;
+    if (stats_out) {
+        stats_ws.alloc(chunks.size() * (size_t)P * 3 * G_TILE);
+        std::vector<int> co(chunks.size());
+        for (size_t ci = 0; ci < chunks.size(); ++ci) co[ci] = chunks[ci].out;
+        d_chunk_out.alloc(co.size());
+        d_chunk_out.upload(co.data(), co.size(), cx.stream);
+    }
 
     // ---- TMA descriptor (FP64, 2-D, box = 36 rows x 128 columns, no swizzle, zero OOB fill) ----
     CUtensorMap tm;
@@ -463,13 +535,14 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     const int ni = (int)items.size();
     const bool C = mean != nullptr, W = roww != nullptr;
     const size_t t_k = cx.tm->start(&cx.st.ms_gram);      // the DMMA kernel alone
-#define OEM_GRAM_DISPATCH(CC, WW)                                                                           \
-    if (use_tma) launch_variant<CC, WW, true>(cx, tm, X, ld, n, q, d_items.p, ni, mean, roww, ws.p);        \
-    else launch_variant<CC, WW, false>(cx, tm, X, ld, n, q, d_items.p, ni, mean, roww, ws.p)
-    if (C && W) { OEM_GRAM_DISPATCH(true, true); }
-    else if (C) { OEM_GRAM_DISPATCH(true, false); }
-    else if (W) { OEM_GRAM_DISPATCH(false, true); }
-    else { OEM_GRAM_DISPATCH(false, false); }
+#define OEM_GRAM_DISPATCH(CC, WW, SS)                                                                               \
+    if (use_tma) launch_variant<CC, WW, true, SS>(cx, tm, X, ld, n, q, d_items.p, ni, mean, roww, ws.p, stats_y, stats_ws.p, P);  \
+    else launch_variant<CC, WW, false, SS>(cx, tm, X, ld, n, q, d_items.p, ni, mean, roww, ws.p, stats_y, stats_ws.p, P)
+    if (stats_out) { OEM_GRAM_DISPATCH(false, false, true); }
+    else if (C && W) { OEM_GRAM_DISPATCH(true, true, false); }
+    else if (C) { OEM_GRAM_DISPATCH(true, false, false); }
+    else if (W) { OEM_GRAM_DISPATCH(false, true, false); }
+    else { OEM_GRAM_DISPATCH(false, false, false); }
 #undef OEM_GRAM_DISPATCH
     cx.tm->stop(t_k);
     const size_t t_r = cx.tm->start(&cx.st.ms_gram_reduce);
@@ -477,6 +550,12 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     dim3 rg(G_TILE * G_TILE / 256, (unsigned)tiles.size());
     gram_reduce_kernel<<<rg, 256, 0, cx.stream>>>(ws.p, d_tiles.p, G, q, accumulate ? 1 : 0);
     OEM_CUDA(cudaGetLastError());
+    if (stats_out) {
+        gram_stats_reduce_kernel<<<dim3((q + 127) / 128, nout), 128, 0, cx.stream>>>(
+            stats_ws.p, d_chunk_out.p, (int)chunks.size(), P, q, nout, stats_out, accumulate ? 1 : 0);
+        OEM_CUDA(cudaGetLastError());
+        cx.st.kernel_launches += 1;
+    }
     cx.tm->stop(t_r);
     cx.st.kernel_launches += 2;
     cx.st.gram_launches += 1;

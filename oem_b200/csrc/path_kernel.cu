@@ -514,7 +514,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     const int team = blockIdx.x / a.team_size, rank = blockIdx.x - team * a.team_size;
     const int c0 = min(q, rank * a.cpc), c1 = min(q, c0 + a.cpc);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
     const int ct0 = a.team_ptr[team], nct = a.team_ptr[team + 1] - ct0;
     const int nvec = max(a.max_ct, 2);
 
