@@ -52,10 +52,10 @@ struct GramTile {
     int pi, pj, slot0, nslots, out, pad;
 };
 
-// STATS: the diagonal-tile CTAs also accumulate, for the 128 columns of their panel, sum x, sum x*y and sum x^2 over the
-// item's rows (the column sweeps of src/oem_big.h:743-837) from the A fragments they load anyway: warp w owns atom rows
-// w and 15-w, so the 8 warps cover the panel's 16 column atoms exactly once.  The DFMAs run on the FP64 CUDA-core pipe
-// next to the DMMA stream; a separate HBM sweep of X (colstats_kernel) is no longer needed.
+// STATS: the diagonal-tile CTAs also accumulate, for the 128 columns of their panel, sum x and sum x*y over the item's
+// rows (the column sweeps of src/oem_big.h:743-837; sum x^2 is the Gram's own diagonal) from the A fragments they load
+// anyway: warp w owns atom rows w and 15-w, so the 8 warps cover the panel's 16 column atoms exactly once.  A separate
+// HBM sweep of X (colstats_kernel) is no longer needed.
 template <bool CENTER, bool WEIGHT, bool USE_TMA, bool STATS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restrict__ X, long long ld,
@@ -262,7 +262,15 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
         double acc[17][2];
 #pragma unroll
         for (int sl = 0; sl < 17; ++sl) acc[sl][0] = acc[sl][1] = 0.0;
-        double st_lo[3] = {0.0, 0.0, 0.0}, st_hi[3] = {0.0, 0.0, 0.0};      // sum x, sum x*y, sum x^2 of my two columns
+        double st_lo[2] = {0.0, 0.0}, st_hi[2] = {0.0, 0.0};      // sum x, sum x*y of my two columns
+        double ynext[G_KSTEPS];
+        if (STATS) {
+#pragma unroll
+            for (int ks = 0; ks < G_KSTEPS; ++ks) {
+                const long long r = it.row0 + t + ks * 4;
+                ynext[ks] = (yvec && r < it.row1) ? __ldg(yvec + r) : 0.0;
+            }
+        }
 
         for (int kt = 0; kt < nk; ++kt) {
             const int s = kt % G_STAGES;
@@ -277,11 +285,12 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
                 }
             }
             double yv[G_KSTEPS];
-            if (STATS) {
+            if (STATS) {      // y of this k-tile was requested one k-tile ago; request the next one now
 #pragma unroll
                 for (int ks = 0; ks < G_KSTEPS; ++ks) {
-                    const long long r = rbase + ks * 4;
-                    yv[ks] = (yvec && r < it.row1) ? __ldg(yvec + r) : 0.0;
+                    yv[ks] = ynext[ks];
+                    const long long r = rbase + G_KT + ks * 4;
+                    ynext[ks] = (yvec && r < it.row1) ? __ldg(yvec + r) : 0.0;
                 }
             }
             const bool tail = CENTER && (it.row0 + (long long)(kt + 1) * G_KT > nrows);
@@ -293,8 +302,8 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
                 const bool valid = !tail || (rbase + ks * 4 < nrows);
                 if (STATS) {
                     // rows past the item's end only occur in the matrix's last k-tile, where the loader zero-fills them
-                    st_lo[0] += alo; st_lo[1] = fma(alo, yv[ks], st_lo[1]); st_lo[2] = fma(alo, alo, st_lo[2]);
-                    st_hi[0] += ahi; st_hi[1] = fma(ahi, yv[ks], st_hi[1]); st_hi[2] = fma(ahi, ahi, st_hi[2]);
+                    st_lo[0] += alo; st_lo[1] = fma(alo, yv[ks], st_lo[1]);       // sum x^2 is the Gram's own diagonal
+                    st_hi[0] += ahi; st_hi[1] = fma(ahi, yv[ks], st_hi[1]);
                 }
                 if (CENTER) { alo -= mlo; ahi -= mhi; }
                 if (WEIGHT) { alo *= wv[ks]; ahi *= wv[ks]; }
@@ -322,16 +331,16 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
         if (STATS) {
             // fixed-order sum over the 4 row lanes t of each column, then one partial per (row chunk, panel)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
+            for (int e = 0; e < 2; ++e) {
                 st_lo[e] += __shfl_xor_sync(0xffffffffu, st_lo[e], 1);
                 st_lo[e] += __shfl_xor_sync(0xffffffffu, st_lo[e], 2);
                 st_hi[e] += __shfl_xor_sync(0xffffffffu, st_hi[e], 1);
                 st_hi[e] += __shfl_xor_sync(0xffffffffu, st_hi[e], 2);
             }
             if (t == 0) {
-                double *so = stats_ws + ((size_t)it.pad * npanels + it.pi) * (3 * G_TILE);
+                double *so = stats_ws + ((size_t)it.pad * npanels + it.pi) * (2 * G_TILE);
 #pragma unroll
-                for (int e = 0; e < 3; ++e) {
+                for (int e = 0; e < 2; ++e) {
                     so[e * G_TILE + rlo * 8 + g] = st_lo[e];
                     so[e * G_TILE + rhi * 8 + g] = st_hi[e];
                 }
@@ -367,23 +376,26 @@ gram_reduce_kernel(const double *__restrict__ ws, const GramTile *__restrict__ t
     Go[(size_t)gi * q + gj] = s;
 }
 
-// stats_out[o][e][j] (+)= sum over the row chunks of output o (in chunk order) of the diagonal CTAs' partial sums
+// stats_out[o][e][j] (+)= sum over the row chunks of output o (in chunk order) of the diagonal CTAs' partial sums for
+// e = 0 (sum x) and 1 (sum x*y); e = 2 (sum x^2) is the diagonal of the finished Gram G[o] (runs after gram_reduce_kernel)
 __global__ void gram_stats_reduce_kernel(const double *__restrict__ stats_ws, const int *__restrict__ chunk_out, int nchunks,
-                                         int npanels, int q, int nout, double *__restrict__ stats_out, int accumulate) {
+                                         int npanels, int q, int nout, const double *__restrict__ G,
+                                         double *__restrict__ stats_out, int accumulate) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int o = blockIdx.y;
     if (j >= q) return;
     const int pi = j / G_TILE, jl = j - pi * G_TILE;
-    double s[3] = {0.0, 0.0, 0.0};
+    double s[2] = {0.0, 0.0};
     for (int c = 0; c < nchunks; ++c) {
         if (chunk_out[c] != o) continue;
-        const double *so = stats_ws + ((size_t)c * npanels + pi) * (3 * G_TILE) + jl;
+        const double *so = stats_ws + ((size_t)c * npanels + pi) * (2 * G_TILE) + jl;
 #pragma unroll
-        for (int e = 0; e < 3; ++e) s[e] += so[e * G_TILE];
+        for (int e = 0; e < 2; ++e) s[e] += so[e * G_TILE];
     }
     double *out = stats_out + (size_t)o * 3 * q;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) out[(size_t)e * q + j] = accumulate ? out[(size_t)e * q + j] + s[e] : s[e];
+    for (int e = 0; e < 2; ++e) out[(size_t)e * q + j] = accumulate ? out[(size_t)e * q + j] + s[e] : s[e];
+    out[(size_t)2 * q + j] = G[(size_t)o * q * q + (size_t)j * q + j];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -510,7 +522,7 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     DBuf<double> stats_ws;
     DBuf<int> d_chunk_out;
     if (stats_out) {
-        stats_ws.alloc(chunks.size() * (size_t)P * 3 * G_TILE);
+        stats_ws.alloc(chunks.size() * (size_t)P * 2 * G_TILE);
         std::vector<int> co(chunks.size());
         for (size_t ci = 0; ci < chunks.size(); ++ci) co[ci] = chunks[ci].out;
         d_chunk_out.alloc(co.size());
@@ -552,7 +564,7 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     OEM_CUDA(cudaGetLastError());
     if (stats_out) {
         gram_stats_reduce_kernel<<<dim3((q + 127) / 128, nout), 128, 0, cx.stream>>>(
-            stats_ws.p, d_chunk_out.p, (int)chunks.size(), P, q, nout, stats_out, accumulate ? 1 : 0);
+            stats_ws.p, d_chunk_out.p, (int)chunks.size(), P, q, nout, G, stats_out, accumulate ? 1 : 0);
         OEM_CUDA(cudaGetLastError());
         cx.st.kernel_launches += 1;
     }
