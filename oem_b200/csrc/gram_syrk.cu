@@ -25,6 +25,8 @@
 // workspace slot; gram_reduce_kernel sums the slots of a tile in a fixed order (deterministic,
 // no atomics) and mirrors the lower triangle.
 #include <algorithm>
+#include <functional>
+#include <cstdlib>
 #include <type_traits>
 #include <mutex>
 #include "runtime.h"
@@ -447,11 +449,61 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
             fail(OEMB200_EINVAL, "gram: interior segment length not a multiple of %d", G_KT);
         rows_total += s.row1 - s.row0;
     }
-    const int waves = 8;
+    // Row-chunk length: a few waves of items, chosen by simulating the block scheduler (items in launch order onto the
+    // earliest free SM) with the three tile-class costs, so that the class sizes divide well over the SMs and the tail
+    // of cheap diagonal items is short.  OEMB200_GRAM_WAVES pins the old "waves x SMs / tiles" rule for experiments.
     const int64_t min_rows = 32 * G_KT;
-    int64_t chunks_target = std::max<int64_t>(1, (int64_t)waves * cx.num_sms / ntile_pairs);
-    int64_t chunk_rows = (rows_total + chunks_target - 1) / chunks_target;
-    chunk_rows = std::max<int64_t>(min_rows, ((chunk_rows + G_KT - 1) / G_KT) * G_KT);
+    auto round_chunk = [&](int64_t target_chunks) {
+        int64_t cr = (rows_total + target_chunks - 1) / std::max<int64_t>(1, target_chunks);
+        return std::max<int64_t>(min_rows, ((cr + G_KT - 1) / G_KT) * G_KT);
+    };
+    int64_t chunk_rows;
+    if (const char *e = getenv("OEMB200_GRAM_WAVES")) {
+        chunk_rows = round_chunk(std::max<int64_t>(1, (int64_t)std::max(1, atoi(e)) * cx.num_sms / ntile_pairs));
+    } else {
+        const bool partial = (q % G_TILE) != 0;
+        const int nfull = partial ? (P - 1) * (P - 2) / 2 : P * (P - 1) / 2;       // tiles per class
+        const int nlast = partial ? P - 1 : 0;
+        const double cost_last = partial ? (8.0 + std::max(0, std::min(8, (q - (P - 1) * G_TILE - 64 + 7) / 8)) +
+                                            std::min(8, (q - (P - 1) * G_TILE + 7) / 8) - 8.0) / 16.0 : 1.0;
+        const double cost_diag = stats_out ? 0.60 : 0.54;
+        auto makespan = [&](int64_t cr) {
+            std::vector<double> cost;      // launch order: class by class, chunk-major
+            std::vector<double> len;       // k-tiles (+3 for pipeline fill / epilogue) of every chunk
+            for (auto &sg : segs) {
+                const int64_t l = sg.row1 - sg.row0;
+                if (l <= 0) continue;
+                const int64_t nc = (l + cr - 1) / cr;
+                const int64_t per = (((l + nc - 1) / nc) + G_KT - 1) / G_KT * G_KT;
+                for (int64_t r = 0; r < l; r += per) len.push_back((double)((std::min(l, r + per) - r + G_KT - 1) / G_KT) + 3.0);
+            }
+            for (double c : {1.0, cost_last, cost_diag}) {
+                const int nt = c == 1.0 ? nfull : (c == cost_diag ? P : nlast);
+                for (double l : len)
+                    for (int t = 0; t < nt; ++t) cost.push_back(l * c);
+            }
+            std::vector<double> sm(cx.num_sms, 0.0);       // min-heap of SM free times
+            std::make_heap(sm.begin(), sm.end(), std::greater<double>());
+            double end = 0.0;
+            for (double c : cost) {
+                std::pop_heap(sm.begin(), sm.end(), std::greater<double>());
+                sm.back() += c;
+                end = std::max(end, sm.back());
+                std::push_heap(sm.begin(), sm.end(), std::greater<double>());
+            }
+            return end;
+        };
+        const int64_t c_lo = std::max<int64_t>(1, (int64_t)6 * cx.num_sms / ntile_pairs);
+        const int64_t c_hi = std::max<int64_t>(c_lo, (int64_t)14 * cx.num_sms / ntile_pairs);
+        chunk_rows = round_chunk(c_lo);
+        double best = makespan(chunk_rows);
+        for (int64_t c = c_lo + 1; c <= c_hi; ++c) {
+            const int64_t cr = round_chunk(c);
+            if (cr == chunk_rows) continue;
+            const double m = makespan(cr);
+            if (m < best * 0.999) { best = m; chunk_rows = cr; }
+        }
+    }
     // cap the workspace at ~1.5 GB of partial tiles
     const int64_t max_slots = (1536ll << 20) / (G_TILE * G_TILE * 8);
     for (;;) {
@@ -482,18 +534,27 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
     std::vector<int> out_base(nout + 1, 0);
     for (int o = 0; o < nout; ++o) out_base[o + 1] = out_base[o] + chunks_per_out[o] * ntile_pairs;
     const int nslots = out_base[nout];
-    for (size_t ci = 0; ci < chunks.size(); ++ci) {
-        const Chunk &c = chunks[ci];
-        int tp = 0;
-        for (int pi = 0; pi < P; ++pi)
-            for (int pj = 0; pj <= pi; ++pj, ++tp) {
-                GramItem it;
-                it.pi = pi; it.pj = pj; it.pad = (int)ci;
-                it.slot = out_base[c.out] + tp * chunks_per_out[c.out] + c.idx;
-                it.row0 = c.r0; it.row1 = c.r1;
-                items.push_back(it);
-            }
-    }
+    // Item order = launch order.  Tiles come in three cost classes (full off-diagonal 1.0, last-panel off-diagonal with
+    // skipped padding, triangular diagonal ~0.6); CTAs of one class take equally long, so listing the items class by
+    // class (row-range-major inside a class) makes the tiles of a row range start together and stream the same rows at
+    // the same time -- that is what lets them share column panels through L2.  Mixed classes drift apart within a wave
+    // and re-read the panels from HBM (measured 5.6x the matrix; class-major order: see profiles/gram_traffic.json).
+    const bool partial_last = (q % G_TILE) != 0;
+    for (int cls = 0; cls < 3; ++cls)
+        for (size_t ci = 0; ci < chunks.size(); ++ci) {
+            const Chunk &c = chunks[ci];
+            int tp = 0;
+            for (int pi = 0; pi < P; ++pi)
+                for (int pj = 0; pj <= pi; ++pj, ++tp) {
+                    const int tcls = pi == pj ? 2 : (partial_last && pi == P - 1) ? 1 : 0;
+                    if (tcls != cls) continue;
+                    GramItem it;
+                    it.pi = pi; it.pj = pj; it.pad = (int)ci;
+                    it.slot = out_base[c.out] + tp * chunks_per_out[c.out] + c.idx;
+                    it.row0 = c.r0; it.row1 = c.r1;
+                    items.push_back(it);
+                }
+        }
     for (int o = 0; o < nout; ++o) {
         int tp = 0;
         for (int pi = 0; pi < P; ++pi)

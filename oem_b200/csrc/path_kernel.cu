@@ -1177,7 +1177,28 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         const int Lm = std::max(pp.Lmax, 1);
         const int nctt = std::max(1, std::min(max_ct, PR_MAXCT));
         const size_t smem_bytes = ((size_t)2 * nctt * QP + (size_t)nctt * Lm + nctt * 8 + 2 * nctt + 2) * 8 + (128 + 4 * nctt) * 4;
+        void *kern = nullptr;
         if (reg_ok && G * NC <= cx.num_sms && smem_bytes <= cx.smem_optin) {
+#define PR_PICK(N)                                                                                                   \
+    case N: kern = q <= 128 ? (void *)oem_path_reg_kernel<16, 4, N> : (void *)oem_path_reg_kernel<4, 8, N>; break
+            switch (nctt) { PR_PICK(1); PR_PICK(2); PR_PICK(3); default: PR_PICK(4); }
+#undef PR_PICK
+            OEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            // a cluster shape this device cannot schedule (MIG slices, odd GPC sizes) falls back to the generic kernel
+            cudaLaunchConfig_t probe;
+            memset(&probe, 0, sizeof probe);
+            probe.gridDim = dim3(G * NC); probe.blockDim = dim3(PK_THREADS); probe.dynamicSmemBytes = smem_bytes;
+            cudaLaunchAttribute pat[1];
+            pat[0].id = cudaLaunchAttributeClusterDimension;
+            pat[0].val.clusterDim.x = NC; pat[0].val.clusterDim.y = 1; pat[0].val.clusterDim.z = 1;
+            probe.attrs = pat; probe.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &probe) != cudaSuccess || nclusters < 1) {
+                (void)cudaGetLastError();
+                kern = nullptr;
+            }
+        }
+        if (kern) {
             if (pp.compute_eig) {
                 PathProblem eig = pp;
                 eig.chains.clear();
@@ -1198,12 +1219,6 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
             DBuf<long long> d_prof;
             const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;
             if (prof) { d_prof.alloc(16); d_prof.zero(cx.stream); a.prof = d_prof.p; }
-            void *kern = nullptr;
-#define PR_PICK(N)                                                                                                   \
-    case N: kern = q <= 128 ? (void *)oem_path_reg_kernel<16, 4, N> : (void *)oem_path_reg_kernel<4, 8, N>; break
-            switch (nctt) { PR_PICK(1); PR_PICK(2); PR_PICK(3); default: PR_PICK(4); }
-#undef PR_PICK
-            OEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
             void *kargs[] = {&a};
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
