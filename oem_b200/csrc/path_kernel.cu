@@ -1122,6 +1122,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathA
             }
         }
         if (advanced) {        // uniform over the whole team: new per-lambda constants before the next epilogue reads them
+            // (the exchange wait already orders every warp's earlier reads of cpar before this point; the explicit
+            // barrier keeps the write-after-read visible to tools and costs nothing at one event per lambda)
+            __syncthreads();
 #pragma unroll
             for (int c = 0; c < NCT; ++c)
                 if (((advanced >> c) & 1u) && threadIdx.x == c) set_cpar(c, lidx[c]);
