@@ -194,6 +194,38 @@ bool fold_bucket_device(Ctx &cx, const int *foldid_dev, int64_t n, int F, int64_
     return true;
 }
 
+// Coefficient operand of the CV-scoring GEMM straight from the path kernel's output (no host round trip):
+//   B[k][j][c] = beta_raw[chain (k+1, pp)][lambda i][icpt + j] * (standardize ? colsq_inv[k+1][j] : 1),  c = pp * L + i
+//   b0[k][c]   = intercept entry; columns beyond a penalty's lambda count (ols) and the padding up to ncld are zero
+// (get_beta() un-scaling of the fold fits, src/oem_xval_dense.h:1102-1120).
+__global__ void cv_build_coef_kernel(const double *__restrict__ beta_raw, const double *__restrict__ cinv, int P, int L, int p,
+                                     int q, int icpt, int standardize, const int *__restrict__ nlam_run, int ncld,
+                                     double *__restrict__ B, double *__restrict__ b0) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;             // 0..p-1: coefficient row, p: intercept row
+    const int k = blockIdx.z;             // fold
+    if (c >= ncld) return;
+    const int pp = c / L, i = c - pp * L;
+    const bool live = pp < P && i < nlam_run[pp];
+    const double *raw = beta_raw + (((size_t)(k + 1) * P + (live ? pp : 0)) * L + (live ? i : 0)) * q;
+    if (j == p) {
+        b0[(size_t)k * ncld + c] = (live && icpt) ? raw[0] : 0.0;
+    } else {
+        double v = live ? raw[icpt + j] : 0.0;
+        if (standardize) v *= cinv[(size_t)(k + 1) * p + j];
+        B[((size_t)k * p + j) * ncld + c] = v;
+    }
+}
+
+void cv_build_coef_launch(Ctx &cx, const double *beta_raw, const double *cinv, int nfolds, int P, int L, int p, int q, int icpt,
+                          bool standardize, const int *nlam_run_dev, double *B, double *b0) {
+    const int ncld = cv_ncld(P * L);
+    dim3 grid((ncld + 127) / 128, p + 1, nfolds);
+    cv_build_coef_kernel<<<grid, 128, 0, cx.stream>>>(beta_raw, cinv, P, L, p, q, icpt, standardize ? 1 : 0, nlam_run_dev, ncld, B, b0);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+}
+
 // EPI: 0 = squared error moments, 1 = absolute error moments (the CV score), 2 = store the linear predictor
 // x_i . b + b0 (predict.oem type = "link", R/methods.R:113-118), 3 = store 1 / (1 + exp(-link)) (type = "response" of
 // predict.oemfit_binomial, R/methods.R:355-358).  The store modes write pred[c * ldo + row] for c < nc.

@@ -196,20 +196,10 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
 
     // ---- 5. CV scoring: coefficient matrices [fold][p][ncld], intercepts [fold][ncld] ----
     const int nc = P * L, ncld = cv_ncld(nc);
-    std::vector<double> hB((size_t)F * p * ncld, 0.0), hb0((size_t)F * ncld, 0.0);
-    for (int k = 0; k < F; ++k)
-        for (int pp = 0; pp < P; ++pp)
-            for (int i = 0; i < su.nlam_run[pp]; ++i) {
-                const double *raw = &pb.h_beta[((size_t)((k + 1) * P + pp) * L + i) * q];
-                const double *w = &hcinv[(size_t)(k + 1) * p];
-                const int c = pp * L + i;
-                if (icpt) hb0[(size_t)k * ncld + c] = raw[0];
-                for (int j = 0; j < p; ++j)
-                    hB[((size_t)k * p + j) * ncld + c] = s->standardize ? raw[icpt + j] * w[j] : raw[icpt + j];
-            }
-    DBuf<double> dB(hB.size()), db0(hb0.size()), out3(3 * (size_t)nc);
-    dB.upload(hB.data(), hB.size(), cx.stream);
-    db0.upload(hb0.data(), hb0.size(), cx.stream);
+    DBuf<double> dB((size_t)F * p * ncld), db0((size_t)F * ncld), out3(3 * (size_t)nc);
+    DBuf<int> d_nlam(P);
+    d_nlam.upload(su.nlam_run.data(), P, cx.stream);
+    cv_build_coef_launch(cx, pb.beta_out.p, cinv.p, F, P, L, p, q, icpt, s->standardize != 0, d_nlam.p, dB.p, db0.p);
     std::vector<std::array<int64_t, 3>> cs;
     for (int k = 0; k < F; ++k) cs.push_back({off[k], off[k + 1], off[k] + cnt[k]});
     cvscore_launch(cx, Xs.p, npad, p, npad, ys.p, weighted ? ws.p : nullptr, F, cs, dB.p, db0.p, nc, mae, out3.p);

@@ -206,6 +206,9 @@ int cv_ncld(int nc);     // leading dimension (columns) of the coefficient matri
 void cvscore_launch(Ctx &cx, const double *Xs, int64_t nrows_total, int p, int64_t lds, const double *ys,
                     const double *ws, int nfolds, const std::vector<std::array<int64_t, 3>> &segs, const double *B,
                     const double *b0, int nc, bool mae, double *out3);
+// B / b0 operands of cvscore_launch built on the device from the path kernel's raw iterates (chains (k+1) * P + pp)
+void cv_build_coef_launch(Ctx &cx, const double *beta_raw, const double *cinv, int nfolds, int P, int L, int p, int q, int icpt,
+                          bool standardize, const int *nlam_run_dev, double *B, double *b0);
 // pred (n x nc col-major, ld ldo) = X B + b0 (B, b0 in cvscore layout with one "fold"); response: 1/(1+exp(-link))
 void predict_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const double *B, const double *b0, int nc,
                     bool response, double *pred, int64_t ldo);
