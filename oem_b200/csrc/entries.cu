@@ -246,7 +246,10 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
     b1.download(h1.data(), nb1, cx.stream);
     cx.sync();
     const double n_tot = h1[nb1 - 1];
-    if (!(n_tot > p)) fail(OEMB200_EUNSUPPORTED, "n <= p branch (XX' form, src/oem_dense.h:363-366) is outside the hot path");
+    // n <= p (src/oem_dense.h:474-483, 515-521): the reference takes d from the n x n matrix XX'/n and iterates
+    // u = X'(Y - X beta)/n + d beta.  XX'/n and X'X/n share their non-zero eigenvalues and that u is (dI - X'X/n) beta + X'Y/n
+    // term by term, so the p x p Gram route below computes the same path (differences are rounding only); it is kept for
+    // every shape instead of a second, GEMV-bound iteration kernel.
 
     std::vector<double> meanX(p, 0.0), scaleX(p, 1.0);
     double meanY = 0.0, scaleY = 1.0;
@@ -279,19 +282,32 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
     const size_t nb2 = (size_t)p * p + 2 * (size_t)p;
     DBuf<double> b2(nb2), stats2(3 * (size_t)p);
     double *G = b2.p, *xy = G + (size_t)p * p, *css = xy + p;
-    const size_t t_c2 = tm.start(&cx.st.ms_colstats);
-    colstats_launch(cx, X.p, n, p, X.ld, yuse, nullptr, center_x ? d_mean.p : nullptr, stats2.p, false);
-    OEM_CUDA(cudaMemcpyAsync(xy, stats2.p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
-    if (flag == 1) {   // sd about the mean although X itself is not centred
-        DBuf<double> stats3(3 * (size_t)p);
-        colstats_launch(cx, X.p, n, p, X.ld, nullptr, nullptr, d_mean.p, stats3.p, false);
-        OEM_CUDA(cudaMemcpyAsync(css, stats3.p + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
-        cx.sync();
-    } else {
+    // X'ys and the (centred) sums of squares ride in the Gram launch (diagonal-tile CTAs) unless flag 1 needs the
+    // sd about the mean of an uncentred X, or OEMB200_SEPARATE_COLSTATS=1 asks for the separate sweep.  Small problems
+    // keep the sweep: at n = 1e6 x p = 100 the fused launch measured 2.84 ms per fit against 2.41 ms (partial-statistics
+    // reduce), while from p = 500 up the Gram dwarfs the statistics and the saved pass over X is a net win
+    const bool fused_stats = flag != 1 && p >= 256 && (double)n * p >= 268435456.0 &&
+                             getenv("OEMB200_SEPARATE_COLSTATS") == nullptr;
+    if (fused_stats) {
+        gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, center_x ? d_mean.p : nullptr, nullptr, G, false, yuse,
+                    stats2.p);
+        OEM_CUDA(cudaMemcpyAsync(xy, stats2.p + (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
         OEM_CUDA(cudaMemcpyAsync(css, stats2.p + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
+    } else {
+        const size_t t_c2 = tm.start(&cx.st.ms_colstats);
+        colstats_launch(cx, X.p, n, p, X.ld, yuse, nullptr, center_x ? d_mean.p : nullptr, stats2.p, false);
+        OEM_CUDA(cudaMemcpyAsync(xy, stats2.p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
+        if (flag == 1) {   // sd about the mean although X itself is not centred
+            DBuf<double> stats3(3 * (size_t)p);
+            colstats_launch(cx, X.p, n, p, X.ld, nullptr, nullptr, d_mean.p, stats3.p, false);
+            OEM_CUDA(cudaMemcpyAsync(css, stats3.p + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
+            cx.sync();
+        } else {
+            OEM_CUDA(cudaMemcpyAsync(css, stats2.p + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToDevice, cx.stream));
+        }
+        tm.stop(t_c2);
+        gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, center_x ? d_mean.p : nullptr, nullptr, G, false);
     }
-    tm.stop(t_c2);
-    gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, center_x ? d_mean.p : nullptr, nullptr, G, false);
     const size_t t_ar = tm.start(&cx.st.ms_allreduce);
     cx.all_reduce(b2.p, (int64_t)nb2);
     tm.stop(t_ar);

@@ -302,12 +302,14 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restr
             for (int ks = 0; ks < G_KSTEPS; ++ks) {
                 double alo = pA[offAlo + ks * 4], ahi = pA[offAhi + ks * 4];
                 const bool valid = !tail || (rbase + ks * 4 < nrows);
+                if (CENTER) { alo -= mlo; ahi -= mhi; }
                 if (STATS) {
                     // rows past the item's end only occur in the matrix's last k-tile, where the loader zero-fills them
-                    st_lo[0] += alo; st_lo[1] = fma(alo, yv[ks], st_lo[1]);       // sum x^2 is the Gram's own diagonal
-                    st_hi[0] += ahi; st_hi[1] = fma(ahi, yv[ks], st_hi[1]);
+                    // (centred: they hold -mean there and are masked like the B operand below)
+                    const double xl = (CENTER && !valid) ? 0.0 : alo, xh = (CENTER && !valid) ? 0.0 : ahi;
+                    st_lo[0] += xl; st_lo[1] = fma(xl, yv[ks], st_lo[1]);         // sum x^2 is the Gram's own diagonal
+                    st_hi[0] += xh; st_hi[1] = fma(xh, yv[ks], st_hi[1]);
                 }
-                if (CENTER) { alo -= mlo; ahi -= mhi; }
                 if (WEIGHT) { alo *= wv[ks]; ahi *= wv[ks]; }
 #pragma unroll
                 for (int sl = 0; sl < 17; ++sl) {
@@ -433,7 +435,7 @@ static void launch_variant(Ctx &cx, const CUtensorMap &tm, const double *X, int6
 void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const std::vector<RowSegment> &segs,
                  int nout, const double *mean, const double *roww, double *G, bool accumulate, const double *stats_y,
                  double *stats_out) {
-    if (stats_out && (mean || roww)) fail(OEMB200_EINVAL, "gram: fused column statistics need the plain (uncentred, unweighted) mode");
+    if (stats_out && roww) fail(OEMB200_EINVAL, "gram: fused column statistics are not available with row weights");
     if (n <= 0 || q <= 0) fail(OEMB200_EINVAL, "gram: empty matrix (n=%lld, p=%d)", (long long)n, q);
     if (n >= (1ll << 31)) fail(OEMB200_EINVAL, "gram: more than 2^31-1 rows per call; shard or chunk the rows");
     const int P = (q + G_TILE - 1) / G_TILE;
@@ -611,7 +613,8 @@ void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const s
 #define OEM_GRAM_DISPATCH(CC, WW, SS)                                                                               \
     if (use_tma) launch_variant<CC, WW, true, SS>(cx, tm, X, ld, n, q, d_items.p, ni, mean, roww, ws.p, stats_y, stats_ws.p, P);  \
     else launch_variant<CC, WW, false, SS>(cx, tm, X, ld, n, q, d_items.p, ni, mean, roww, ws.p, stats_y, stats_ws.p, P)
-    if (stats_out) { OEM_GRAM_DISPATCH(false, false, true); }
+    if (stats_out && C) { OEM_GRAM_DISPATCH(true, false, true); }
+    else if (stats_out) { OEM_GRAM_DISPATCH(false, false, true); }
     else if (C && W) { OEM_GRAM_DISPATCH(true, true, false); }
     else if (C) { OEM_GRAM_DISPATCH(true, false, false); }
     else if (W) { OEM_GRAM_DISPATCH(false, true, false); }

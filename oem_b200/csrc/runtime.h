@@ -105,7 +105,7 @@ bool is_device_ptr(const void *p);
 struct RowSegment { int64_t row0, row1; int out; };   // rows [row0,row1) accumulate into Gram #out
 // G[out] (q x q col-major, full symmetric; nout matrices, stride q*q) (+)= X_seg' diag(w) X_seg with
 // optional column centring.  Segment boundaries must be multiples of 36 rows except at n.
-// stats_out (optional, plain mode only): nout x 3 x q = [sum x, sum x*stats_y, sum x^2] per output, in the layout of
+// stats_out (optional, not with row weights): nout x 3 x q = [sum xs, sum xs*stats_y, sum xs^2] (xs = x - mean) per output, in the layout of
 // colstats_launch, accumulated by the diagonal-tile CTAs of the same launch (stats_y may be NULL: sum x*y = 0)
 void gram_launch(Ctx &cx, const double *X, int64_t n, int q, int64_t ld, const std::vector<RowSegment> &segs,
                  int nout, const double *mean, const double *roww, double *G, bool accumulate,

@@ -273,7 +273,12 @@ def oem_fit_dense(x, y, family, penalty, weights, groups, unique_groups, group_w
     # init_oem: src/oem_dense.h:693-712, compute_XtX_d_update_A :458-506
     XY = X.T @ Y / n
     XX = (xtx_fn(X) if xtx_fn else X.T @ X) / n
-    d = top_eig(XX) * 1.005
+    if n > p:
+        d = top_eig(XX) * 1.005
+    else:
+        # src/oem_dense.h:474-483: d comes from the n x n matrix XX'/n; next_u (:515-521) is then
+        # X'(Y - X beta)/n + d beta, which is (dI - X'X/n) beta + XY term by term -- iterated below in that form
+        d = top_eig(X @ X.T / n) * 1.005
     A = -XX
     A[np.diag_indices(p)] += d
     lmax = float(np.abs(XY).max()) * scaleY

@@ -247,15 +247,27 @@ def test_maxit_exhausted_reports_maxit_plus_one(lib, oracle):
 
 
 def test_unsupported_paths_fail_loudly(lib):
-    X, y = gaussian_problem(1, 20, 30)           # n <= p: XX' branch is outside the hot path
-    with pytest.raises(lib.OemB200Error) as ei:
-        lib.oem_fit_dense(*args_xy(X, y, "gaussian", ["lasso"]))
+    X, y = gaussian_problem(1, 20, 30)           # n <= p + intercept in big.oem: the reference's own branch is incoherent
+    with pytest.raises(lib.OemB200Error) as ei:  # (X' has p rows, beta p + 1: src/oem_big.h:570-581), so there is nothing to match
+        lib.oem_fit_big(*args_xy(X, y, "gaussian", ["lasso"]))
     assert ei.value.code == 4
     Xs, ys = gaussian_problem(1, 200, 5)
     a = args_xy(Xs, ys, "gaussian", ["lasso"])
     bad = a[:17] + [3, np.array([0] * 200), False, "mse", a[18]]
     with pytest.raises(lib.OemB200Error, match="foldid"):
         lib.oem_xval_dense(*bad)
+
+
+@pytest.mark.parametrize("n,p", [(20, 30), (25, 25), (60, 200)])
+@pytest.mark.parametrize("standardize,intercept", [(True, True), (False, False), (False, True)])
+def test_dense_n_le_p_branch(lib, oracle, n, p, standardize, intercept):
+    # src/oem_dense.h:474-483, 515-521 (XX' form): d from XX'/n, u = X'(Y - X beta)/n + d beta
+    X, y = gaussian_problem(600 + n + p, n, p)
+    groups = np.arange(p) // 5 + 1
+    a = args_xy(X, y, "gaussian", ["lasso", "mcp", "grp.lasso"], nlambda=12, lmin_ratio=0.01, standardize=standardize,
+                intercept=intercept, groups=groups, unique_groups=np.unique(groups), opts=dict(maxit=500, tol=1e-9))
+    got, ref = lib.oem_fit_dense(*a), oracle.oem_fit_dense(*a)
+    assert_same_fit(got, ref)
 
 
 def test_wide_problem_streams_A_from_l2(lib, oracle):
