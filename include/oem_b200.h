@@ -159,6 +159,14 @@ int oemb200_fit_logistic_dense(const double *x, int64_t n, int p, int64_t ldx, c
 int oemb200_fit_big(const double *x, int64_t n, int p, int64_t ldx, const double *y,
                     const oemb200_spec *spec, const oemb200_opts *opts, oemb200_result *res);
 
+/* src/oem_sparse.cpp:30 -- x is a Matrix::dgCMatrix (what R/oem.R:236-240 coerces every sparseMatrix to), passed as its
+ * three slots: row_idx = x@i (nnz 0-based row indices), col_ptr = x@p (p + 1 column pointers, col_ptr[p] = nnz),
+ * values = x@x; host or device pointers.  Gaussian family, n > p.  Same result layout as oemb200_fit_dense
+ * (beta (p+1) x L per penalty, row 0 = intercept). */
+int oemb200_fit_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p,
+                       const double *y, const oemb200_spec *spec, const oemb200_opts *opts,
+                       oemb200_result *res);
+
 /* predict.oem (R/methods.R:48-119; logistic response R/methods.R:346-366): out (n x nlambda, column-major,
  * ldo >= n, host or device) = newx (n x p) * beta[intercept rows dropped] + beta[0, :].  beta is the host
  * coefficient matrix of one model as the fit entries return it: beta_rows x nlambda column-major with

@@ -94,6 +94,7 @@ def load():
     sp, op, rp = ctypes.POINTER(Spec), ctypes.POINTER(Opts), ctypes.POINTER(Result)
     L.oemb200_fit_dense.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
     L.oemb200_fit_big.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
+    L.oemb200_fit_sparse.argtypes = [vp, vp, vp, i64, ci, vp, sp, op, rp]
     L.oemb200_fit_logistic_dense.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
     L.oemb200_xtx.argtypes = [vp, vp, ci, sp, vp, ci, op, rp]
     L.oemb200_xval_dense.argtypes = [vp, i64, ci, i64, vp, sp, ci, vp, ctypes.c_char_p, op, rp]
@@ -111,7 +112,7 @@ def load():
 
 EXPORTS = ["oemb200_last_error", "oemb200_version", "oemb200_device_count", "oemb200_default_opts",
            "oemb200_penalty_id", "oemb200_nlambda_max", "oemb200_fit_dense", "oemb200_xtx", "oemb200_xval_dense",
-           "oemb200_fit_logistic_dense", "oemb200_fit_big", "oemb200_gram", "oemb200_colstats",
+           "oemb200_fit_logistic_dense", "oemb200_fit_big", "oemb200_fit_sparse", "oemb200_gram", "oemb200_colstats",
            "oemb200_xb_logistic", "oemb200_top_eig", "oemb200_lambda_grid", "oemb200_stop_rule",
            "oemb200_release_cache", "oemb200_predict"]
 
@@ -322,6 +323,55 @@ def oem_fit_big(x, y, family, penalty, weights, groups, unique_groups, group_wei
     return _run_xy("oemb200_fit_big", x, y, family, penalty, weights, groups, unique_groups, group_weights,
                    lambda_, nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept,
                    compute_loss, opts, comm)
+
+
+def _csc_slots(x):
+    """(i, p, x, n, ncol) of a dgCMatrix-like input: a scipy.sparse matrix (converted to CSC with sorted, summed
+    entries like as(x, "CsparseMatrix"), R/oem.R:240) or a tuple (i, p, x, (n, ncol)) of numpy arrays / CUDA tensors."""
+    if isinstance(x, tuple):
+        ri, cp, vals, (n, ncol) = x
+        return ri, cp, vals, int(n), int(ncol)
+    import scipy.sparse as sps
+    if not sps.issparse(x):
+        raise ValueError("oem_fit_sparse needs a scipy.sparse matrix or the (i, p, x, dim) slots of a dgCMatrix")
+    c = sps.csc_matrix(x, dtype=np.float64)
+    c.sum_duplicates()
+    if c.nnz >= 2 ** 31:
+        raise ValueError("more than 2^31 - 1 stored entries (the dgCMatrix limit)")
+    return c.indices.astype(np.int32, copy=False), c.indptr.astype(np.int32, copy=False), c.data, c.shape[0], c.shape[1]
+
+
+def _int_array_arg(a, keep):
+    if _is_torch_cuda(a):
+        import torch
+        if a.dtype != torch.int32:
+            raise ValueError("device index arrays must be int32")
+        a = a.contiguous().view(-1)
+        keep.refs.append(a)
+        return a.data_ptr()
+    a = keep.arr(a, np.int32)
+    return a.ctypes.data if a.size else None
+
+
+def oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+                   lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss, opts,
+                   comm=None):
+    """src/oem_sparse.cpp:30-264 (x = dgCMatrix: scipy.sparse matrix or its (i, p, x, dim) slots)."""
+    L = load()
+    keep = _Keep()
+    ri, cp, vals, n, p = _csc_slots(x)
+    rip, cpp = _int_array_arg(ri, keep), _int_array_arg(cp, keep)
+    vp_, _ = _vector_arg(vals, keep) if (_is_torch_cuda(vals) or np.asarray(vals).size) else (None, 0)
+    yp, ny = _vector_arg(y, keep)
+    if ny != n:
+        raise ValueError("length of y must equal nrow(x)")
+    spec = _make_spec(keep, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+                      lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss)
+    o = opts if isinstance(opts, Opts) else make_opts(opts, comm)
+    Lmax = L.oemb200_nlambda_max(ctypes.byref(spec))
+    out = _Out(len(penalty), Lmax, p + 1, xval=False)
+    _check(L.oemb200_fit_sparse(rip, cpp, vp_, n, p, yp, ctypes.byref(spec), ctypes.byref(o), ctypes.byref(out.res)))
+    return out.as_dict()
 
 
 def oem_fit_logistic_dense(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_,

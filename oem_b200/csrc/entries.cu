@@ -4,7 +4,7 @@
 //   oemb200_fit_dense   <- oem_fit_dense   src/oem_dense.cpp:30-309  (+ DataStd.h, oem_dense.h)
 //   oemb200_xtx         <- oem_xtx         src/oem_xtx.cpp:29-219    (+ oem_xtx.h)
 //   oemb200_fit_big     <- oem_fit_big     src/oem_big.cpp:30-258    (+ oem_big.h)
-// (logistic: entry_logistic.cu, xval: entry_xval.cu)
+// (logistic: entry_logistic.cu, xval: entry_xval.cu, sparse: entry_sparse.cu)
 //
 // Each driver owns only bookkeeping: which sums to take over X, the lambda grid (host libm, so it
 // is bit-identical to a CPU implementation), the penalty x lambda layout of the result.  All
@@ -471,6 +471,8 @@ static void fit_xtx(const double *xtx, const double *xty, int p, const oemb200_s
 
 void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s,
                   const oemb200_opts *o, oemb200_result *res);
+void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
+                const oemb200_spec *s, const oemb200_opts *o, oemb200_result *res);
 void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s, int nfolds,
               const int *foldid, const char *type_measure, const oemb200_opts *o, oemb200_result *res);
 
@@ -599,6 +601,10 @@ int oemb200_xtx(const double *xtx, const double *xty, int p, const oemb200_spec 
 int oemb200_fit_big(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *spec,
                     const oemb200_opts *opts, oemb200_result *res) {
     return guarded([&] { fit_big(x, n, p, ldx, y, spec, opts, res); });
+}
+int oemb200_fit_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
+                       const oemb200_spec *spec, const oemb200_opts *opts, oemb200_result *res) {
+    return guarded([&] { fit_sparse(row_idx, col_ptr, values, n, p, y, spec, opts, res); });
 }
 int oemb200_fit_logistic_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y,
                                const oemb200_spec *spec, const oemb200_opts *opts, oemb200_result *res) {

@@ -1,0 +1,426 @@
+// entry_sparse.cu -- oemb200_fit_sparse <- oem_fit_sparse  src/oem_sparse.cpp:30-264 (+ oem_sparse.h), SURVEY.md 8f row 4.
+//
+// X arrives as the three slots of a Matrix::dgCMatrix (compressed sparse column: i = 0-based row indices, p = column
+// pointers, x = values; R/oem.R:236-240 coerces every sparseMatrix to it).  What the reference computes from it
+// (oem_sparse.h:490-636, 791-862) are the same sufficient statistics as oem_big -- X'X (dense p x p), column sums,
+// X'y, column sums of squares -- so the sparse entry only replaces the data pass; assembly, top eigenvalue and the whole
+// lambda path are the kernels every other entry uses.
+//
+// Data pass, all deterministic (no floating-point atomics):
+//   csc_colstats_kernel   one CTA per column: sum x, sum x*y, sum x^2                       (oem_sparse.h:495-507, 580, 829)
+//   csr_count / scan / fill   CSC -> CSR on the device (integer atomics only; the order of a row's entries is
+//                         irrelevant below because they land in different accumulator slots)
+//   sparse_gram_kernel    CTA (j, split): for every stored x_ij of column j (in storage order, dealt round-robin to the
+//                         warps) add x_ij * row_i into the warp's private p-vector in shared memory; fixed-order reduce
+//                         over warps, then over splits -> column j of X'X.  Work = sum_i nnz(row i)^2 multiply-adds, the
+//                         same count as the row-wise outer-product form Eigen's rankUpdate performs (oem_sparse.h:341-344)
+//   sparse_loss_kernel    compute.loss: one warp per row, lanes over the (penalty, lambda) columns       (oem_sparse.h:918-943)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "host_common.h"
+
+namespace oemb200 {
+
+// ------------------------------------------------------------------------------------------------ column statistics
+__global__ void __launch_bounds__(256) csc_colstats_kernel(const int *__restrict__ col_ptr, const int *__restrict__ row_idx,
+                                                           const double *__restrict__ val, const double *__restrict__ y,
+                                                           int p, double *__restrict__ stats) {
+    const int j = blockIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int e = col_ptr[j] + threadIdx.x; e < col_ptr[j + 1]; e += 256) {
+        const double v = val[e];
+        s0 += v;
+        s1 = fma(v, y[row_idx[e]], s1);
+        s2 = fma(v, v, s2);
+    }
+    __shared__ double sh[3][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s0; sh[1][threadIdx.x >> 5] = s1; sh[2][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+        stats[(size_t)threadIdx.x * p + j] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CSC -> CSR
+__global__ void csr_count_kernel(const int *__restrict__ row_idx, int nnz, int *__restrict__ cnt) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnz) atomicAdd(&cnt[row_idx[e]], 1);
+}
+
+constexpr int SCAN_ITEMS = 4, SCAN_THREADS = 1024, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+
+// exclusive scan of one tile in place; the tile total goes to totals[blockIdx.x]
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    const int base = w ? wsum[w - 1] : 0;
+    *total = wsum[31];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(int *__restrict__ a, int n, int *__restrict__ totals) {
+    const int i0 = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (i0 + k < n) ? a[i0 + k] : 0; s += v[k]; }
+    int total;
+    int ex = block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (i0 + k < n) a[i0 + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+
+// one CTA: exclusive scan of the tile totals (any count, chunk by chunk with a running carry)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_totals_kernel(int *__restrict__ totals, int nt) {
+    int carry = 0;
+    for (int c0 = 0; c0 < nt; c0 += SCAN_THREADS) {
+        const int i = c0 + threadIdx.x;
+        const int v = i < nt ? totals[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, &total);
+        if (i < nt) totals[i] = carry + ex;
+        carry += total;
+    }
+}
+
+// row_ptr[i] = tile-local scan + tile offset; row_ptr[n] = nnz; cursor = row_ptr copy for the fill
+__global__ void scan_finish_kernel(int *__restrict__ row_ptr, int n, const int *__restrict__ totals, int nnz,
+                                   int *__restrict__ cursor) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int v = row_ptr[i] + totals[i / SCAN_TILE];
+        row_ptr[i] = v;
+        cursor[i] = v;
+    } else if (i == n) row_ptr[n] = nnz;
+}
+
+__global__ void __launch_bounds__(256) csr_fill_kernel(const int *__restrict__ col_ptr, const int *__restrict__ row_idx,
+                                                       const double *__restrict__ val, int *__restrict__ cursor,
+                                                       int *__restrict__ csr_col, double *__restrict__ csr_val) {
+    const int j = blockIdx.x;
+    for (int e = col_ptr[j] + threadIdx.x; e < col_ptr[j + 1]; e += 256) {
+        const int pos = atomicAdd(&cursor[row_idx[e]], 1);
+        csr_col[pos] = j;
+        csr_val[pos] = val[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ sparse Gram
+// grid (p, nsplit); dynamic smem = nwarps * p doubles.  Split s of column j owns the contiguous part
+// [e0 + s * len, e0 + (s + 1) * len) of the column's stored entries.
+__global__ void __launch_bounds__(256) sparse_gram_kernel(const int *__restrict__ col_ptr, const int *__restrict__ row_idx,
+                                                          const double *__restrict__ val, const int *__restrict__ row_ptr,
+                                                          const int *__restrict__ csr_col, const double *__restrict__ csr_val,
+                                                          int p, int nwarps, double *__restrict__ Gpart) {
+    extern __shared__ double acc[];
+    const int j = blockIdx.x, s = blockIdx.y, ns = gridDim.y;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < nwarps * p; c += blockDim.x) acc[c] = 0.0;
+    __syncthreads();
+    const int e0 = col_ptr[j], e1 = col_ptr[j + 1];
+    const int len = (e1 - e0 + ns - 1) / ns;
+    const int b = e0 + s * len, e = min(b + len, e1);
+    if (w < nwarps) {
+        double *a = acc + (size_t)w * p;
+        for (int t = b + w; t < e; t += nwarps) {
+            const int i = row_idx[t];
+            const double xv = val[t];
+            const int k1 = row_ptr[i + 1];
+            for (int k = row_ptr[i] + lane; k < k1; k += 32) {
+                const int c = csr_col[k];
+                a[c] = fma(xv, csr_val[k], a[c]);      // a row's entries hit distinct slots
+            }
+            __syncwarp();                               // orders this row's updates before the next row's
+        }
+    }
+    __syncthreads();
+    double *out = Gpart + ((size_t)s * p + j) * p;
+    for (int c = threadIdx.x; c < p; c += blockDim.x) {
+        double t = 0.0;
+        for (int ww = 0; ww < nwarps; ++ww) t += acc[(size_t)ww * p + c];
+        out[c] = t;
+    }
+}
+
+__global__ void sum_splits_kernel(const double *__restrict__ Gpart, int ns, size_t pp, double *__restrict__ G) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= pp) return;
+    double t = 0.0;
+    for (int s = 0; s < ns; ++s) t += Gpart[(size_t)s * pp + e];
+    G[e] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+// Bt: p x C row-major (row = variable, C = all (penalty, lambda) columns), b0: C.  One warp per row, lanes over columns in
+// chunks of 32 * LOSS_CPL; per-warp partial sums, summed in fixed order by sum_partials below.
+constexpr int LOSS_CPL = 4;
+__global__ void __launch_bounds__(256) sparse_loss_kernel(const int *__restrict__ row_ptr, const int *__restrict__ csr_col,
+                                                          const double *__restrict__ csr_val, const double *__restrict__ y,
+                                                          int n, const double *__restrict__ Bt, const double *__restrict__ b0,
+                                                          int C, double *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int c0 = 0; c0 < C; c0 += 32 * LOSS_CPL) {
+        double sum[LOSS_CPL], bb[LOSS_CPL];
+#pragma unroll
+        for (int u = 0; u < LOSS_CPL; ++u) {
+            const int c = c0 + u * 32 + lane;
+            sum[u] = 0.0;
+            bb[u] = c < C ? b0[c] : 0.0;
+        }
+        for (int i = gw; i < n; i += nw) {
+            double pr[LOSS_CPL];
+#pragma unroll
+            for (int u = 0; u < LOSS_CPL; ++u) pr[u] = 0.0;
+            for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) {
+                const double v = csr_val[k];
+                const double *brow = Bt + (size_t)csr_col[k] * C;
+#pragma unroll
+                for (int u = 0; u < LOSS_CPL; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    if (c < C) pr[u] = fma(v, brow[c], pr[u]);
+                }
+            }
+            const double yi = y[i];
+#pragma unroll
+            for (int u = 0; u < LOSS_CPL; ++u) {
+                const double r = (yi - pr[u]) - bb[u];          // (Y - X b).array() - beta(0)   oem_sparse.h:925
+                sum[u] = fma(r, r, sum[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < LOSS_CPL; ++u) {
+            const int c = c0 + u * 32 + lane;
+            if (c < C) partial[(size_t)gw * C + c] = sum[u];
+        }
+    }
+}
+
+__global__ void sum_rows_kernel(const double *__restrict__ partial, int rows, int C, double *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double t = 0.0;
+    for (int r = 0; r < rows; ++r) t += partial[(size_t)r * C + c];
+    out[c] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+template <typename T>
+static const T *to_device_array(Ctx &cx, const T *h, size_t cnt, DBuf<T> &own) {
+    if (cnt == 0) return nullptr;
+    if (is_device_ptr(h)) return h;
+    own.alloc(cnt);
+    own.upload(h, cnt, cx.stream);
+    cx.st.h2d_bytes += (int64_t)(cnt * sizeof(T));
+    return own.p;
+}
+
+void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
+                const oemb200_spec *s, const oemb200_opts *o, oemb200_result *res) {
+    check_common(s, o, res, "gaussian");
+    if (n < 1 || p < 1 || !col_ptr || !y) fail(OEMB200_EINVAL, "bad sparse input: n=%lld p=%d", (long long)n, p);
+    if (n >= (1ll << 31)) fail(OEMB200_EINVAL, "sparse: more than 2^31-1 rows per call; shard the rows");
+    const int icpt = s->intercept ? 1 : 0, q = p + icpt;
+    Ctx cx(o);
+    PhaseTimers &tm = *cx.tm;
+    const size_t t_total = tm.start(&cx.st.ms_total);
+    Setup su;
+    su.parse(s, q, /*scan=*/q, /*zero_w0=*/false);      // scans all of `groups` (src/oem_sparse.h:466)
+
+    // ---- inputs to the device ----
+    const size_t t_h = tm.start(&cx.st.ms_h2d);
+    std::vector<int> h_cp(p + 1);
+    if (is_device_ptr(col_ptr)) {
+        OEM_CUDA(cudaMemcpyAsync(h_cp.data(), col_ptr, sizeof(int) * (p + 1), cudaMemcpyDeviceToHost, cx.stream));
+        cx.sync();
+    } else memcpy(h_cp.data(), col_ptr, sizeof(int) * (p + 1));
+    if (h_cp[0] != 0) fail(OEMB200_EINVAL, "sparse: col_ptr[0] must be 0");
+    for (int j = 0; j < p; ++j)
+        if (h_cp[j + 1] < h_cp[j]) fail(OEMB200_EINVAL, "sparse: col_ptr must be non-decreasing");
+    const int nnz = h_cp[p];
+    if (nnz > 0 && (!row_idx || !values)) fail(OEMB200_EINVAL, "sparse: row_idx / values missing");
+    if (!is_device_ptr(row_idx))
+        for (int e = 0; e < nnz; ++e)
+            if (row_idx[e] < 0 || row_idx[e] >= n) fail(OEMB200_EINVAL, "sparse: row index %d out of range at entry %d", row_idx[e], e);
+    DBuf<int> o_cp, o_ri;
+    DBuf<double> o_v;
+    const int *d_cp = to_device_array(cx, col_ptr, (size_t)p + 1, o_cp);
+    const int *d_ri = to_device_array(cx, row_idx, (size_t)nnz, o_ri);
+    const double *d_v = to_device_array(cx, values, (size_t)nnz, o_v);
+    DevVector yv;
+    to_device_vector(cx, y, n, yv);
+    tm.stop(t_h);
+
+    // bundle = [G p*p | stats 3p | sum y, sum y^2 | n]  -> one all-reduce (row-sharded runs)
+    const size_t pp2 = (size_t)p * p;
+    const size_t nb = pp2 + 3 * (size_t)p + 3;
+    DBuf<double> bundle(nb);
+    bundle.zero(cx.stream);
+    double *G = bundle.p, *stats = G + pp2, *ysum = stats + 3 * (size_t)p, *nobs = ysum + 2;
+
+    const size_t t_c = tm.start(&cx.st.ms_colstats);
+    vecsum_launch(cx, yv.p, n, 0.0, ysum, false);
+    csc_colstats_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, yv.p, p, stats);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+    tm.stop(t_c);
+
+    // ---- CSC -> CSR ----
+    const size_t t_g = tm.start(&cx.st.ms_gram);
+    const int ntile = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    DBuf<int> row_ptr((size_t)n + 1), cursor((size_t)n), totals((size_t)ntile), csr_col((size_t)std::max(nnz, 1));
+    DBuf<double> csr_val((size_t)std::max(nnz, 1));
+    row_ptr.zero(cx.stream);
+    if (nnz > 0) csr_count_kernel<<<(nnz + 255) / 256, 256, 0, cx.stream>>>(d_ri, nnz, row_ptr.p);
+    scan_tiles_kernel<<<ntile, SCAN_THREADS, 0, cx.stream>>>(row_ptr.p, (int)n, totals.p);
+    scan_totals_kernel<<<1, SCAN_THREADS, 0, cx.stream>>>(totals.p, ntile);
+    scan_finish_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, cx.stream>>>(row_ptr.p, (int)n, totals.p, nnz, cursor.p);
+    csr_fill_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, cursor.p, csr_col.p, csr_val.p);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 4 + (nnz > 0 ? 1 : 0);
+
+    // ---- X'X ----
+    int nwarps = 8;
+    while (nwarps > 1 && (size_t)nwarps * p * 8 > cx.smem_optin) nwarps >>= 1;
+    if ((size_t)nwarps * p * 8 > cx.smem_optin) fail(OEMB200_EUNSUPPORTED, "sparse: p = %d exceeds the shared-memory accumulator", p);
+    const int nsplit = std::max(1, std::min(16, (4 * cx.num_sms + p - 1) / p));
+    DBuf<double> Gpart;
+    double *gout = G;
+    if (nsplit > 1) { Gpart.alloc((size_t)nsplit * pp2); gout = Gpart.p; }
+    const size_t smem = (size_t)nwarps * p * 8;
+    OEM_CUDA(cudaFuncSetAttribute(sparse_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparse_gram_kernel<<<dim3(p, nsplit), 256, smem, cx.stream>>>(d_cp, d_ri, d_v, row_ptr.p, csr_col.p, csr_val.p, p, nwarps, gout);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+    if (nsplit > 1) {
+        sum_splits_kernel<<<(unsigned)((pp2 + 255) / 256), 256, 0, cx.stream>>>(Gpart.p, nsplit, pp2, G);
+        OEM_CUDA(cudaGetLastError());
+        cx.st.kernel_launches += 1;
+    }
+    cx.st.gram_launches += 1;
+    tm.stop(t_g);
+
+    const double nd = (double)n;
+    OEM_CUDA(cudaMemcpyAsync(nobs, &nd, 8, cudaMemcpyHostToDevice, cx.stream));
+    const size_t t_ar = tm.start(&cx.st.ms_allreduce);
+    cx.all_reduce(bundle.p, (int64_t)nb);
+    tm.stop(t_ar);
+    double n_tot = 0.0;
+    OEM_CUDA(cudaMemcpyAsync(&n_tot, nobs, 8, cudaMemcpyDeviceToHost, cx.stream));
+    cx.sync();
+    if (!(n_tot > p)) fail(OEMB200_EUNSUPPORTED, "n <= p sparse branch (XX' form, src/oem_sparse.h:609-616) is outside the hot path");
+
+    // ---- assembly: the oem_big layout, then row / column 0 times intval (src/oem_sparse.h:566-594, 829-846) ----
+    const size_t t_as = tm.start(&cx.st.ms_assemble);
+    DBuf<double> XX0((size_t)q * q), XY0(q), XX((size_t)q * q), XY(q), cinv(p), dscale;
+    assemble_aug_launch(cx, p, icpt, s->standardize ? 1 : 0, 1, 1, G, stats, ysum, 1, nobs, nobs, XX0.p, XY0.p, cinv.p, nullptr);
+    std::vector<double> hcinv(p), hsq(p), hXY(q);
+    cinv.download(hcinv.data(), p, cx.stream);
+    OEM_CUDA(cudaMemcpyAsync(hsq.data(), stats + 2 * (size_t)p, sizeof(double) * p, cudaMemcpyDeviceToHost, cx.stream));
+    cx.sync();
+    double intval = 1.0;
+    const double *pXX = XX0.p, *pXY = XY0.p;
+    if (icpt) {
+        double tr = 0.0;       // xxdiag = XX.diagonal().tail(nvars).mean() of the (scaled) X block before the division by n
+        for (int j = 0; j < p; ++j) tr += s->standardize ? (hcinv[j] * hsq[j]) * hcinv[j] : hsq[j];
+        const double xxdiag = tr / p;
+        intval = std::sqrt(xxdiag / n_tot);
+        std::vector<double> hd(q, 1.0);
+        hd[0] = intval;
+        dscale.alloc(q);
+        dscale.upload(hd.data(), q, cx.stream);
+        scale_sym_launch(cx, q, dscale.p, XX0.p, XY0.p, XX.p, XY.p);
+        pXX = XX.p; pXY = XY.p;
+    }
+    OEM_CUDA(cudaMemcpyAsync(hXY.data(), pXY, sizeof(double) * q, cudaMemcpyDeviceToHost, cx.stream));
+    tm.stop(t_as);
+    cx.sync();
+
+    double lmax = 0.0;   // compute_lambda_zero: the X entries only (src/oem_sparse.h:851-862)
+    for (int j = icpt; j < q; ++j) lmax = std::max(lmax, std::fabs(hXY[j]));
+    su.build_lambdas(s, lmax, false);
+
+    std::vector<double> pf(q, 0.0);
+    for (int j = 0; j < p; ++j) pf[icpt + j] = s->penalty_factor[j];
+    PathBuffers pb;
+    const size_t t_p = tm.start(&cx.st.ms_path);
+    // get_beta() multiplies the member beta(0) by intval in place (src/oem_sparse.h:895-900): the path kernel's post-scale
+    run_paths(cx, su, o, q, 1, pXX, pXY, pf, 1.0, 1.005, false, icpt ? dscale.p : nullptr, pb);
+    tm.stop(t_p);
+
+    const int L = su.Lmax;
+    fill_common_outputs(su, res);
+    memset(res->beta, 0, sizeof(double) * (size_t)su.P * (p + 1) * L);
+    for (int pp = 0; pp < su.P; ++pp)
+        for (int i = 0; i < su.nlam_run[pp]; ++i) {
+            const double *raw = &pb.h_beta[((size_t)pp * L + i) * q];
+            double *out = res->beta + ((size_t)pp * L + i) * (p + 1);
+            if (icpt) out[0] = raw[0];
+            for (int j = 0; j < p; ++j) out[1 + j] = s->standardize ? raw[icpt + j] * hcinv[j] : raw[icpt + j];
+            res->niter[(size_t)pp * L + i] = pb.h_niter[(size_t)pp * L + i];
+        }
+    *res->d = pb.h_d[0];
+
+    // ---- compute.loss: all (penalty, lambda) columns in one pass over the CSR copy ----
+    if (s->compute_loss && res->loss) {
+        std::vector<std::pair<int, int>> cols;
+        for (int pp = 0; pp < su.P; ++pp)
+            for (int i = 0; i < su.nlam_run[pp]; ++i) cols.push_back({pp, i});
+        const int C = (int)cols.size();
+        std::vector<double> hBt((size_t)p * C), hb0(C);
+        for (int c = 0; c < C; ++c) {
+            const double *b = res->beta + ((size_t)cols[c].first * L + cols[c].second) * (p + 1);
+            hb0[c] = b[0];
+            for (int j = 0; j < p; ++j) hBt[(size_t)j * C + c] = b[1 + j];
+        }
+        const int nblk = 2 * cx.num_sms, nw = nblk * 8;
+        DBuf<double> dBt(hBt.size()), db0(C), partial((size_t)nw * C), dloss(C);
+        dBt.upload(hBt.data(), hBt.size(), cx.stream);
+        db0.upload(hb0.data(), C, cx.stream);
+        const size_t t_l = tm.start(&cx.st.ms_cvscore);
+        sparse_loss_kernel<<<nblk, 256, 0, cx.stream>>>(row_ptr.p, csr_col.p, csr_val.p, yv.p, (int)n, dBt.p, db0.p, C, partial.p);
+        sum_rows_kernel<<<(C + 127) / 128, 128, 0, cx.stream>>>(partial.p, nw, C, dloss.p);
+        OEM_CUDA(cudaGetLastError());
+        cx.st.kernel_launches += 2;
+        tm.stop(t_l);
+        cx.all_reduce(dloss.p, C);
+        std::vector<double> hl(C);
+        dloss.download(hl.data(), C, cx.stream);
+        cx.sync();
+        for (int c = 0; c < C; ++c) res->loss[(size_t)cols[c].first * L + cols[c].second] = hl[c];
+    }
+    finish_stats(cx, tm, t_total, res);
+}
+
+}  // namespace oemb200

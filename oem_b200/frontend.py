@@ -32,6 +32,17 @@ def _match_penalty(penalty):
     return pens
 
 
+def _is_sparse(x):
+    """A scipy.sparse matrix, or the (i, p, x, dim) slots of a dgCMatrix as a tuple."""
+    if isinstance(x, tuple):
+        return True
+    try:
+        import scipy.sparse as sps
+    except ImportError:
+        return False
+    return sps.issparse(x)
+
+
 def _shape(x):
     if hasattr(x, "shape") and len(x.shape) == 2:
         return int(x.shape[0]), int(x.shape[1])
@@ -151,7 +162,8 @@ def oem(x, y, family="gaussian", penalty=None, weights=(), lambda_=(), nlambda=1
     if hessian_type not in ("upper.bound", "full"):
         raise ValueError("'arg' should be one of 'upper.bound', 'full'")
     penalty = _match_penalty(penalty)
-    n, p = _shape(x)
+    is_sparse = _is_sparse(x)                                  # inherits(x, "sparseMatrix"), R/oem.R:235-241
+    n, p = (int(x[3][0]), int(x[3][1])) if isinstance(x, tuple) else _shape(x)
     if len(weights) > 0:
         raise ValueError("weights not implemented yet.")
     ylen = int(y.shape[0]) if hasattr(y, "shape") else len(y)
@@ -159,11 +171,14 @@ def oem(x, y, family="gaussian", penalty=None, weights=(), lambda_=(), nlambda=1
     if family == "binomial" and not hasattr(y, "is_cuda"):
         if np.unique(np.asarray(y)).size > 2:
             raise ValueError("y must be a binary outcome")
-    g, ug, gw = _groups(penalty, groups, group_weights, p, explicit_intercept=(intercept and family != "gaussian"))
+    if is_sparse and family != "gaussian":
+        raise NotImplementedError("oem(family = 'binomial') on a sparse x (oem_fit_logistic_sparse) is outside the hot path")
+    g, ug, gw = _groups(penalty, groups, group_weights, p,
+                        explicit_intercept=(intercept and (family != "gaussian" or is_sparse)))      # R/oem.R:300-337
     lam = _lambda_list(lambda_, len(penalty))
     opts = dict(maxit=int(maxit), tol=float(tol), irls_maxit=int(irls_maxit), irls_tol=float(irls_tol), ncores=int(ncores),
                 hessian_type=hessian_type, accelerate=bool(accelerate))
-    fn = api.oem_fit_dense if family == "gaussian" else api.oem_fit_logistic_dense
+    fn = api.oem_fit_sparse if is_sparse else api.oem_fit_dense if family == "gaussian" else api.oem_fit_logistic_dense
     res = fn(x, y, family, penalty, [], g, ug, gw, lam, int(nlambda), lmr, float(alpha), gamma, float(tau), pf,
              bool(standardize), bool(intercept), bool(compute_loss), opts, comm=comm)
     return _decorate(res, penalty, n, p, family, varnames)

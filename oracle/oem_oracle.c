@@ -1,14 +1,16 @@
 /*
- * oracle/oem_oracle.c -- TEST INFRASTRUCTURE ONLY (parity unpinned).
+ * oracle/oem_oracle.c -- TEST INFRASTRUCTURE ONLY (see DESIGN.md section 2 for what pins it).
  *
  * Plain-C CPU restatement of the OEM iteration of jaredhuling/oem 2.0.12.  It is
  * the checker for the CUDA path: only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it.  The product
  * library (oem_b200/lib/liboem_b200.so) never links, loads or calls it.
  *
- * "Parity unpinned": the reference ships no tests, golden vectors or fixtures
- * for this path and cannot be compiled here (needs
- * R, Rcpp, Eigen, Spectra).  Every function below cites the reference
+ * The reference cannot be compiled here (needs R, Rcpp, Eigen, Spectra) and
+ * ships no test suite; this iteration is pinned through oracle/oracle.py on
+ * the values the reference's rendered documentation prints for seeded inputs
+ * (tests/test_reference_pins.py: gaussian entry points; the logistic entry
+ * remains "parity unpinned").  Every function below cites the reference
  * file:line it restates (paths relative to /root/reference).
  *
  * Build: gcc -O2 -fPIC -shared -o oracle/_build/liboem_oracle.so oracle/oem_oracle.c -lm

@@ -1,4 +1,5 @@
-"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY ("parity unpinned").
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY (pinned on the reference's printed outputs for the four
+gaussian entry points; the logistic entry stays "parity unpinned").
 
 CPU restatement (numpy + the plain-C iteration in oracle/oem_oracle.c) of the five C++
 entry points of jaredhuling/oem 2.0.12 that make up the hot path:
@@ -13,9 +14,15 @@ Each function keeps the reference's argument order and returns the reference's n
 as a dict (beta / lambda / niter / loss / d [/ cvm / cvsd]).  Only tests/, smoke() and
 bench.py's cpu_baseline / --impl reference legs may import this module; the product never does.
 
-The reference cannot be built here (no R / Rcpp / Eigen / Spectra) and ships no tests or
-golden vectors, so this oracle is pinned only by the identities the reference's own examples
-print (oem == oem.xtx, KKT conditions, ...; tests/test_oracle.py) -- "parity unpinned".
+The reference cannot be built here (no R / Rcpp / Eigen / Spectra) and ships no test suite.
+What it does ship is rendered documentation (docs/reference/*.html, vignettes/oem_vignette.html)
+with the values its own oem(), xval.oem(), oem.xtx() and big.oem() returned on seeded inputs.
+oracle/r_rng.py restates R's set.seed / runif / rnorm stream, tests/reference_examples.py re-runs
+those examples and tests/test_reference_pins.py requires this oracle (and, on the GPU, the CUDA
+path) to round to every digit the reference printed: 28 test-set MSEs (6-7 digits), 300
+log-likelihoods of compute.loss paths (7 digits), max |big.oem - oem| = 1.534783e-05 (7 digits)
+and the oem == oem.xtx identity.  No seeded binomial example prints a value, so
+oem_fit_logistic_dense is pinned only by identities (tests/test_oracle.py) -- "parity unpinned".
 
 Third-party arithmetic restated (not vendored under /root/reference):
   * Eigen (RcppEigen, unpinned): SYRK/GEMV = numpy/OpenBLAS here; LinSpaced = linspace_eigen().
@@ -586,6 +593,95 @@ def oem_fit_big(x, y, family, penalty, weights, groups, unique_groups, group_wei
         out["lambda_"].append(lam)
         out["niter"].append(niter)
         out["loss"].append(np.full(L, 1e99))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# oem_fit_sparse
+# ------------------------------------------------------------------------------------------
+def oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_,
+                   nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize_, intercept,
+                   compute_loss, opts):
+    """src/oem_sparse.cpp:30-264, src/oem_sparse.h:490-636,791-943: dgCMatrix X,
+    n > p branch, unweighted.  Like oem_fit_big it scales by the uncentred colsq/(n-1) and carries an
+    explicit intercept column -- but that column is the CONSTANT intval = sqrt(mean(diag(X-block))/n)
+    (:577-594), lambda_max skips the intercept entry (:851-862), and get_beta() multiplies the member
+    beta(0) by intval IN PLACE (:895-900), so the next lambda warm-starts from the rescaled intercept and
+    get_loss (:918-943, called after get_beta) sees the real one."""
+    import scipy.sparse as sp
+    o = _as_opts(opts)
+    if family != "gaussian":
+        raise ValueError("binomial not available for oem_fit_sparse, use oem_fit_logistic_sparse")
+    if np.asarray(weights).size:
+        raise ValueError("weights not implemented yet.")   # R/oem.R:244
+    X = sp.csc_matrix(x, dtype=np.float64)
+    Y = np.asarray(y, dtype=np.float64).ravel()
+    n, p = X.shape
+    if not n > p:
+        raise NotImplementedError("n <= p sparse branch (XX' form) is out of scope")
+    q = p + int(intercept)
+    pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
+    if intercept:
+        pf = np.concatenate([[0.0], pf])
+    colsq_inv = np.ones(p)
+    if standardize_:
+        colsq = np.asarray(X.multiply(X).sum(axis=0)).ravel() / (float(n) - 1.0)
+        colsq = np.where(colsq == 0.0, 1.0, colsq)
+        colsq_inv = 1.0 / np.sqrt(colsq)
+    G = np.asarray((X.T @ X).todense())
+    if standardize_:
+        G = colsq_inv[:, None] * G * colsq_inv[None, :]
+    XX = np.zeros((q, q))
+    XX[q - p:, q - p:] = G
+    intval = 1.0
+    if intercept:
+        xxdiag = float(np.diag(G).mean())
+        intval = np.sqrt(xxdiag / n)
+        colsums = np.asarray(X.sum(axis=0)).ravel() * intval
+        if standardize_:
+            colsums = colsums * colsq_inv
+        XX[0, 1:] = colsums
+        XX[1:, 0] = colsums
+        XX[0, 0] = xxdiag
+    XX /= n
+    XY = np.zeros(q)
+    XY[q - p:] = X.T @ Y
+    if intercept:
+        XY[0] = Y.sum() * intval
+    if standardize_:
+        XY[q - p:] *= colsq_inv
+    XY /= n
+    d = top_eig(XX) * 1.005
+    A = -XX
+    A[np.diag_indices(q)] += d
+    lmax = float(np.abs(XY[q - p:]).max())          # compute_lambda_zero: tail only
+    lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha)
+    grp = _Groups(groups, unique_groups, group_weights, scan=q)      # scans groups.size() (:466)
+    s = _Solver(q, pf, grp, o["maxit"], o["tol"])
+    out = dict(beta=[], lambda_=[], niter=[], loss=[], d=d)
+    for pp, pen in enumerate(penalty):
+        lam = lams[pp]
+        L = 1 if pen == "ols" else lam.size
+        beta = np.zeros((p + 1, L), order="F")
+        niter = np.zeros(L, dtype=np.int32)
+        loss = np.full(L, 1e99)
+        s.init(pen, alpha, _gamma_for(gamma, pp), tau)
+        for i in range(L):
+            niter[i] = s.solve(A, XY, d, lam[i])
+            if intercept:
+                s.beta[0] *= intval                  # in place: the warm start of the next lambda inherits it
+            res = s.beta.copy()
+            res[q - p:] *= colsq_inv if standardize_ else 1.0
+            beta[1 - int(intercept):, i] = res
+            if compute_loss:
+                r = Y - X @ res[q - p:]
+                if intercept:
+                    r = r - res[0]
+                loss[i] = float((r ** 2).sum())
+        out["beta"].append(beta)
+        out["lambda_"].append(lam)
+        out["niter"].append(niter)
+        out["loss"].append(loss)
     return out
 
 

@@ -68,3 +68,22 @@ def assert_same_fit(got, ref, tol=1e-8, check_niter=True, lam_ulps=None, lam_rto
             # an iteration-count flip (1-ulp difference at the stop threshold) is tolerated on a few lambdas
             assert np.mean(ng != nr) <= 0.1 and np.max(np.abs(ng - nr)) <= 2, (ng, nr)
     assert abs(got["d"] - ref["d"]) <= 1e-9 * abs(ref["d"]), (got["d"], ref["d"])
+
+
+def sparse_problem(seed, n, p, density=0.05, nnz=10, noise=0.5, shift_y=0.0, empty_cols=(), empty_rows=0):
+    """A dgCMatrix-like design (scipy CSC, sorted indices) in the style of man/oem.Rd:104-112 (rsparsematrix + rnorm)."""
+    import scipy.sparse as sps
+    rng = np.random.default_rng(seed)
+    X = sps.random(n, p, density=density, random_state=np.random.RandomState(seed), format="lil",
+                   data_rvs=rng.standard_normal)
+    for j in empty_cols:
+        X[:, j] = 0.0
+    if empty_rows:
+        X[:empty_rows, :] = 0.0
+    X = sps.csc_matrix(X)
+    X.eliminate_zeros()
+    X.sort_indices()
+    b = np.zeros(p)
+    b[:min(nnz, p)] = rng.uniform(-1.0, 1.0, size=min(nnz, p))
+    y = X @ b + rng.normal(0.0, noise, size=n) + shift_y
+    return X, y

@@ -1,0 +1,96 @@
+"""oem_fit_sparse: dgCMatrix input through the C ABI against the oracle's restatement of
+src/oem_sparse.cpp / oem_sparse.h -- all penalties, the four standardize / intercept combinations (the intercept column
+is the constant `intval`, get_beta() rescales beta(0) in place), compute.loss, empty rows / columns, device-resident
+slots, run-to-run determinism of the atomics-free Gram."""
+import numpy as np
+import pytest
+
+from cases import args_xy, assert_same_fit, sparse_problem
+
+pytestmark = pytest.mark.gpu
+
+ALL_PENS = ["lasso", "ols", "elastic.net", "scad", "scad.net", "mcp", "mcp.net", "grp.lasso", "grp.lasso.net", "grp.mcp",
+            "grp.scad", "grp.mcp.net", "grp.scad.net", "sparse.grp.lasso"]
+
+
+def _groups(p, size, intercept):
+    g = np.arange(p) // size + 1
+    if intercept:                     # R/oem.R:300-337: group 0 for the explicit intercept of a sparse x
+        g = np.concatenate([[0], g])
+    return g, np.unique(g)
+
+
+@pytest.mark.parametrize("standardize,intercept", [(True, True), (True, False), (False, True), (False, False)])
+def test_sparse_all_penalties(lib, oracle, standardize, intercept):
+    X, y = sparse_problem(70 + 2 * standardize + intercept, 4000, 45, density=0.08, shift_y=2.0, empty_cols=(7,), empty_rows=5)
+    g, ug = _groups(45, 5, intercept)
+    a = args_xy(X, y, "gaussian", ALL_PENS, groups=g, unique_groups=ug, alpha=0.6, gamma=3.5, tau=0.4, nlambda=15,
+                standardize=standardize, intercept=intercept, compute_loss=True, opts=dict(tol=1e-9))
+    got, ref = lib.oem_fit_sparse(*a), oracle.oem_fit_sparse(*a)
+    assert_same_fit(got, ref)
+    for lg, lr in zip(got["loss"], ref["loss"]):
+        assert np.allclose(lg[:len(lr)], lr, rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("n,p,density", [(300, 7, 0.5), (2500, 130, 0.02), (20000, 300, 0.01), (9000, 1001, 0.004)])
+def test_sparse_shapes(lib, oracle, n, p, density):
+    # p around / above the 4 * SMs split threshold, ragged sizes, very sparse rows (many empty)
+    X, y = sparse_problem(n + p, n, p, density=density)
+    a = args_xy(X, y, "gaussian", ["lasso", "mcp"], nlambda=10, lmin_ratio=1e-3, opts=dict(tol=1e-8))
+    got, ref = lib.oem_fit_sparse(*a), oracle.oem_fit_sparse(*a)
+    assert_same_fit(got, ref)
+    assert got["stats"]["gram_launches"] == 1 and got["stats"]["kernel_launches"] >= 8
+
+
+def test_sparse_equals_dense_identity(lib):
+    # man/oem.Rd:104-125 -> docs/reference/oem.html prints max|dense - sparse| = 1.58e-15 / 1.61e-15 for
+    # standardize = FALSE, intercept = FALSE (inputs from rsparsematrix, not reproducible): same order here
+    X, y = sparse_problem(5, 6000, 60, density=0.03)
+    g, ug = _groups(60, 5, False)
+    a = args_xy(X, y, "gaussian", ["lasso", "grp.lasso"], groups=g, unique_groups=ug, standardize=False, intercept=False,
+                nlambda=30)
+    fs = lib.oem_fit_sparse(*a)
+    a[0] = np.asfortranarray(X.toarray())
+    a[8] = [np.array(l) for l in fs["lambda_"]]           # lambda = fit$lambda, as in the example
+    fd = lib.oem_fit_dense(*a)
+    for bs, bd in zip(fs["beta"], fd["beta"]):
+        assert np.max(np.abs(bs - bd)) <= 1e-12
+
+
+def test_sparse_device_slots_and_determinism(lib, oracle):
+    import torch
+    X, y = sparse_problem(11, 15000, 90, density=0.05)
+    a = args_xy(X, y, "gaussian", ["lasso", "scad"], nlambda=12, compute_loss=True)
+    ref = oracle.oem_fit_sparse(*a)
+    dev = torch.device("cuda", 0)
+    slots = (torch.from_numpy(X.indices.astype(np.int32)).to(dev), torch.from_numpy(X.indptr.astype(np.int32)).to(dev),
+             torch.from_numpy(X.data).to(dev), X.shape)
+    a[0], a[1] = slots, torch.from_numpy(y).to(dev)
+    r1, r2 = lib.oem_fit_sparse(*a), lib.oem_fit_sparse(*a)
+    assert_same_fit(r1, ref)
+    for b1, b2 in zip(r1["beta"], r2["beta"]):
+        assert np.array_equal(b1, b2)                      # no floating-point atomics anywhere: bit-identical reruns
+    assert r1["d"] == r2["d"] and all(np.array_equal(u, v) for u, v in zip(r1["loss"], r2["loss"]))
+
+
+def test_sparse_frontend_and_errors(lib, oracle):
+    from oem_b200 import frontend as fe
+    X, y = sparse_problem(21, 3000, 40, density=0.1, shift_y=-1.0)
+    groups = np.repeat(np.arange(1, 9), 5)
+    r = fe.oem(X, y, penalty=["lasso", "grp.lasso"], groups=groups, nlambda=20)
+    g0 = np.concatenate([[0], groups])
+    ref = oracle.oem_fit_sparse(X, y, "gaussian", ["lasso", "grp.lasso"], [], g0, np.unique(g0), [], [[], []], 20, 1e-4, 1.0,
+                                3.0, 0.5, np.ones(40), True, True, False, dict(maxit=500, tol=1e-7))
+    for i, pen in enumerate(["lasso", "grp.lasso"]):
+        assert np.max(np.abs(r["beta"][pen] - ref["beta"][i])) <= 1e-8
+    with pytest.raises(NotImplementedError):
+        fe.oem(X, (y > 0).astype(float), family="binomial", penalty="lasso")
+    Xw, yw = sparse_problem(3, 30, 40, density=0.3)
+    with pytest.raises(lib.OemB200Error) as ei:           # n <= p: XX' branch
+        lib.oem_fit_sparse(*args_xy(Xw, yw, "gaussian", ["lasso"]))
+    assert ei.value.code == 4
+    bad = (X.indices.astype(np.int32), X.indptr.astype(np.int32)[::-1].copy(), X.data, X.shape)
+    a = args_xy(X, y, "gaussian", ["lasso"])
+    a[0] = bad
+    with pytest.raises(lib.OemB200Error, match="col_ptr"):
+        lib.oem_fit_sparse(*a)
