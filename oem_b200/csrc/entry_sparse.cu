@@ -8,8 +8,8 @@
 //
 // Data pass, all deterministic (no floating-point atomics):
 //   csc_colstats_kernel   one CTA per column: sum x, sum x*y, sum x^2                       (oem_sparse.h:495-507, 580, 829)
-//   csr_count / scan / fill   CSC -> CSR on the device (integer atomics only; the order of a row's entries is
-//                         irrelevant below because they land in different accumulator slots)
+//   csr_count / scan / fill / sort_rows   CSC -> CSR on the device (integer atomics only; rows are then put into
+//                         ascending column order by ranking, so every later sum has a fixed order)
 //   sparse_gram_kernel    CTA (j, split): for every stored x_ij of column j (in storage order, dealt round-robin to the
 //                         warps) add x_ij * row_i into the warp's private p-vector in shared memory; fixed-order reduce
 //                         over warps, then over splits -> column j of X'X.  Work = sum_i nnz(row i)^2 multiply-adds, the
@@ -133,6 +133,31 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const int *__restrict__ c
         const int pos = atomicAdd(&cursor[row_idx[e]], 1);
         csr_col[pos] = j;
         csr_val[pos] = val[e];
+    }
+}
+
+// The fill's atomics leave a row's entries in arbitrary order.  The Gram does not care (distinct slots), but the loss sums
+// along a row, so rows are put into ascending column order: one warp per row, every entry's position is its rank (the
+// number of smaller column indices) -- m^2 / 32 comparisons per lane for a row of m entries, never more than the Gram's
+// own m^2 multiply-adds for that row.
+__global__ void __launch_bounds__(256) csr_sort_rows_kernel(const int *__restrict__ row_ptr, int n, const int *__restrict__ col_in,
+                                                            const double *__restrict__ val_in, int *__restrict__ col_out,
+                                                            double *__restrict__ val_out) {
+    const int lane = threadIdx.x & 31;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int s = row_ptr[i], m = row_ptr[i + 1] - s;
+    for (int base = 0; base < m; base += 32) {
+        const int k = base + lane;
+        const int mycol = k < m ? col_in[s + k] : 0x7fffffff;
+        const double myval = k < m ? val_in[s + k] : 0.0;
+        int rank = 0;
+        for (int b0 = 0; b0 < m; b0 += 32) {
+            const int oc = b0 + lane < m ? col_in[s + b0 + lane] : 0x7fffffff;
+#pragma unroll
+            for (int t = 0; t < 32; ++t) rank += __shfl_sync(0xffffffffu, oc, t) < mycol;
+        }
+        if (k < m) { col_out[s + rank] = mycol; val_out[s + rank] = myval; }
     }
 }
 
@@ -299,16 +324,19 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
     // ---- CSC -> CSR ----
     const size_t t_g = tm.start(&cx.st.ms_gram);
     const int ntile = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
-    DBuf<int> row_ptr((size_t)n + 1), cursor((size_t)n), totals((size_t)ntile), csr_col((size_t)std::max(nnz, 1));
-    DBuf<double> csr_val((size_t)std::max(nnz, 1));
+    DBuf<int> row_ptr((size_t)n + 1), cursor((size_t)n), totals((size_t)ntile), csr_col((size_t)std::max(nnz, 1)),
+        csr_col_u((size_t)std::max(nnz, 1));
+    DBuf<double> csr_val((size_t)std::max(nnz, 1)), csr_val_u((size_t)std::max(nnz, 1));
     row_ptr.zero(cx.stream);
     if (nnz > 0) csr_count_kernel<<<(nnz + 255) / 256, 256, 0, cx.stream>>>(d_ri, nnz, row_ptr.p);
     scan_tiles_kernel<<<ntile, SCAN_THREADS, 0, cx.stream>>>(row_ptr.p, (int)n, totals.p);
     scan_totals_kernel<<<1, SCAN_THREADS, 0, cx.stream>>>(totals.p, ntile);
     scan_finish_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, cx.stream>>>(row_ptr.p, (int)n, totals.p, nnz, cursor.p);
-    csr_fill_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, cursor.p, csr_col.p, csr_val.p);
+    csr_fill_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, cursor.p, csr_col_u.p, csr_val_u.p);
+    csr_sort_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, cx.stream>>>(row_ptr.p, (int)n, csr_col_u.p, csr_val_u.p, csr_col.p,
+                                                                         csr_val.p);
     OEM_CUDA(cudaGetLastError());
-    cx.st.kernel_launches += 4 + (nnz > 0 ? 1 : 0);
+    cx.st.kernel_launches += 5 + (nnz > 0 ? 1 : 0);
 
     // ---- X'X ----
     int nwarps = 8;
