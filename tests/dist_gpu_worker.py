@@ -10,7 +10,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cases import args_xy, assert_same_fit, binomial_problem, gaussian_problem   # noqa: E402
+from cases import args_xy, assert_same_fit, binomial_problem, gaussian_problem, sparse_problem   # noqa: E402
 
 
 def main():
@@ -67,6 +67,18 @@ def main():
         for pp in range(2):
             assert np.allclose(got["cvm"][pp], ref["cvm"][pp], rtol=1e-9)
             assert np.allclose(got["cvsd"][pp], ref["cvsd"][pp], rtol=1e-8)
+    # sparse (dgCMatrix row blocks; the loss partials are a second all-reduce)
+    Xs, ysp = sparse_problem(106, 8000, 50, density=0.06, shift_y=1.0)
+    a = args_xy(Xs, ysp, "gaussian", ["lasso", "mcp"], nlambda=15, compute_loss=True)
+    ref = orc.oem_fit_sparse(*a) if rank == 0 else None
+    r0, r1 = shard_rows(8000, rank, world)
+    sa = list(a)
+    sa[0], sa[1] = Xs[r0:r1].tocsc(), ysp[r0:r1]
+    got_s = oem_b200.oem_fit_sparse(*sa, comm=comm)
+    if rank == 0:
+        assert_same_fit(got_s, ref)
+        for lg, lr in zip(got_s["loss"], ref["loss"]):
+            assert np.allclose(lg[:len(lr)], lr, rtol=1e-10, atol=0)
     # every rank holds the same replicated result
     chk = torch.tensor([float(np.sum(got["beta"][0]))], dtype=torch.float64, device="cuda")
     lo, hi = chk.clone(), chk.clone()

@@ -1,11 +1,11 @@
-"""-m gpu: seeded random sweep of the argument space of the five entry points (penalty mixes, groups with and
+"""-m gpu: seeded random sweep of the argument space of the six entry points (penalty mixes, groups with and
 without the unpenalised group 0, zero / uneven penalty factors, user lambda lists, alpha / gamma / tau, the
 standardize x intercept flags, ragged n and p, observation weights for xval) -- every draw is run through the C ABI
 and compared with the CPU oracle at the BASELINE bar (max |delta beta| <= 1e-8, equal lambda sequences, d to 1e-9)."""
 import numpy as np
 import pytest
 
-from cases import args_xy, assert_same_fit, binomial_problem, gaussian_problem
+from cases import args_xy, assert_same_fit, binomial_problem, gaussian_problem, sparse_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +26,7 @@ def draw(rng, entry):
     g = np.sort(rng.integers(1, ngrp + 1, size=p)).astype(np.int32)
     if rng.uniform() < 0.3:
         g[g == g[0]] = 0                                   # an unpenalised group of variables
-    explicit = intercept and entry in ("big", "xval", "logistic")
+    explicit = intercept and entry in ("big", "xval", "logistic", "sparse")
     groups = np.concatenate([[0], g]).astype(np.int32) if explicit else g
     pf = rng.uniform(0.3, 2.0, size=p)
     if rng.uniform() < 0.4:
@@ -81,6 +81,24 @@ def test_fuzz_big(lib, oracle, seed):
     assert_same_fit(got, ref, check_niter=False)
     a = args_xy(X, y, "gaussian", pens, **user_lambda(rng, ref, kw))
     assert_same_fit(lib.oem_fit_big(*a), oracle.oem_fit_big(*a), check_niter=False)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_sparse(lib, oracle, seed):
+    rng = np.random.default_rng(13000 + seed)
+    n, p, pens, kw = draw(rng, "sparse")
+    n = max(n, 12 * p + 50)
+    X, y = sparse_problem(13500 + seed, n, p, density=float(rng.choice([0.02, 0.1, 0.4])), shift_y=float(rng.uniform(-2, 2)),
+                          empty_cols=(int(rng.integers(0, p)),) if rng.uniform() < 0.3 else ())
+    kw["compute_loss"] = bool(rng.integers(0, 2))
+    a = args_xy(X, y, "gaussian", pens, **kw)
+    got, ref = lib.oem_fit_sparse(*a), oracle.oem_fit_sparse(*a)
+    assert_same_fit(got, ref, check_niter=False)
+    if kw["compute_loss"]:
+        for pp in range(len(pens)):
+            assert np.allclose(got["loss"][pp][:len(ref["loss"][pp])], ref["loss"][pp], rtol=1e-8)
+    a = args_xy(X, y, "gaussian", pens, **user_lambda(rng, ref, kw))
+    assert_same_fit(lib.oem_fit_sparse(*a), oracle.oem_fit_sparse(*a), check_niter=False)
 
 
 @pytest.mark.parametrize("seed", range(24))
