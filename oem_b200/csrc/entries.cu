@@ -282,12 +282,16 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
     const size_t nb2 = (size_t)p * p + 2 * (size_t)p;
     DBuf<double> b2(nb2), stats2(3 * (size_t)p);
     double *G = b2.p, *xy = G + (size_t)p * p, *css = xy + p;
-    // X'ys and the (centred) sums of squares ride in the Gram launch (diagonal-tile CTAs) unless flag 1 needs the
-    // sd about the mean of an uncentred X, or OEMB200_SEPARATE_COLSTATS=1 asks for the separate sweep.  Small problems
-    // keep the sweep: at n = 1e6 x p = 100 the fused launch measured 2.84 ms per fit against 2.41 ms (partial-statistics
-    // reduce), while from p = 500 up the Gram dwarfs the statistics and the saved pass over X is a net win
-    const bool fused_stats = flag != 1 && p >= 256 && (double)n * p >= 268435456.0 &&
-                             getenv("OEMB200_SEPARATE_COLSTATS") == nullptr;
+    // X'ys and the (centred) sums of squares can ride in the Gram launch (diagonal-tile CTAs, CENTER + STATS variant), but
+    // for this entry it does not pay: the centred variant masks the tail rows of every fragment, and measured on a B200
+    // the fused launch lost at both ends -- n = 1e6 x p = 100: 2.84 ms per fit against 2.41 ms; n = 2e6 x p = 512:
+    // 28.9 ms against 27.3 ms (Gram 19.9 vs 18.4 ms for a 1.2 ms sweep saved; tools/bench_dense_stats.py).  The separate
+    // HBM sweep therefore stays the default whenever X is centred; OEMB200_FUSED_COLSTATS=1 selects the fused launch
+    // (kept under test).  Uncentred, unscaled fits (flag 0) use the plain STATS variant that already pays for big.oem and
+    // xval.oem from p = 500 up.
+    const bool forced = getenv("OEMB200_FUSED_COLSTATS") != nullptr;
+    const bool fused_stats = getenv("OEMB200_SEPARATE_COLSTATS") == nullptr &&
+                             ((flag != 1 && forced) || (flag == 0 && p >= 256 && (double)n * p >= 268435456.0));
     if (fused_stats) {
         gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, center_x ? d_mean.p : nullptr, nullptr, G, false, yuse,
                     stats2.p);
