@@ -10,13 +10,14 @@
 //   csc_colstats_kernel   one CTA per column: sum x, sum x*y, sum x^2                       (oem_sparse.h:495-507, 580, 829)
 //   csr_count / scan / fill / sort_rows   CSC -> CSR on the device (integer atomics only; rows are then put into
 //                         ascending column order by ranking, so every later sum has a fixed order)
-//   sparse_gram_kernel    CTA (j, split): for every stored x_ij of column j (in storage order, dealt round-robin to the
-//                         warps) add x_ij * row_i into the warp's private p-vector in shared memory; fixed-order reduce
-//                         over warps, then over splits -> column j of X'X.  Work = sum_i nnz(row i)^2 multiply-adds, the
+//   sparse_gram_kernel    CTA (j, split): for every stored x_ij of column j (32 at a time per warp, chunks dealt round-robin
+//                         to the warps) add x_ij * row_i into the warp's private p-vector in shared memory; fixed-order
+//                         reduce over warps, then over splits -> column j of X'X.  Work = sum_i nnz(row i)^2 multiply-adds, the
 //                         same count as the row-wise outer-product form Eigen's rankUpdate performs (oem_sparse.h:341-344)
 //   sparse_loss_kernel    compute.loss: one warp per row, lanes over the (penalty, lambda) columns       (oem_sparse.h:918-943)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "host_common.h"
 
@@ -178,15 +179,49 @@ __global__ void __launch_bounds__(256) sparse_gram_kernel(const int *__restrict_
     const int b = e0 + s * len, e = min(b + len, e1);
     if (w < nwarps) {
         double *a = acc + (size_t)w * p;
-        for (int t = b + w; t < e; t += nwarps) {
-            const int i = row_idx[t];
-            const double xv = val[t];
-            const int k1 = row_ptr[i + 1];
-            for (int k = row_ptr[i] + lane; k < k1; k += 32) {
-                const int c = csr_col[k];
-                a[c] = fma(xv, csr_val[k], a[c]);      // a row's entries hit distinct slots
+        const unsigned lt = (1u << lane) - 1u;
+        // A warp takes 32 stored entries of column j at a time: lane l owns entry t = chunk + l (row i_l, value x_l, the
+        // row's CSR extent).  The rows' entries are then walked as ONE flat list, 32 per step, so every step has 32
+        // independent loads in flight instead of one short row's worth (the first version: long_scoreboard 20.7 warps per
+        // issue, profiles/r01_sparse_gram_ncu_summary.md).  Two lanes of a step can hit the same slot (different rows,
+        // same column): they are applied in lane order = flat order, so each slot still sees a fixed sequence of adds.
+        for (int chunk = b + w * 32; chunk < e; chunk += nwarps * 32) {
+            const int t = chunk + lane;
+            const bool own = t < e;
+            const int i = own ? row_idx[t] : 0;
+            const double xv = own ? val[t] : 0.0;
+            const int rs = own ? row_ptr[i] : 0;
+            const int m = own ? row_ptr[i + 1] - rs : 0;
+            int inc = m;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
             }
-            __syncwarp();                               // orders this row's updates before the next row's
+            const int pre = inc - m;                                   // exclusive prefix of the row lengths
+            const int T = __shfl_sync(0xffffffffu, inc, 31);
+            for (int f0 = 0; f0 < T; f0 += 32) {
+                const int f = f0 + lane;
+                const bool act = f < T;
+                int u = 0;                                             // last lane whose prefix is <= f: the owning row
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int cand = u + step;
+                    const int pc = __shfl_sync(0xffffffffu, pre, cand & 31);
+                    if (cand < 32 && pc <= f) u = cand;
+                }
+                const int k = __shfl_sync(0xffffffffu, rs, u) + (f - __shfl_sync(0xffffffffu, pre, u));
+                const double x = __shfl_sync(0xffffffffu, xv, u);
+                const int c = act ? csr_col[k] : -1 - lane;            // inactive lanes get unique dummies
+                const double v = act ? csr_val[k] : 0.0;
+                const unsigned same = __match_any_sync(0xffffffffu, c);
+                const unsigned r = __popc(same & lt);                  // my position among the lanes hitting slot c
+                const unsigned rmax = __reduce_max_sync(0xffffffffu, act ? r : 0u);
+                for (unsigned rr = 0; rr <= rmax; ++rr) {
+                    if (act && r == rr) a[c] = fma(x, v, a[c]);
+                    __syncwarp();
+                }
+            }
         }
     }
     __syncthreads();
@@ -195,6 +230,36 @@ __global__ void __launch_bounds__(256) sparse_gram_kernel(const int *__restrict_
         double t = 0.0;
         for (int ww = 0; ww < nwarps; ++ww) t += acc[(size_t)ww * p + c];
         out[c] = t;
+    }
+}
+
+// ---- dense route for not-so-sparse designs: rows [r0, r1) of the CSC matrix scattered into a zeroed column-major tile ----
+__global__ void __launch_bounds__(256) csc_densify_kernel(const int *__restrict__ col_ptr, const int *__restrict__ row_idx,
+                                                          const double *__restrict__ val, int r0, int r1, long long ld,
+                                                          double *__restrict__ dense) {
+    const int j = blockIdx.x;
+    for (int e = col_ptr[j] + threadIdx.x; e < col_ptr[j + 1]; e += 256) {
+        const int i = row_idx[e];
+        if (i >= r0 && i < r1) dense[(size_t)j * ld + (i - r0)] = val[e];
+    }
+}
+
+// sum_i nnz(row i)^2 = multiply-adds of the sparse route (one partial per CTA, summed on the host)
+__global__ void __launch_bounds__(256) row_pairs_kernel(const int *__restrict__ row_ptr, int n, double *__restrict__ partial) {
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const double m = (double)(row_ptr[i + 1] - row_ptr[i]);
+        s = fma(m, m, s);
+    }
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        partial[blockIdx.x] = t;
     }
 }
 
@@ -338,26 +403,64 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
     OEM_CUDA(cudaGetLastError());
     cx.st.kernel_launches += 5 + (nnz > 0 ? 1 : 0);
 
+    tm.stop(t_g);
+
     // ---- X'X ----
+    // Route: the sparse kernel costs sum_i nnz(row i)^2 shared-memory multiply-adds at ~8e10 / s (measured: n = 1e6,
+    // p = 1000: 1.8 ms at 1 % density, 31 ms at 5 %), the dense route (scatter 2 GB row blocks into a zeroed tile, TMA / DMMA
+    // Gram on each) a flat 43 ms at that shape, i.e. n p (p + 1) flops at ~2.4e13 / s all in.  From about 6 % density on the
+    // dense route is cheaper (same deterministic result, different rounding).
+    const int npart = 4 * cx.num_sms;
+    DBuf<double> pairs_part((size_t)npart);
+    row_pairs_kernel<<<npart, 256, 0, cx.stream>>>(row_ptr.p, (int)n, pairs_part.p);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+    std::vector<double> h_pairs(npart);
+    pairs_part.download(h_pairs.data(), npart, cx.stream);
+    cx.sync();
+    double row_pairs = 0.0;
+    for (double v : h_pairs) row_pairs += v;
+    const char *route_env = getenv("OEMB200_SPARSE_ROUTE");       // "dense" / "sparse" force a route (tests, A/B)
+    bool dense_route = 300.0 * row_pairs > (double)n * p * (p + 1.0) && p >= 64;
+    if (route_env && !strcmp(route_env, "dense")) dense_route = true;
+    if (route_env && !strcmp(route_env, "sparse")) dense_route = false;
+    if (dense_route) {
+        const int64_t align = 2 * gram_kt();
+        int64_t rows = (int64_t)((double)(1ll << 31) / (8.0 * p));
+        rows = std::max<int64_t>(align, rows / align * align);
+        rows = std::min<int64_t>(rows, (n + align - 1) / align * align);
+        DBuf<double> tile((size_t)rows * p);
+        for (int64_t r0 = 0, c = 0; r0 < n; r0 += rows, ++c) {
+            const int64_t nr = std::min(rows, n - r0);
+            tile.zero(cx.stream);
+            csc_densify_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, (int)r0, (int)(r0 + nr), (long long)rows, tile.p);
+            OEM_CUDA(cudaGetLastError());
+            cx.st.kernel_launches += 1;
+            gram_launch(cx, tile.p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, nullptr, G, c > 0);
+        }
+    }
     int nwarps = 8;
     while (nwarps > 1 && (size_t)nwarps * p * 8 > cx.smem_optin) nwarps >>= 1;
     if ((size_t)nwarps * p * 8 > cx.smem_optin) fail(OEMB200_EUNSUPPORTED, "sparse: p = %d exceeds the shared-memory accumulator", p);
     const int nsplit = std::max(1, std::min(16, (4 * cx.num_sms + p - 1) / p));
-    DBuf<double> Gpart;
-    double *gout = G;
-    if (nsplit > 1) { Gpart.alloc((size_t)nsplit * pp2); gout = Gpart.p; }
-    const size_t smem = (size_t)nwarps * p * 8;
-    OEM_CUDA(cudaFuncSetAttribute(sparse_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sparse_gram_kernel<<<dim3(p, nsplit), 256, smem, cx.stream>>>(d_cp, d_ri, d_v, row_ptr.p, csr_col.p, csr_val.p, p, nwarps, gout);
-    OEM_CUDA(cudaGetLastError());
-    cx.st.kernel_launches += 1;
-    if (nsplit > 1) {
-        sum_splits_kernel<<<(unsigned)((pp2 + 255) / 256), 256, 0, cx.stream>>>(Gpart.p, nsplit, pp2, G);
+    if (!dense_route) {
+        const size_t t_k = tm.start(&cx.st.ms_gram);
+        DBuf<double> Gpart;
+        double *gout = G;
+        if (nsplit > 1) { Gpart.alloc((size_t)nsplit * pp2); gout = Gpart.p; }
+        const size_t smem = (size_t)nwarps * p * 8;
+        OEM_CUDA(cudaFuncSetAttribute(sparse_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sparse_gram_kernel<<<dim3(p, nsplit), 256, smem, cx.stream>>>(d_cp, d_ri, d_v, row_ptr.p, csr_col.p, csr_val.p, p, nwarps, gout);
         OEM_CUDA(cudaGetLastError());
         cx.st.kernel_launches += 1;
+        if (nsplit > 1) {
+            sum_splits_kernel<<<(unsigned)((pp2 + 255) / 256), 256, 0, cx.stream>>>(Gpart.p, nsplit, pp2, G);
+            OEM_CUDA(cudaGetLastError());
+            cx.st.kernel_launches += 1;
+        }
+        cx.st.gram_launches += 1;
+        tm.stop(t_k);
     }
-    cx.st.gram_launches += 1;
-    tm.stop(t_g);
 
     const double nd = (double)n;
     OEM_CUDA(cudaMemcpyAsync(nobs, &nd, 8, cudaMemcpyHostToDevice, cx.stream));

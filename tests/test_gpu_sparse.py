@@ -42,6 +42,23 @@ def test_sparse_shapes(lib, oracle, n, p, density):
     assert got["stats"]["gram_launches"] == 1 and got["stats"]["kernel_launches"] >= 8
 
 
+@pytest.mark.parametrize("route", ["dense", "sparse", None])
+def test_sparse_routes_agree(lib, oracle, monkeypatch, route):
+    # 40 % density at p = 80: the cost model (sum nnz(row)^2 against n p^2) picks the dense-tile route by itself (None);
+    # both forced routes must give the same fit
+    if route:
+        monkeypatch.setenv("OEMB200_SPARSE_ROUTE", route)
+    X, y = sparse_problem(33, 3001, 80, density=0.4, shift_y=0.5, empty_rows=3)
+    g, ug = _groups(80, 8, True)
+    a = args_xy(X, y, "gaussian", ["lasso", "grp.lasso", "scad"], groups=g, unique_groups=ug, nlambda=12, compute_loss=True,
+                opts=dict(tol=1e-9))
+    got, ref = lib.oem_fit_sparse(*a), oracle.oem_fit_sparse(*a)
+    assert_same_fit(got, ref)
+    for lg, lr in zip(got["loss"], ref["loss"]):
+        assert np.allclose(lg[:len(lr)], lr, rtol=1e-10, atol=0)
+    assert got["stats"]["gram_flops"] == (0.0 if route == "sparse" else 3001.0 * 80 * 81)      # which kernel built X'X
+
+
 def test_sparse_equals_dense_identity(lib):
     # man/oem.Rd:104-125 -> docs/reference/oem.html prints max|dense - sparse| = 1.58e-15 / 1.61e-15 for
     # standardize = FALSE, intercept = FALSE (inputs from rsparsematrix, not reproducible): same order here
