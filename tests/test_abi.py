@@ -91,3 +91,37 @@ def test_argument_validation_precedes_device_use(lib):
         api.make_opts({"no_such_option": 1})
     o = api.make_opts({"maxit": 10, "tol": 1e-9, "hessian.type": "full", "irls.maxit": 7})
     assert (o.maxit, o.tol, o.hessian_full, o.irls_maxit) == (10, 1e-9, 1, 7)
+
+
+def test_header_is_plain_c_and_callable_from_c(lib, tmp_path):
+    """The boundary is a C ABI: include/oem_b200.h compiles as C99 (no C++ / torch types in the signatures) and a C
+    program linked against liboem_b200.so can call it -- host-only helpers here, the compute entries need a GPU."""
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "abi_probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "oem_b200.h"
+int main(void) {
+    oemb200_opts o; oemb200_spec s; oemb200_result r; oemb200_stats st;
+    double grid[5];
+    memset(&s, 0, sizeof s); memset(&r, 0, sizeof r); memset(&st, 0, sizeof st);
+    oemb200_default_opts(&o);
+    if (o.maxit != 500 || o.irls_maxit != 100) return 2;
+    if (oemb200_penalty_id("grp.lasso") < 0 || oemb200_penalty_id("nope") != -1) return 3;
+    if (oemb200_lambda_grid(2.0, 5, 1e-2, grid) != OEMB200_OK) return 4;
+    if (!(grid[0] == 2.0 && grid[4] < grid[3] && grid[3] < grid[0])) return 5;
+    /* a compute entry with NULL arguments must come back as a status code, never crash or throw */
+    if (oemb200_fit_sparse(0, 0, 0, 10, 2, 0, 0, 0, 0) == OEMB200_OK) return 6;
+    if (strlen(oemb200_last_error()) == 0) return 7;
+    printf("%s\n", oemb200_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi_probe"
+    libdir = os.path.dirname(lib.lib_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe),
+                           "-L", libdir, "-loem_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "sm_100a" in out.stdout
