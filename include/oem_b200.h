@@ -176,6 +176,12 @@ int oemb200_predict(const double *x, int64_t n, int p, int64_t ldx, const double
                     int nlambda, int type, double *out, int64_t ldo, const oemb200_opts *opts,
                     oemb200_stats *stats);
 
+/* predict.oem on a sparse newx (dgCMatrix slots as in oemb200_fit_sparse; `as.matrix(newx %*% nbeta)`, R/methods.R:113-118).
+ * Same beta / type / out conventions as oemb200_predict. */
+int oemb200_predict_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p,
+                           const double *beta, int beta_rows, int nlambda, int type, double *out, int64_t ldo,
+                           const oemb200_opts *opts, oemb200_stats *stats);
+
 /* ------------------------------------------------------------------------------------------
  * Phase-level entries (device pointers only) used by bench.py for the roofline numbers and by
  * the Gram-level parity tests.  They are the kernels the five entries above are made of.

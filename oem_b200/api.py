@@ -106,6 +106,7 @@ def load():
     L.oemb200_stop_rule.argtypes = [vp, vp, ci, dbl]
     L.oemb200_release_cache.restype = None
     L.oemb200_predict.argtypes = [vp, i64, ci, i64, vp, ci, ci, ci, vp, i64, op, ctypes.POINTER(Stats)]
+    L.oemb200_predict_sparse.argtypes = [vp, vp, vp, i64, ci, vp, ci, ci, ci, vp, i64, op, ctypes.POINTER(Stats)]
     _lib = L
     return L
 
@@ -114,7 +115,7 @@ EXPORTS = ["oemb200_last_error", "oemb200_version", "oemb200_device_count", "oem
            "oemb200_penalty_id", "oemb200_nlambda_max", "oemb200_fit_dense", "oemb200_xtx", "oemb200_xval_dense",
            "oemb200_fit_logistic_dense", "oemb200_fit_big", "oemb200_fit_sparse", "oemb200_gram", "oemb200_colstats",
            "oemb200_xb_logistic", "oemb200_top_eig", "oemb200_lambda_grid", "oemb200_stop_rule",
-           "oemb200_release_cache", "oemb200_predict"]
+           "oemb200_release_cache", "oemb200_predict", "oemb200_predict_sparse"]
 
 
 def lambda_grid(lmax, nlambda, lmin_ratio):
@@ -419,11 +420,17 @@ def oem_xtx(xtx, xty, family, penalty, groups, unique_groups, group_weights, lam
 def predict_matrix(newx, beta, response=False, opts=None, out=None, return_stats=False):
     """newx %*% beta (+ intercept row) on the device: the GEMM of predict.oem (R/methods.R:113-118); response=True
     applies the logistic link of predict.oemfit_binomial (R/methods.R:355-358).  newx: n x p host (numpy) or device
-    (column-major torch) matrix; beta: (p+1) x L with the intercept in row 0, or p x L.  Returns an n x L
+    (column-major torch) matrix, or sparse (scipy.sparse / dgCMatrix slots -> oemb200_predict_sparse); beta: (p+1) x L with the intercept in row 0, or p x L.  Returns an n x L
     column-major numpy array, or fills `out` (a column-major float64 cuda tensor n x L) in place."""
     L = load()
     keep = _Keep()
-    xp, n, p, ld = _matrix_arg(newx, keep)
+    sparse = isinstance(newx, tuple) or type(newx).__module__.startswith("scipy.sparse")
+    if sparse:
+        ri, cp, vals, n, p = _csc_slots(newx)
+        rip, cpp = _int_array_arg(ri, keep), _int_array_arg(cp, keep)
+        vp_, _ = _vector_arg(vals, keep) if (_is_torch_cuda(vals) or np.asarray(vals).size) else (None, 0)
+    else:
+        xp, n, p, ld = _matrix_arg(newx, keep)
     b = np.asfortranarray(np.asarray(beta, dtype=np.float64))
     if b.ndim == 1:
         b = b.reshape(-1, 1, order="F")
@@ -437,6 +444,10 @@ def predict_matrix(newx, beta, response=False, opts=None, out=None, return_stats
         if not _is_torch_cuda(out) or tuple(out.shape) != (n, nl) or (out.stride(0) != 1 and n > 1):
             raise ValueError("out must be a column-major float64 cuda tensor of shape (n, nlambda)")
         res, op_, ldo = out, out.data_ptr(), max(out.stride(1) if nl > 1 else n, n)
-    _check(L.oemb200_predict(xp, n, p, ld, b.ctypes.data, rows, nl, 1 if response else 0, op_, ldo, ctypes.byref(o),
-                             ctypes.byref(st)))
+    if sparse:
+        _check(L.oemb200_predict_sparse(rip, cpp, vp_, n, p, b.ctypes.data, rows, nl, 1 if response else 0, op_, ldo,
+                                        ctypes.byref(o), ctypes.byref(st)))
+    else:
+        _check(L.oemb200_predict(xp, n, p, ld, b.ctypes.data, rows, nl, 1 if response else 0, op_, ldo, ctypes.byref(o),
+                                 ctypes.byref(st)))
     return (res, st.as_dict()) if return_stats else res

@@ -477,6 +477,8 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                   const oemb200_opts *o, oemb200_result *res);
 void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
                 const oemb200_spec *s, const oemb200_opts *o, oemb200_result *res);
+void predict_sparse_entry(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *beta,
+                          int nrows, int L, int type, double *out, int64_t ldo, const oemb200_opts *o, oemb200_stats *stats);
 void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s, int nfolds,
               const int *foldid, const char *type_measure, const oemb200_opts *o, oemb200_result *res);
 
@@ -623,6 +625,12 @@ int oemb200_xval_dense(const double *x, int64_t n, int p, int64_t ldx, const dou
 int oemb200_predict(const double *x, int64_t n, int p, int64_t ldx, const double *beta, int beta_rows, int nlambda, int type,
                     double *out, int64_t ldo, const oemb200_opts *opts, oemb200_stats *stats) {
     return guarded([&] { predict_entry(x, n, p, ldx, beta, beta_rows, nlambda, type, out, ldo, opts, stats); });
+}
+
+int oemb200_predict_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *beta,
+                           int beta_rows, int nlambda, int type, double *out, int64_t ldo, const oemb200_opts *opts,
+                           oemb200_stats *stats) {
+    return guarded([&] { predict_sparse_entry(row_idx, col_ptr, values, n, p, beta, beta_rows, nlambda, type, out, ldo, opts, stats); });
 }
 
 // ---------------- phase-level entries ----------------

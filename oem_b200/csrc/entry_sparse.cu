@@ -326,6 +326,29 @@ __global__ void sum_rows_kernel(const double *__restrict__ partial, int rows, in
 }
 
 // ------------------------------------------------------------------------------------------------ driver
+// CSC slots -> CSR copy on the device, rows in ascending column order (count / scan / fill / rank-sort above)
+struct DeviceCsr {
+    DBuf<int> row_ptr, col;
+    DBuf<double> val;
+    void build(Ctx &cx, const int *d_cp, const int *d_ri, const double *d_v, int64_t n, int p, int nnz) {
+        const int ntile = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+        DBuf<int> cursor((size_t)n), totals((size_t)ntile), col_u((size_t)std::max(nnz, 1));
+        DBuf<double> val_u((size_t)std::max(nnz, 1));
+        row_ptr.alloc((size_t)n + 1);
+        col.alloc((size_t)std::max(nnz, 1));
+        val.alloc((size_t)std::max(nnz, 1));
+        row_ptr.zero(cx.stream);
+        if (nnz > 0) csr_count_kernel<<<(nnz + 255) / 256, 256, 0, cx.stream>>>(d_ri, nnz, row_ptr.p);
+        scan_tiles_kernel<<<ntile, SCAN_THREADS, 0, cx.stream>>>(row_ptr.p, (int)n, totals.p);
+        scan_totals_kernel<<<1, SCAN_THREADS, 0, cx.stream>>>(totals.p, ntile);
+        scan_finish_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, cx.stream>>>(row_ptr.p, (int)n, totals.p, nnz, cursor.p);
+        csr_fill_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, cursor.p, col_u.p, val_u.p);
+        csr_sort_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, cx.stream>>>(row_ptr.p, (int)n, col_u.p, val_u.p, col.p, val.p);
+        OEM_CUDA(cudaGetLastError());
+        cx.st.kernel_launches += 5 + (nnz > 0 ? 1 : 0);
+    }
+};
+
 template <typename T>
 static const T *to_device_array(Ctx &cx, const T *h, size_t cnt, DBuf<T> &own) {
     if (cnt == 0) return nullptr;
@@ -334,6 +357,97 @@ static const T *to_device_array(Ctx &cx, const T *h, size_t cnt, DBuf<T> &own) {
     own.upload(h, cnt, cx.stream);
     cx.st.h2d_bytes += (int64_t)(cnt * sizeof(T));
     return own.p;
+}
+
+// validated CSC slots on the device
+struct CscInput {
+    DBuf<int> o_cp, o_ri;
+    DBuf<double> o_v;
+    const int *cp = nullptr, *ri = nullptr;
+    const double *v = nullptr;
+    int nnz = 0;
+    void load(Ctx &cx, const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p) {
+        std::vector<int> h_cp(p + 1);
+        if (is_device_ptr(col_ptr)) {
+            OEM_CUDA(cudaMemcpyAsync(h_cp.data(), col_ptr, sizeof(int) * (p + 1), cudaMemcpyDeviceToHost, cx.stream));
+            cx.sync();
+        } else memcpy(h_cp.data(), col_ptr, sizeof(int) * (p + 1));
+        if (h_cp[0] != 0) fail(OEMB200_EINVAL, "sparse: col_ptr[0] must be 0");
+        for (int j = 0; j < p; ++j)
+            if (h_cp[j + 1] < h_cp[j]) fail(OEMB200_EINVAL, "sparse: col_ptr must be non-decreasing");
+        nnz = h_cp[p];
+        if (nnz > 0 && (!row_idx || !values)) fail(OEMB200_EINVAL, "sparse: row_idx / values missing");
+        if (!is_device_ptr(row_idx))
+            for (int e = 0; e < nnz; ++e)
+                if (row_idx[e] < 0 || row_idx[e] >= n)
+                    fail(OEMB200_EINVAL, "sparse: row index %d out of range at entry %d", row_idx[e], e);
+        cp = to_device_array(cx, col_ptr, (size_t)p + 1, o_cp);
+        ri = to_device_array(cx, row_idx, (size_t)nnz, o_ri);
+        v = to_device_array(cx, values, (size_t)nnz, o_v);
+    }
+};
+
+// out[i + c * ldo] = b0[c] + sum_k x_ik Bt[col_k, c] (+ logistic response): one warp per row, lanes over the columns
+__global__ void __launch_bounds__(256) sparse_predict_kernel(const int *__restrict__ row_ptr, const int *__restrict__ csr_col,
+                                                             const double *__restrict__ csr_val, int n,
+                                                             const double *__restrict__ Bt, const double *__restrict__ b0,
+                                                             int C, int response, double *__restrict__ out, long long ldo) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = gw; i < n; i += nw) {
+        const int k0 = row_ptr[i], k1 = row_ptr[i + 1];
+        for (int c = lane; c < C; c += 32) {
+            double pr = 0.0;
+            for (int k = k0; k < k1; ++k) pr = fma(csr_val[k], Bt[(size_t)csr_col[k] * C + c], pr);
+            pr += b0[c];
+            out[i + (size_t)c * ldo] = response ? 1.0 / (1.0 + exp(-pr)) : pr;
+        }
+    }
+}
+
+void predict_sparse_entry(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *beta,
+                          int nrows, int L, int type, double *out, int64_t ldo, const oemb200_opts *o, oemb200_stats *stats) {
+    if (!col_ptr || !beta || !out || !o) fail(OEMB200_EINVAL, "col_ptr / beta / out / opts must not be NULL");
+    if (n < 1 || p < 1 || L < 1 || ldo < n || n >= (1ll << 31))
+        fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d L=%d ldo=%lld", (long long)n, p, L, (long long)ldo);
+    if (nrows != p && nrows != p + 1)
+        fail(OEMB200_EINVAL, "beta has %d rows; newx has %d columns (expected %d or %d)", nrows, p, p, p + 1);   // R/methods.R:115-116
+    if (type != 0 && type != 1) fail(OEMB200_EINVAL, "type must be 0 (link) or 1 (response)");
+    if (is_device_ptr(beta)) fail(OEMB200_EINVAL, "beta must be a host pointer");
+    Ctx cx(o);
+    PhaseTimers &tm = *cx.tm;
+    const size_t t_total = tm.start(&cx.st.ms_total);
+    CscInput in;
+    in.load(cx, row_idx, col_ptr, values, n, p);
+    DeviceCsr csr;
+    csr.build(cx, in.cp, in.ri, in.v, n, p, in.nnz);
+    const int icpt = nrows - p;
+    std::vector<double> hBt((size_t)p * L), hb0(L, 0.0);
+    for (int c = 0; c < L; ++c) {
+        const double *col = beta + (size_t)c * nrows;
+        if (icpt) hb0[c] = col[0];
+        for (int j = 0; j < p; ++j) hBt[(size_t)j * L + c] = col[icpt + j];
+    }
+    DBuf<double> dBt(hBt.size()), db0(L), dout;
+    dBt.upload(hBt.data(), hBt.size(), cx.stream);
+    db0.upload(hb0.data(), L, cx.stream);
+    const bool out_dev = is_device_ptr(out);
+    double *po = out;
+    int64_t ldp = ldo;
+    if (!out_dev) { dout.alloc((size_t)n * L); po = dout.p; ldp = n; }
+    const size_t t_k = tm.start(&cx.st.ms_cvscore);
+    sparse_predict_kernel<<<4 * cx.num_sms, 256, 0, cx.stream>>>(csr.row_ptr.p, csr.col.p, csr.val.p, (int)n, dBt.p, db0.p, L,
+                                                               type, po, (long long)ldp);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+    tm.stop(t_k);
+    if (!out_dev) {
+        OEM_CUDA(cudaMemcpy2DAsync(out, (size_t)ldo * 8, po, (size_t)n * 8, (size_t)n * 8, L, cudaMemcpyDeviceToHost, cx.stream));
+        cx.st.d2h_bytes += (int64_t)n * L * 8;
+    }
+    tm.stop(t_total);
+    cx.finish();
+    if (stats) *stats = cx.st;
 }
 
 void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
@@ -350,24 +464,11 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
 
     // ---- inputs to the device ----
     const size_t t_h = tm.start(&cx.st.ms_h2d);
-    std::vector<int> h_cp(p + 1);
-    if (is_device_ptr(col_ptr)) {
-        OEM_CUDA(cudaMemcpyAsync(h_cp.data(), col_ptr, sizeof(int) * (p + 1), cudaMemcpyDeviceToHost, cx.stream));
-        cx.sync();
-    } else memcpy(h_cp.data(), col_ptr, sizeof(int) * (p + 1));
-    if (h_cp[0] != 0) fail(OEMB200_EINVAL, "sparse: col_ptr[0] must be 0");
-    for (int j = 0; j < p; ++j)
-        if (h_cp[j + 1] < h_cp[j]) fail(OEMB200_EINVAL, "sparse: col_ptr must be non-decreasing");
-    const int nnz = h_cp[p];
-    if (nnz > 0 && (!row_idx || !values)) fail(OEMB200_EINVAL, "sparse: row_idx / values missing");
-    if (!is_device_ptr(row_idx))
-        for (int e = 0; e < nnz; ++e)
-            if (row_idx[e] < 0 || row_idx[e] >= n) fail(OEMB200_EINVAL, "sparse: row index %d out of range at entry %d", row_idx[e], e);
-    DBuf<int> o_cp, o_ri;
-    DBuf<double> o_v;
-    const int *d_cp = to_device_array(cx, col_ptr, (size_t)p + 1, o_cp);
-    const int *d_ri = to_device_array(cx, row_idx, (size_t)nnz, o_ri);
-    const double *d_v = to_device_array(cx, values, (size_t)nnz, o_v);
+    CscInput in;
+    in.load(cx, row_idx, col_ptr, values, n, p);
+    const int nnz = in.nnz;
+    const int *d_cp = in.cp, *d_ri = in.ri;
+    const double *d_v = in.v;
     DevVector yv;
     to_device_vector(cx, y, n, yv);
     tm.stop(t_h);
@@ -388,21 +489,10 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
 
     // ---- CSC -> CSR ----
     const size_t t_g = tm.start(&cx.st.ms_gram);
-    const int ntile = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
-    DBuf<int> row_ptr((size_t)n + 1), cursor((size_t)n), totals((size_t)ntile), csr_col((size_t)std::max(nnz, 1)),
-        csr_col_u((size_t)std::max(nnz, 1));
-    DBuf<double> csr_val((size_t)std::max(nnz, 1)), csr_val_u((size_t)std::max(nnz, 1));
-    row_ptr.zero(cx.stream);
-    if (nnz > 0) csr_count_kernel<<<(nnz + 255) / 256, 256, 0, cx.stream>>>(d_ri, nnz, row_ptr.p);
-    scan_tiles_kernel<<<ntile, SCAN_THREADS, 0, cx.stream>>>(row_ptr.p, (int)n, totals.p);
-    scan_totals_kernel<<<1, SCAN_THREADS, 0, cx.stream>>>(totals.p, ntile);
-    scan_finish_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, cx.stream>>>(row_ptr.p, (int)n, totals.p, nnz, cursor.p);
-    csr_fill_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, cursor.p, csr_col_u.p, csr_val_u.p);
-    csr_sort_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, cx.stream>>>(row_ptr.p, (int)n, csr_col_u.p, csr_val_u.p, csr_col.p,
-                                                                         csr_val.p);
-    OEM_CUDA(cudaGetLastError());
-    cx.st.kernel_launches += 5 + (nnz > 0 ? 1 : 0);
-
+    DeviceCsr csr;
+    csr.build(cx, d_cp, d_ri, d_v, n, p, nnz);
+    DBuf<int> &row_ptr = csr.row_ptr, &csr_col = csr.col;
+    DBuf<double> &csr_val = csr.val;
     tm.stop(t_g);
 
     // ---- X'X ----

@@ -333,8 +333,6 @@ def predict(fit, newx=None, s=None, which_model=1, type="link", opts=None):
         nz[0, :] = False                                      # "rem intercept" (R/methods.R:95)
         return [np.nonzero(nz[:, j])[0] + 1 if nz[:, j].any() else None for j in range(nz.shape[1])]   # 1-based rows
     binomial = fit.get("family") == "binomial"
-    if _is_sparse(newx):
-        raise NotImplementedError("predict on a sparse newx is not built (no silent densification): pass a dense matrix")
     pred = api.predict_matrix(newx, nbeta, response=(binomial and type == "response"), opts=opts)
     if type == "class":
         if not binomial:

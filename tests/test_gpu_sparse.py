@@ -111,3 +111,23 @@ def test_sparse_frontend_and_errors(lib, oracle):
     a[0] = bad
     with pytest.raises(lib.OemB200Error, match="col_ptr"):
         lib.oem_fit_sparse(*a)
+
+
+def test_sparse_predict(lib):
+    # predict.oem with a sparse newx: as.matrix(newx %*% nbeta) (R/methods.R:113-118) and the binomial response
+    from oem_b200 import api, frontend as fe
+    X, y = sparse_problem(41, 5003, 33, density=0.07, shift_y=1.0, empty_rows=4)
+    rng = np.random.default_rng(5)
+    B = rng.normal(size=(34, 9))
+    want = B[0][None, :] + X @ B[1:]
+    got = api.predict_matrix(X, B)
+    assert got.shape == (5003, 9) and np.max(np.abs(got - want)) <= 1e-12
+    assert np.max(np.abs(api.predict_matrix(X, B[1:]) - X @ B[1:])) <= 1e-12            # p x L (oem.xtx): no intercept row
+    assert np.max(np.abs(api.predict_matrix(X, B, response=True) - 1 / (1 + np.exp(-want)))) <= 1e-14
+    assert np.array_equal(got, api.predict_matrix(X, B))                               # fixed summation order
+    fit = fe.oem(X, y, penalty=["lasso", "mcp"], nlambda=8)
+    pr = fe.predict(fit, newx=X, which_model="mcp", s=[0.03, 0.2])
+    nb = fe.predict(fit, which_model="mcp", s=[0.03, 0.2], type="coefficients")
+    assert np.max(np.abs(pr - (nb[0][None, :] + X @ nb[1:]))) <= 1e-12
+    with pytest.raises(api.OemB200Error, match="columns"):
+        api.predict_matrix(X, B[:-2])
