@@ -359,6 +359,19 @@ static const T *to_device_array(Ctx &cx, const T *h, size_t cnt, DBuf<T> &own) {
     return own.p;
 }
 
+// dgCMatrix invariants: 0 <= i < n, strictly increasing inside every column (no duplicates).  flag: bit 0 = range, bit 1 = order
+__global__ void __launch_bounds__(256) csc_validate_kernel(const int *__restrict__ col_ptr, const int *__restrict__ row_idx, int n,
+                                                           int *__restrict__ flag) {
+    const int j = blockIdx.x;
+    int bad = 0;
+    for (int e = col_ptr[j] + threadIdx.x; e < col_ptr[j + 1]; e += 256) {
+        const int i = row_idx[e];
+        if (i < 0 || i >= n) bad |= 1;
+        if (e > col_ptr[j] && row_idx[e - 1] >= i) bad |= 2;
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
 // validated CSC slots on the device
 struct CscInput {
     DBuf<int> o_cp, o_ri;
@@ -377,13 +390,21 @@ struct CscInput {
             if (h_cp[j + 1] < h_cp[j]) fail(OEMB200_EINVAL, "sparse: col_ptr must be non-decreasing");
         nnz = h_cp[p];
         if (nnz > 0 && (!row_idx || !values)) fail(OEMB200_EINVAL, "sparse: row_idx / values missing");
-        if (!is_device_ptr(row_idx))
-            for (int e = 0; e < nnz; ++e)
-                if (row_idx[e] < 0 || row_idx[e] >= n)
-                    fail(OEMB200_EINVAL, "sparse: row index %d out of range at entry %d", row_idx[e], e);
         cp = to_device_array(cx, col_ptr, (size_t)p + 1, o_cp);
         ri = to_device_array(cx, row_idx, (size_t)nnz, o_ri);
         v = to_device_array(cx, values, (size_t)nnz, o_v);
+        if (nnz > 0) {
+            DBuf<int> flag(1);
+            flag.zero(cx.stream);
+            csc_validate_kernel<<<p, 256, 0, cx.stream>>>(cp, ri, (int)n, flag.p);
+            OEM_CUDA(cudaGetLastError());
+            cx.st.kernel_launches += 1;
+            int h = 0;
+            flag.download(&h, 1, cx.stream);
+            cx.sync();
+            if (h & 1) fail(OEMB200_EINVAL, "sparse: a row index is outside [0, n)");
+            if (h & 2) fail(OEMB200_EINVAL, "sparse: row indices must be strictly increasing inside every column (dgCMatrix invariant)");
+        }
     }
 };
 

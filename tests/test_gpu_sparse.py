@@ -111,6 +111,16 @@ def test_sparse_frontend_and_errors(lib, oracle):
     a[0] = bad
     with pytest.raises(lib.OemB200Error, match="col_ptr"):
         lib.oem_fit_sparse(*a)
+    ri = X.indices.astype(np.int32).copy()
+    ri[5] = 3000                                            # row index == n
+    a[0] = (ri, X.indptr.astype(np.int32), X.data, X.shape)
+    with pytest.raises(lib.OemB200Error, match="outside"):
+        lib.oem_fit_sparse(*a)
+    ri = X.indices.astype(np.int32).copy()
+    ri[1] = ri[0]                                           # duplicate entry inside column 0: not a valid dgCMatrix
+    a[0] = (ri, X.indptr.astype(np.int32), X.data, X.shape)
+    with pytest.raises(lib.OemB200Error, match="strictly increasing"):
+        lib.oem_fit_sparse(*a)
 
 
 def test_sparse_predict(lib):
