@@ -122,6 +122,20 @@ def test_logistic(lib, oracle, hessian):
         assert np.allclose(lg, lr, rtol=1e-9)
 
 
+@pytest.mark.parametrize("n,p,intercept,standardize", [(4000, 40, True, True), (3001, 17, False, True), (6002, 130, True, False)])
+def test_logistic_fused_single_sweep_kernel(lib, oracle, monkeypatch, n, p, intercept, standardize):
+    # OEMB200_LOGIT_FUSED=1: the opt-in IRLS data pass that reads X from HBM once (logit_fused.cu) must give the same
+    # path as the default two sweeps; odd n falls back to the two-sweep route through logit_fused_supported (ld parity)
+    monkeypatch.setenv("OEMB200_LOGIT_FUSED", "1")
+    X, y = binomial_problem(300 + p, n, p)
+    a = args_xy(X, y, "binomial", ["lasso", "mcp"], nlambda=10, lmin_ratio=1e-2, intercept=intercept, standardize=standardize,
+                compute_loss=True)
+    got, ref = lib.oem_fit_logistic_dense(*a), oracle.oem_fit_logistic_dense(*a)
+    assert_same_fit(got, ref, tol=1e-8)
+    for lg, lr in zip(got["loss"], ref["loss"]):
+        assert np.allclose(lg, lr, rtol=1e-9)
+
+
 def test_errors_mirror_reference(lib):
     X, y = gaussian_problem(1, 100, 5)
     a = args_xy(X, y, "binomial", ["lasso"])
