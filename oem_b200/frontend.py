@@ -136,7 +136,7 @@ def getmin(lambda_, cvm, cvsd):
         cv_models[m] = c[idmin].min()
         first = int(np.nonzero(lam == lam_min[m])[0][0])
         semin = (c + s)[first]
-        lam_1se[m] = lam[c < semin].max()
+        lam_1se[m] = lam[c < semin].max() if np.any(c < semin) else -np.inf     # max(numeric(0)) = -Inf in R (cvsd == 0)
     mmin = int(np.argmin(cv_models))
     return dict(lambda_min=float(lam_min[mmin]), model_min=mmin + 1, lambda_1se=float(lam_1se[mmin]),
                 lambda_min_models=lam_min, lambda_1se_models=lam_1se)
@@ -277,6 +277,146 @@ def xval_oem(x, y, nfolds=10, foldid=None, type_measure="mse", ncores=-1, family
     return out
 
 
+def _take_rows(x, keep):
+    """x[keep, , drop = FALSE] for a numpy / scipy.sparse matrix or a (column-major) CUDA tensor."""
+    if hasattr(x, "is_cuda"):
+        import torch
+        idx = torch.from_numpy(np.nonzero(keep)[0]).to(x.device)
+        if x.dim() == 1:
+            return x.index_select(0, idx)
+        return x.t().index_select(1, idx).contiguous().t()          # stays column-major
+    if _is_sparse(x):
+        return x.tocsr()[np.nonzero(keep)[0]].tocsc()
+    x = np.asarray(x)
+    return np.asfortranarray(x[keep]) if x.ndim == 2 else x[keep]
+
+
+def _cvcompute(mat, weights, foldid, nlams):
+    """R/utils.R:126-144 (after glmnet): weighted mean of the raw losses inside every fold."""
+    nfolds = int(foldid.max())
+    outmat = np.full((nfolds, mat.shape[1]), np.nan)
+    good = np.zeros((nfolds, mat.shape[1]))
+    mat = np.where(np.isinf(mat), np.nan, mat)
+    wisum = np.zeros(nfolds)
+    for i in range(nfolds):
+        w = foldid == i + 1
+        wi = weights[w]
+        wisum[i] = wi.sum()
+        mi = mat[w]
+        ok = ~np.isnan(mi)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            outmat[i] = np.where(ok, mi * wi[:, None], 0.0).sum(0) / np.where(ok, wi[:, None], 0.0).sum(0)
+        good[i, :int(nlams[i])] = 1
+    return outmat, wisum, good.sum(0)
+
+
+def cv_oem(x, y, penalty=None, weights=(), lambda_=(), type_measure="default", nfolds=10, foldid=None, grouped=True,
+           keep=False, seed=None, **oem_args):
+    """cv.oem (R/cv_oem.R:58-253): K refits of oem() on the training folds (each with its own lambda sequence), held-out
+    predictions interpolated onto the full fit's lambdas (never extrapolated below a fold's smallest lambda), glmnet-style
+    fold-grouped cvm / cvsd, then getmin().  Every fit and every prediction runs on the device through oem() / predict();
+    xval.oem() computes the same thing from one pass over X and is the fast route (R/oem_xval.R).
+    type.measure: gaussian mse | deviance | mae; binomial deviance | class | mse | mae ('auc' is not mirrored)."""
+    family = oem_args.get("family", "gaussian")
+    if len(lambda_) and all(np.ndim(l) == 0 for l in lambda_) and len(lambda_) < 2:
+        raise ValueError("Need more than one value of lambda for cv.oem")
+    n, _ = (int(x[3][0]), int(x[3][1])) if isinstance(x, tuple) else _shape(x)
+    if len(weights) > 0:
+        raise ValueError("weights not implemented yet.")             # oem() itself rejects them (R/oem.R:244)
+    fit = oem(x, y, penalty=penalty, lambda_=lambda_, **oem_args)
+    pens = fit["penalty"]
+    nz = fit["nzero"]
+    if foldid is None:
+        rng = np.random.default_rng(seed)
+        foldid = rng.permutation(np.resize(np.arange(1, int(nfolds) + 1), n))      # sample(rep(seq(nfolds), length = N))
+    else:
+        foldid = np.asarray(foldid).ravel()
+        nfolds = int(foldid.max())
+    if nfolds < 3:
+        raise ValueError("nfolds must be bigger than 3; nfolds=10 recommended")
+    yh = y.cpu().numpy() if hasattr(y, "is_cuda") else np.asarray(y, dtype=np.float64).ravel()
+    outlist = []
+    for i in range(1, nfolds + 1):
+        tr = foldid != i
+        outlist.append(oem(_take_rows(x, tr), _take_rows(y, tr), penalty=penalty, lambda_=lambda_, **oem_args))
+    lam = fit["lambda"]
+    nmodels = len(pens)
+    which_lam = []
+    for m in range(nmodels):
+        mlami = max(float(np.min(o["lambda"][m])) for o in outlist)                 # do not extrapolate smaller lambdas
+        which_lam.append(np.asarray(lam[m]) >= mlami)
+    nlam0 = len(lam[0])
+    predlist = [np.full((n, nlam0), np.nan) for _ in range(nmodels)]
+    nlams = np.zeros(nfolds)
+    for i in range(1, nfolds + 1):
+        w = foldid == i
+        xt = _take_rows(x, w)
+        for m in range(nmodels):
+            s_use = np.asarray(lam[m])[which_lam[m]]
+            pr = predict(outlist[i - 1], newx=xt, s=s_use, which_model=m + 1,
+                         type="response" if family == "binomial" else "link")
+            predlist[m][w, :s_use.size] = pr
+            nlams[i - 1] = s_use.size
+    if family == "gaussian":
+        tm = "mse" if type_measure in ("default", "deviance") else type_measure
+        if tm not in ("mse", "mae"):
+            raise ValueError("Only 'mse', 'deviance' or 'mae' available for Gaussian models")
+        name = "Mean-Squared Error" if tm == "mse" else "Mean Absolute Error"
+        cvraw = [(yh[:, None] - p_) ** 2 if tm == "mse" else np.abs(yh[:, None] - p_) for p_ in predlist]
+    else:
+        tm = "deviance" if type_measure == "default" else type_measure
+        if tm == "auc":
+            raise NotImplementedError("type.measure = 'auc' is not mirrored; use 'deviance' or 'class'")
+        if tm not in ("mse", "mae", "deviance", "class"):
+            raise ValueError("Only 'deviance', 'class', 'auc', 'mse' or 'mae' available for binomial models")
+        name = {"mse": "Mean-Squared Error", "mae": "Mean Absolute Error", "deviance": "Binomial Deviance",
+                "class": "Misclassification Error"}[tm]
+        y1 = (yh == np.max(yh)).astype(np.float64)                                   # second factor level
+        y0 = 1.0 - y1
+        cvraw = []
+        for p_ in predlist:                                                          # R/cv_oem.R:311-330
+            if tm == "mse":
+                cvraw.append((y0[:, None] - (1 - p_)) ** 2 + (y1[:, None] - p_) ** 2)
+            elif tm == "mae":
+                cvraw.append(np.abs(y0[:, None] - (1 - p_)) + np.abs(y1[:, None] - p_))
+            elif tm == "deviance":
+                pm = np.minimum(np.maximum(p_, 1e-5), 1 - 1e-5)
+                cvraw.append(-2.0 * (y0[:, None] * np.log(1 - pm) + y1[:, None] * np.log(pm)))
+            else:
+                cvraw.append(y0[:, None] * (p_ > 0.5) + y1[:, None] * (p_ <= 0.5))
+    wts = np.ones(n)
+    N = [n - np.isnan(p_).sum(0) for p_ in predlist]
+    if n / nfolds < 3 and grouped:
+        grouped = False
+    cvm, cvsd = [], []
+    for m in range(nmodels):
+        raw, w_m, N_m = cvraw[m], wts, N[m]
+        if grouped:
+            raw, w_m, N_m = _cvcompute(raw, wts, foldid, nlams)
+        ok = ~np.isnan(raw)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            wsum = np.where(ok, w_m[:, None], 0.0).sum(0)
+            mean = np.where(ok, raw * w_m[:, None], 0.0).sum(0) / wsum
+            var = np.where(ok, (raw - mean[None, :]) ** 2 * w_m[:, None], 0.0).sum(0) / wsum
+            cvm.append(mean)
+            cvsd.append(np.sqrt(var / (N_m - 1)))
+    nas = np.zeros(nlam0, dtype=bool)
+    for m in range(nmodels):
+        nas |= np.isnan(cvsd[m])
+    lam_out = [np.asarray(l)[~nas] for l in lam]
+    cvm = [c[~nas] for c in cvm]
+    cvsd = [c[~nas] for c in cvsd]
+    out = dict(lambda_=lam_out, cvm=cvm, cvsd=cvsd, cvup=[a + b for a, b in zip(cvm, cvsd)],
+               cvlo=[a - b for a, b in zip(cvm, cvsd)], nzero=[z[~nas] for z in nz], name=name, oem_fit=fit,
+               penalty=pens, foldid=foldid)
+    out["lambda"] = out.pop("lambda_")
+    if keep:
+        out["fit_preval"] = predlist
+    out.update(getmin(lam_out, cvm, cvsd))
+    out["best_model"] = pens[out["model_min"] - 1]
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # S3 methods the front-ends' users call next (R/methods.R): predict / logLik on the fitted object
 # ------------------------------------------------------------------------------------------
@@ -317,6 +457,18 @@ def predict(fit, newx=None, s=None, which_model=1, type="link", opts=None):
     newx %*% beta runs on the device (api.predict_matrix -> oemb200_predict)."""
     if type not in ("link", "response", "coefficients", "nonzero", "class"):
         raise ValueError("'arg' should be one of 'link', 'response', 'coefficients', 'nonzero', 'class'")
+    if "oem_fit" in fit or "cvm" in fit:
+        # predict.cv.oem / predict.xval.oem (R/methods.R:674-714, 765-806): s defaults to lambda.min, "best.model" allowed
+        if s is None or (isinstance(s, str) and s == "lambda.min"):
+            s = fit["lambda_min"]
+        elif isinstance(s, str):
+            if s != "lambda.1se":
+                raise ValueError("Invalid form for s")
+            s = fit["lambda_1se"]
+        if isinstance(which_model, str) and which_model == "best.model":
+            which_model = fit["model_min"]
+        if "oem_fit" in fit:
+            return predict(fit["oem_fit"], newx=newx, s=s, which_model=which_model, type=type, opts=opts)
     m = _which_model(fit, which_model)
     if newx is None and type not in ("coefficients", "nonzero"):
         raise ValueError("A value for 'newx' must be supplied")
@@ -343,6 +495,8 @@ def predict(fit, newx=None, s=None, which_model=1, type="link", opts=None):
 
 def logLik(fit, which_model=1):
     """logLik.oem (R/methods.R:431-478, after ncvreg): needs compute_loss=True."""
+    if "oem_fit" in fit:                                       # logLik.cv.oem works on the full-data fit
+        return logLik(fit["oem_fit"], which_model)
     m = _which_model(fit, which_model)
     loss = np.asarray(fit["loss"][m], dtype=np.float64)
     if np.all(loss == 1e99):

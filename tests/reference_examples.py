@@ -67,12 +67,26 @@ def example_predict_xval_oem(fe):
     x, y, x_test, y_test = _predict_inputs()
     foldid = 1 + (np.arange(x.shape[0]) % 10)
     fit = fe.xval_oem(x, y, penalty=["lasso", "grp.lasso"], groups=np.repeat(np.arange(1, 11), 10), nlambda=10, foldid=foldid)
-    s = fit["lambda_min"]
-    best = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model=fit["model_min"], s=s))
-    gl = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model="grp.lasso", s=s))
-    la = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model=1, s=s))
+    best = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model="best.model"))    # s = lambda.min
+    gl = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model="grp.lasso"))
+    la = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model=1))
     return {"mse_best": _pair(best, g["mse_best"]), "mse_grp_lasso": _pair(gl, g["mse_grp_lasso"]),
             "mse_lasso": _pair(la, g["mse_lasso"])}
+
+
+def example_predict_cv_oem(fe):
+    """man/predict.cv.oem.Rd -> docs/reference/predict.cv.oem.html, the literal example: cv.oem() (ten refits + held-out
+    predictions) and predict(fit, newx, which.model = "best.model" | "grp.lasso" | 1) at lambda.min.  The reference's
+    folds came from sample(); any balanced assignment that selects the same lambda.min reproduces the printed values."""
+    g = printed()["predict_cv_oem"]
+    x, y, x_test, y_test = _predict_inputs()
+    foldid = 1 + (np.arange(x.shape[0]) % 10)
+    fit = fe.cv_oem(x, y, penalty=["lasso", "grp.lasso"], groups=np.repeat(np.arange(1, 11), 10), nlambda=10, foldid=foldid)
+    best = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model="best.model"))
+    gl = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model="grp.lasso"))
+    la = _mse(y_test, fe.predict(fit, newx=x_test, type="response", which_model=1))
+    return {"mse_best": _pair(best, g["mse_best"]), "mse_grp_lasso": _pair(gl, g["mse_grp_lasso"]),
+            "mse_lasso": _pair(la, g["mse_lasso"])}, fit
 
 
 def example_logLik(fe):

@@ -4,7 +4,7 @@ The reference has no test suite, but its rendered documentation (docs/reference/
 shows what `oem()`, `xval.oem()`, `oem.xtx()` and `big.oem()` returned on seeded inputs (`set.seed(123)`).  oracle/r_rng.py
 regenerates those inputs, tests/reference_examples.py re-runs the examples, and the results must round to the digits
 the reference printed (|got - printed| <= half a unit of the last printed digit): 20 + 5 test-set MSEs of
-predict.oem / predict.cv.oem, 3 of predict.xval.oem, 300 log-likelihoods (compute.loss paths of oem and xval.oem,
+predict.oem / predict.cv.oem (the latter also through the cv.oem mirror itself), 3 of predict.xval.oem, 300 log-likelihoods (compute.loss paths of oem and xval.oem,
 lasso + mcp), the oem <-> oem.xtx identity over twelve penalties and max |big.oem - oem| of the bigmemory example.
 
 CPU leg: the oracle (through the front-end mirrors) against the printed values -- this is what pins the oracle.
@@ -79,6 +79,17 @@ def test_oracle_predict_xval_oem(fe_oracle):
     ex.assert_printed(ex.example_predict_xval_oem(fe_oracle))
 
 
+def test_oracle_predict_cv_oem(fe_oracle):
+    res, fit = ex.example_predict_cv_oem(fe_oracle)
+    ex.assert_printed(res)
+    assert fit["best_model"] == "grp.lasso" and fit["name"] == "Mean-Squared Error"
+    # each fold generates its own lambda sequence; full-fit lambdas below a fold's smallest one are not extrapolated and
+    # drop out as NA (R/cv_oem.R:360-368, 192-206): here the last of the ten
+    assert len(fit["cvm"]) == 2 and fit["cvm"][0].shape == (9,) and fit["lambda"][0].shape == (9,)
+    assert np.all(fit["cvsd"][1] > 0) and np.all(fit["cvup"][0] > fit["cvlo"][0])
+    assert fit["lambda_min"] == fit["lambda"][1][int(np.argmin(fit["cvm"][1]))]
+
+
 def test_oracle_logLik(fe_oracle):
     ex.assert_printed(ex.example_logLik(fe_oracle))
 
@@ -103,6 +114,13 @@ def test_gpu_predict_xval_oem(fe_gpu):
 
 
 @pytest.mark.gpu
+def test_gpu_predict_cv_oem(fe_gpu):
+    res, fit = ex.example_predict_cv_oem(fe_gpu)
+    ex.assert_printed(res)
+    assert fit["best_model"] == "grp.lasso"
+
+
+@pytest.mark.gpu
 def test_gpu_logLik(fe_gpu):
     ex.assert_printed(ex.example_logLik(fe_gpu))
 
@@ -117,3 +135,30 @@ def test_gpu_vignette_bigmat(fe_gpu):
     # the printed value is a DIFFERENCE of two coefficient paths (1.5e-05 to 7 digits, unit 1e-11): one full unit allows
     # for the ~1e-12 summation-order differences between the GPU Gram and the reference's BLAS
     ex.assert_printed(ex.example_vignette_bigmat(fe_gpu), units=1.0)
+
+
+# ------------------------------------------------------------ cv.oem mirror, binomial measures (host logic, oracle behind it)
+def test_cv_oem_binomial_measures(fe_oracle):
+    from cases import binomial_problem
+    X, y = binomial_problem(9, 1500, 8)
+    foldid = 1 + (np.arange(1500) % 5)
+    dev = fe_oracle.cv_oem(X, y, family="binomial", penalty="lasso", nlambda=6, lambda_min_ratio=0.05, foldid=foldid)
+    cls = fe_oracle.cv_oem(X, y, family="binomial", penalty="lasso", nlambda=6, lambda_min_ratio=0.05, foldid=foldid,
+                           type_measure="class")
+    assert dev["name"] == "Binomial Deviance" and cls["name"] == "Misclassification Error"
+    # the first lambda of the full fit is >= every fold's lambda_max up to sampling noise: there the held-out prediction is
+    # (nearly) the training folds' mean of y, so the deviance is the null deviance and the error rate min(ybar, 1 - ybar)
+    null_dev, null_err = [], []
+    for k in range(1, 6):
+        p = y[foldid != k].mean()
+        yk = y[foldid == k]
+        null_dev.append(-2 * np.mean(yk * np.log(p) + (1 - yk) * np.log(1 - p)))
+        null_err.append(np.mean(yk == (p <= 0.5)))
+    assert abs(dev["cvm"][0][0] - np.mean(null_dev)) < 5e-3
+    assert abs(cls["cvm"][0][0] - np.mean(null_err)) < 2e-2
+    assert dev["cvm"][0].min() < dev["cvm"][0][0] and np.all(dev["cvsd"][0] > 0)
+    assert dev["lambda_1se"] >= dev["lambda_min"] and cls["lambda_min"] > 0
+    with pytest.raises(NotImplementedError):
+        fe_oracle.cv_oem(X, y, family="binomial", penalty="lasso", nlambda=6, foldid=foldid, type_measure="auc")
+    with pytest.raises(ValueError, match="nfolds must be bigger than 3"):
+        fe_oracle.cv_oem(X, y, family="binomial", penalty="lasso", nfolds=2)
