@@ -266,6 +266,9 @@ def run_ours(args):
             traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu capture in profiles/gram_traffic.json"
     except Exception:
         pass
+    sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 0.0
+    dmma_limit = 4 * 512 / 16 * sm_count * sm_mhz * 1e6 / 1e12
     line = {"metric": "full lambda-path fit time", "value": ms_step / 1e3, "unit": "s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -280,7 +283,11 @@ def run_ours(args):
                          "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_note,
                          "algorithmic_bytes_per_launch": 8.0 * rows * P,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "algorithmic_flops_per_launch": gram_flops, "ms_per_launch": gram_ms}}
+                         "algorithmic_flops_per_launch": gram_flops, "ms_per_launch": gram_ms,
+                         # second yardstick: one DMMA.8x8x4 (512 flop) per 16 cycles per SM sub-partition
+                         # (tools/micro/fp64_lat.cu) x 4 sub-partitions x SMs x the sampled SM clock
+                         "dmma_issue_limit_tflops": dmma_limit,
+                         "frac_of_dmma_issue_limit": achieved / dmma_limit if dmma_limit else None}}
 
     # ---- e2e: HOST buffers through the same C-ABI call ----
     if not args.no_e2e:
