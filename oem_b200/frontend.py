@@ -316,7 +316,7 @@ def cv_oem(x, y, penalty=None, weights=(), lambda_=(), type_measure="default", n
     predictions interpolated onto the full fit's lambdas (never extrapolated below a fold's smallest lambda), glmnet-style
     fold-grouped cvm / cvsd, then getmin().  Every fit and every prediction runs on the device through oem() / predict();
     xval.oem() computes the same thing from one pass over X and is the fast route (R/oem_xval.R).
-    type.measure: gaussian mse | deviance | mae; binomial deviance | class | mse | mae ('auc' is not mirrored)."""
+    type.measure: gaussian mse | deviance | mae; binomial deviance | class | auc | mse | mae."""
     family = oem_args.get("family", "gaussian")
     if len(lambda_) and all(np.ndim(l) == 0 for l in lambda_) and len(lambda_) < 2:
         raise ValueError("Need more than one value of lambda for cv.oem")
@@ -365,17 +365,30 @@ def cv_oem(x, y, penalty=None, weights=(), lambda_=(), type_measure="default", n
         cvraw = [(yh[:, None] - p_) ** 2 if tm == "mse" else np.abs(yh[:, None] - p_) for p_ in predlist]
     else:
         tm = "deviance" if type_measure == "default" else type_measure
-        if tm == "auc":
-            raise NotImplementedError("type.measure = 'auc' is not mirrored; use 'deviance' or 'class'")
-        if tm not in ("mse", "mae", "deviance", "class"):
+        if tm not in ("mse", "mae", "deviance", "class", "auc"):
             raise ValueError("Only 'deviance', 'class', 'auc', 'mse' or 'mae' available for binomial models")
+        if tm == "auc" and n / nfolds < 10:
+            tm = "deviance"                 # "Too few (< 10) observations per fold for type.measure='auc'" (R/cv_oem.R:276-281)
         name = {"mse": "Mean-Squared Error", "mae": "Mean Absolute Error", "deviance": "Binomial Deviance",
-                "class": "Misclassification Error"}[tm]
+                "class": "Misclassification Error", "auc": "AUC"}[tm]
         y1 = (yh == np.max(yh)).astype(np.float64)                                   # second factor level
         y0 = 1.0 - y1
         cvraw = []
-        for p_ in predlist:                                                          # R/cv_oem.R:311-330
-            if tm == "mse":
+        for p_ in predlist:                                                          # R/cv_oem.R:288-330
+            if tm == "auc":
+                # one AUC per (fold, lambda), R/utils.R:89-124 with unit weights = the rank-sum statistic; tied scores get
+                # half credit here (the reference breaks ties with runif(), R/utils.R:103-104)
+                from scipy.stats import rankdata
+                raw = np.full((nfolds, nlam0), np.nan)
+                for i in range(nfolds):
+                    w = foldid == i + 1
+                    pos = y1[w] == 1
+                    n1, n0 = int(pos.sum()), int((~pos).sum())
+                    for j in range(int(nlams[i])):
+                        r = rankdata(p_[w, j])
+                        raw[i, j] = (r[pos].sum() - n1 * (n1 + 1) / 2.0) / (n1 * n0) if n1 and n0 else np.nan
+                cvraw.append(raw)
+            elif tm == "mse":
                 cvraw.append((y0[:, None] - (1 - p_)) ** 2 + (y1[:, None] - p_) ** 2)
             elif tm == "mae":
                 cvraw.append(np.abs(y0[:, None] - (1 - p_)) + np.abs(y1[:, None] - p_))
@@ -389,9 +402,16 @@ def cv_oem(x, y, penalty=None, weights=(), lambda_=(), type_measure="default", n
     if n / nfolds < 3 and grouped:
         grouped = False
     cvm, cvsd = [], []
+    auc = family != "gaussian" and tm == "auc"
     for m in range(nmodels):
         raw, w_m, N_m = cvraw[m], wts, N[m]
-        if grouped:
+        if auc:                                               # already one row per fold; weights = fold sizes
+            w_m = np.array([float((foldid == i + 1).sum()) for i in range(nfolds)])
+            good = np.zeros((nfolds, nlam0))
+            for i in range(nfolds):
+                good[i, :int(nlams[i])] = 1
+            N_m = good.sum(0)
+        elif grouped:
             raw, w_m, N_m = _cvcompute(raw, wts, foldid, nlams)
         ok = ~np.isnan(raw)
         with np.errstate(invalid="ignore", divide="ignore"):
@@ -412,7 +432,7 @@ def cv_oem(x, y, penalty=None, weights=(), lambda_=(), type_measure="default", n
     out["lambda"] = out.pop("lambda_")
     if keep:
         out["fit_preval"] = predlist
-    out.update(getmin(lam_out, cvm, cvsd))
+    out.update(getmin(lam_out, [-c for c in cvm], cvsd) if auc else getmin(lam_out, cvm, cvsd))      # R/cv_oem.R:246-247
     out["best_model"] = pens[out["model_min"] - 1]
     return out
 

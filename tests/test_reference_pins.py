@@ -158,7 +158,9 @@ def test_cv_oem_binomial_measures(fe_oracle):
     assert abs(cls["cvm"][0][0] - np.mean(null_err)) < 2e-2
     assert dev["cvm"][0].min() < dev["cvm"][0][0] and np.all(dev["cvsd"][0] > 0)
     assert dev["lambda_1se"] >= dev["lambda_min"] and cls["lambda_min"] > 0
-    with pytest.raises(NotImplementedError):
-        fe_oracle.cv_oem(X, y, family="binomial", penalty="lasso", nlambda=6, foldid=foldid, type_measure="auc")
+    auc = fe_oracle.cv_oem(X, y, family="binomial", penalty="lasso", nlambda=6, lambda_min_ratio=0.05, foldid=foldid,
+                           type_measure="auc")
+    assert auc["name"] == "AUC" and abs(auc["cvm"][0][0] - 0.5) < 0.05 and auc["cvm"][0].max() > 0.55
+    assert auc["lambda_min"] == auc["lambda"][0][int(np.argmax(auc["cvm"][0]))]        # AUC is maximised
     with pytest.raises(ValueError, match="nfolds must be bigger than 3"):
         fe_oracle.cv_oem(X, y, family="binomial", penalty="lasso", nfolds=2)
