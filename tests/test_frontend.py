@@ -182,3 +182,26 @@ def test_predict_and_loglik_frontends(lib, oracle):
     eta = Xb @ Bb[1:] + Bb[0:1]
     assert np.allclose(fe.predict(fb, Xb, type="response"), 1 / (1 + np.exp(-eta)), rtol=1e-12)
     assert np.array_equal(fe.predict(fb, Xb, type="class"), np.where(eta > 0, 2, 1))
+
+
+def test_cv_helpers_known_answers():
+    """Host helpers of the cv.oem mirror: row selection for every container kind, glmnet's fold-grouped means."""
+    import scipy.sparse as sps
+    from oem_b200 import frontend as fe
+    X = np.asfortranarray(np.arange(12, dtype=np.float64).reshape(4, 3))
+    keep = np.array([True, False, True, True])
+    d = fe._take_rows(X, keep)
+    assert d.flags["F_CONTIGUOUS"] and np.array_equal(d, X[[0, 2, 3]])
+    s = fe._take_rows(sps.csc_matrix(X), keep)
+    assert sps.issparse(s) and s.format == "csc" and np.array_equal(s.toarray(), X[[0, 2, 3]])
+    assert np.array_equal(fe._take_rows(np.array([1.0, 2.0, 3.0, 4.0]), keep), [1.0, 3.0, 4.0])
+    # cvcompute (R/utils.R:126-144): per-fold weighted means, NA-aware; N counts the folds that reach each lambda
+    mat = np.array([[1.0, 2.0], [3.0, np.nan], [5.0, 6.0], [7.0, np.inf]])
+    foldid = np.array([1, 1, 2, 2])
+    out, wsum, N = fe._cvcompute(mat, np.array([1.0, 3.0, 1.0, 1.0]), foldid, np.array([2, 1]))
+    assert np.allclose(out, [[(1 + 9) / 4.0, 2.0], [6.0, 6.0]]) and wsum.tolist() == [4.0, 2.0] and N.tolist() == [2.0, 1.0]
+    # lambda.interp (R/utils.R:64-87): exact at grid points, linear in between, clamped outside
+    lam = np.array([1.0, 0.5, 0.25])
+    l, r, f = fe.lambda_interp(lam, [0.5, 0.75, 2.0, 0.1])
+    assert l.tolist() == [1, 0, 0, 2] and r.tolist() == [1, 1, 0, 2]
+    assert np.allclose(f, [1.0, 0.5, 1.0, 1.0])
