@@ -125,3 +125,18 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "sm_100a" in out.stdout
+
+
+def test_r_shim_matches_the_c_abi():
+    """integration/r_shim/oem_b200_shim.cpp is the reference-side binding.  R / Rcpp are not in this image,
+    so it is syntax-checked against stand-in headers (tests/stubs): every oemb200_* call in it must match the prototypes
+    of include/oem_b200.h, and it must define each .Call symbol the R code of the reference looks up for this path."""
+    shim = os.path.join(ROOT, "integration", "r_shim", "oem_b200_shim.cpp")
+    out = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-Werror", "-DOEM_B200_WITH_BIGMEMORY",
+                          "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"), shim],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    src = open(shim).read()
+    for sym in ("oem_fit_dense", "oem_fit_logistic_dense", "oem_fit_sparse", "oem_fit_big", "oem_fit_fb_big", "oem_xtx",
+                "oem_xval_dense"):
+        assert re.search(rf"RcppExport SEXP {sym}\(", src), sym
