@@ -104,6 +104,18 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle on a bounded sample
 # ----------------------------------------------------------------------------------------------
+def cpu_fit_time_one_thread(rows_full, sample_rows, seed=1234):
+    """The same port with BLAS limited to ONE thread (the reference's default is ncores = 1, R/oem.R:191): one untimed and
+    one timed fit on a quarter of the all-cores sample, extrapolated like cpu_fit_time.  None if threadpoolctl is missing."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:
+        return None
+    with threadpool_limits(limits=1):
+        sec, info = cpu_fit_time(rows_full, max(20_000, sample_rows // 4), 1, 1, seed)
+    return {"value": sec, "unit": "s", "cores": 1, "sample_rows": info["sample_rows"]}
+
+
 def cpu_fit_time(rows_full, sample_rows, steps, warmup, seed=1234):
     """Times oracle.oem_fit_big (numpy/OpenBLAS X'X + column sweeps, plain-C OEM iterations) on
     `sample_rows` rows with all host threads.  The O(n) data passes are timed again on their own and
@@ -301,6 +313,12 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": sec, "unit": "s", "cores": info["cores"], "kind": "port",
                                 "sample": f"oracle.oem_fit_big on {info['sample_rows']} x {P} rows; data passes scaled "
                                           f"x{rows / info['sample_rows']:.0f} to n={rows:.3g}, path phase unscaled"}
+        try:
+            one = cpu_fit_time_one_thread(rows, args.cpu_sample_rows)
+        except Exception as e:                              # a reported extra, never a reason to lose the line
+            one = {"error": repr(e)}
+        if one:
+            line["cpu_baseline"]["one_thread"] = one        # the reference's default ncores = 1
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
