@@ -24,6 +24,17 @@ def shard_rows(n, rank, world, align=72):
     return r0, r1
 
 
+def shard_csc_rows(x, rank, world, align=72):
+    """Row block of `rank` of a sparse design as its own dgCMatrix (scipy CSC with sorted indices), the input
+    oem_fit_sparse expects on every rank of a row-sharded run; same blocks as shard_rows."""
+    import scipy.sparse as sps
+    r0, r1 = shard_rows(x.shape[0], rank, world, align)
+    blk = sps.csc_matrix(sps.csr_matrix(x)[r0:r1])
+    blk.sum_duplicates()
+    blk.sort_indices()
+    return blk, r0, r1
+
+
 class Comm:
     """All-reduce callback over torch.distributed (NCCL for CUDA buffers, gloo for host buffers)."""
 

@@ -19,7 +19,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     import oem_b200
-    from oem_b200.dist import Comm, shard_rows
+    from oem_b200.dist import Comm, shard_csc_rows, shard_rows
     from oracle import oracle as orc
     comm = Comm()
 
@@ -71,9 +71,9 @@ def main():
     Xs, ysp = sparse_problem(106, 8000, 50, density=0.06, shift_y=1.0)
     a = args_xy(Xs, ysp, "gaussian", ["lasso", "mcp"], nlambda=15, compute_loss=True)
     ref = orc.oem_fit_sparse(*a) if rank == 0 else None
-    r0, r1 = shard_rows(8000, rank, world)
+    blk, r0, r1 = shard_csc_rows(Xs, rank, world)
     sa = list(a)
-    sa[0], sa[1] = Xs[r0:r1].tocsc(), ysp[r0:r1]
+    sa[0], sa[1] = blk, ysp[r0:r1]
     got_s = oem_b200.oem_fit_sparse(*sa, comm=comm)
     if rank == 0:
         assert_same_fit(got_s, ref)

@@ -81,3 +81,23 @@ def test_shard_rows_cover_and_align():
             assert a1 == b0 and a1 > a0
         if n // world >= 72:
             assert all(b[0] % 72 == 0 for b in blocks)
+
+
+def test_shard_csc_rows_partition_the_statistics():
+    """Sparse row blocks: the per-rank dgCMatrix pieces tile the matrix and their sufficient statistics add up to the
+    whole -- what the single all-reduce of oem_fit_sparse's bundle relies on."""
+    import scipy.sparse as sps
+    from cases import sparse_problem
+    from oem_b200.dist import shard_csc_rows
+    X, y = sparse_problem(8, 1003, 11, density=0.2)
+    G, xty, nnz, rows = np.zeros((11, 11)), np.zeros(11), 0, 0
+    for rank in range(3):
+        blk, r0, r1 = shard_csc_rows(X, rank, 3)
+        assert sps.isspmatrix_csc(blk) and blk.has_sorted_indices and blk.shape == (r1 - r0, 11)
+        assert np.array_equal(blk.toarray(), X.toarray()[r0:r1])
+        G += (blk.T @ blk).toarray()
+        xty += blk.T @ y[r0:r1]
+        nnz += blk.nnz
+        rows += r1 - r0
+    assert rows == 1003 and nnz == X.nnz
+    assert np.allclose(G, (X.T @ X).toarray(), rtol=1e-13, atol=1e-13) and np.allclose(xty, X.T @ y, rtol=1e-13)
