@@ -73,6 +73,7 @@ typedef struct oemb200_opts {
     oemb200_allreduce_fn allreduce;  /* row-sharded multi-process runs; NULL = single process */
     void  *allreduce_ctx;
     int    rank, world;    /* informational (world<=1: single process) */
+    struct oemb200_comm *comm;       /* in-library communicator (oemb200_comm_create); takes precedence over `allreduce` */
 } oemb200_opts;
 
 /* Arguments shared by all entries, in the reference's .Call order (family .. compute_loss). */
@@ -108,6 +109,13 @@ typedef struct oemb200_stats {
     int64_t total_oem_iters;  /* sum of niter over all chains */
     int64_t lanczos_steps;
     int64_t h2d_bytes, d2h_bytes;
+    /* appended in 0.2 */
+    int64_t allreduce_calls;    /* sum all-reduces issued inside the call (0 in single-process runs) */
+    int64_t allreduce_doubles;  /* FP64 values they carried */
+    int64_t data_passes;        /* logistic: IRLS data passes over X (fused sigma(X beta) / X'r sweeps) */
+    int64_t host_syncs;         /* stream synchronisations the host driver performed inside the call */
+    double  ms_relayout;        /* logistic: one-time row-slab re-layout of X */
+    double  ms_ingest_wait;     /* oem_fit_big from host memory: time the compute stream waited for staged chunks */
 } oemb200_stats;
 
 /*
@@ -122,6 +130,33 @@ typedef struct oemb200_result {
     double *cvm;  double *cvsd;   int *nlam_out;
     oemb200_stats *stats;          /* may be NULL */
 } oemb200_result;
+
+/*
+ * In-library communicator for row-sharded runs (one process per GPU).  The sum all-reduces of the path -- the packed
+ * sufficient statistics once per fit, the (p+1)-vector X'(y - prob) once per IRLS iteration of the logistic entry
+ * (src/oem_logistic_dense.h:970-1000 is the single-process sum it replaces) -- are then issued by the library itself on
+ * its own CUDA stream: ncclAllReduce from the libnccl.so.2 already loaded in the process (else the system one; the
+ * library is dlopen()ed, never linked), or, for vectors up to OEMB200_P2P_MAX_DOUBLES on one NVLink / NVSwitch node, a
+ * one-shot peer-memory kernel (every rank stores its vector into every peer's mailbox over NVLink and sums the
+ * mailboxes in rank order, so all ranks hold bit-identical results).  No host callback, no host synchronisation.
+ *
+ *   rank 0:     oemb200_comm_unique_id(id)           -> broadcast the 128 bytes by any host channel
+ *   every rank: oemb200_comm_create(id, rank, world, device, &comm);   opts.comm = comm;   ...fits...
+ *               oemb200_comm_destroy(comm)
+ * An R / C++ host that already owns an ncclComm_t wraps it with oemb200_comm_from_nccl (not owned, not destroyed).
+ */
+#define OEMB200_COMM_ID_BYTES 128
+#define OEMB200_P2P_MAX_DOUBLES 8192
+typedef struct oemb200_comm oemb200_comm;
+int  oemb200_comm_unique_id(void *id_out);
+int  oemb200_comm_create(const void *id, int rank, int world, int device, oemb200_comm **out);
+int  oemb200_comm_from_nccl(void *nccl_comm, int rank, int world, int device, oemb200_comm **out);
+int  oemb200_comm_destroy(oemb200_comm *c);
+/* in-place sum all-reduce of `count` device doubles on `stream` (what the entries call internally); *us_out (optional)
+ * = device time of the collective in microseconds (forces a stream synchronisation: measurement only) */
+int  oemb200_comm_allreduce(oemb200_comm *c, double *dev_buf, int64_t count, void *stream, double *us_out);
+/* 1 if the one-shot NVLink peer-memory path is active for this communicator (all ranks on one node with P2P access) */
+int  oemb200_comm_p2p_enabled(const oemb200_comm *c);
 
 const char *oemb200_last_error(void);
 const char *oemb200_version(void);
@@ -204,6 +239,16 @@ int oemb200_colstats(const double *x_dev, int64_t n, int p, int64_t ldx,
 int oemb200_xb_logistic(const double *x_dev, int64_t n, int p, int64_t ldx, const double *b_dev,
                         double b0, const double *y_dev, double *prob_dev, double *resid_dev,
                         double *w_dev, void *stream, double *ms_out);
+
+/* One fused IRLS data pass of the logistic entry on a row-slab copy of x (csrc/logit_slab.cu): X is read from HBM
+ * once, grad_dev[0] = sum_i (y_i - prob_i), grad_dev[1 + j] = sum_i x_ij (y_i - prob_i); prob_dev / w_dev as in
+ * oemb200_xb_logistic (either may be NULL).  The slab copy is built inside the call (time reported separately in
+ * *ms_relayout_out); the pass is run `reps` times and *ms_out is the CUDA-event average of one pass.  Returns
+ * OEMB200_EUNSUPPORTED for p outside the slab kernel's range (128..2048).
+ * src/oem_logistic_dense.h:864-949 + 970-992 in one sweep. */
+int oemb200_logit_slab_pass(const double *x_dev, int64_t n, int p, int64_t ldx, const double *b_dev, double b0,
+                            const double *y_dev, double *prob_dev, double *w_dev, double *grad_dev, int reps,
+                            void *stream, double *ms_out, double *ms_relayout_out);
 
 /* Largest eigenvalue of the symmetric q x q matrix (device, col-major) by on-device Lanczos.
  * Stands in for Spectra::SymEigsSolver at src/oem_dense.h:485-498. */

@@ -36,7 +36,7 @@ class Opts(ctypes.Structure):
                 ("irls_tol", ctypes.c_double), ("ncores", ctypes.c_int), ("hessian_full", ctypes.c_int),
                 ("accelerate", ctypes.c_int), ("gigs", ctypes.c_double), ("device", ctypes.c_int),
                 ("stream", ctypes.c_void_p), ("allreduce", ALLREDUCE_FN), ("allreduce_ctx", ctypes.c_void_p),
-                ("rank", ctypes.c_int), ("world", ctypes.c_int)]
+                ("rank", ctypes.c_int), ("world", ctypes.c_int), ("comm", ctypes.c_void_p)]
 
 
 class Spec(ctypes.Structure):
@@ -59,7 +59,9 @@ class Stats(ctypes.Structure):
                  "ms_cvscore", "ms_irls_xb", "ms_irls_xtr", "ms_total", "gram_flops", "gemv_bytes")] + \
                [(k, ctypes.c_int64) for k in
                 ("kernel_launches", "gram_launches", "xb_launches", "xtr_launches", "total_oem_iters",
-                 "lanczos_steps", "h2d_bytes", "d2h_bytes")]
+                 "lanczos_steps", "h2d_bytes", "d2h_bytes", "allreduce_calls", "allreduce_doubles", "data_passes",
+                 "host_syncs")] + \
+               [(k, ctypes.c_double) for k in ("ms_relayout", "ms_ingest_wait")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -102,6 +104,14 @@ def load():
     L.oemb200_colstats.argtypes = [vp, i64, ci, i64, vp, vp, vp, vp, ctypes.POINTER(dbl)]
     L.oemb200_xb_logistic.argtypes = [vp, i64, ci, i64, vp, dbl, vp, vp, vp, vp, vp, ctypes.POINTER(dbl)]
     L.oemb200_top_eig.argtypes = [vp, ci, ctypes.POINTER(dbl), ctypes.POINTER(ci), vp]
+    L.oemb200_logit_slab_pass.argtypes = [vp, i64, ci, i64, vp, dbl, vp, vp, vp, vp, ci, vp, ctypes.POINTER(dbl),
+                                          ctypes.POINTER(dbl)]
+    L.oemb200_comm_unique_id.argtypes = [vp]
+    L.oemb200_comm_create.argtypes = [vp, ci, ci, ci, ctypes.POINTER(vp)]
+    L.oemb200_comm_from_nccl.argtypes = [vp, ci, ci, ci, ctypes.POINTER(vp)]
+    L.oemb200_comm_destroy.argtypes = [vp]
+    L.oemb200_comm_allreduce.argtypes = [vp, vp, i64, vp, ctypes.POINTER(dbl)]
+    L.oemb200_comm_p2p_enabled.argtypes = [vp]
     L.oemb200_lambda_grid.argtypes = [dbl, ci, dbl, vp]
     L.oemb200_stop_rule.argtypes = [vp, vp, ci, dbl]
     L.oemb200_release_cache.restype = None
@@ -115,7 +125,9 @@ EXPORTS = ["oemb200_last_error", "oemb200_version", "oemb200_device_count", "oem
            "oemb200_penalty_id", "oemb200_nlambda_max", "oemb200_fit_dense", "oemb200_xtx", "oemb200_xval_dense",
            "oemb200_fit_logistic_dense", "oemb200_fit_big", "oemb200_fit_sparse", "oemb200_gram", "oemb200_colstats",
            "oemb200_xb_logistic", "oemb200_top_eig", "oemb200_lambda_grid", "oemb200_stop_rule",
-           "oemb200_release_cache", "oemb200_predict", "oemb200_predict_sparse"]
+           "oemb200_release_cache", "oemb200_predict", "oemb200_predict_sparse", "oemb200_logit_slab_pass",
+           "oemb200_comm_unique_id", "oemb200_comm_create", "oemb200_comm_from_nccl", "oemb200_comm_destroy",
+           "oemb200_comm_allreduce", "oemb200_comm_p2p_enabled"]
 
 
 def lambda_grid(lmax, nlambda, lmin_ratio):
@@ -207,7 +219,10 @@ def make_opts(opts=None, comm=None):
         else:
             raise ValueError(f"unknown option {k}")
     if comm is not None and comm.world > 1:
-        o.allreduce = comm.callback
+        if getattr(comm, "handle", None):           # oem_b200.dist.LibComm: the library all-reduces by itself
+            o.comm = comm.handle
+        else:                                       # oem_b200.dist.Comm: host callback (torch.distributed)
+            o.allreduce = comm.callback
         o.rank, o.world = comm.rank, comm.world
     return o
 

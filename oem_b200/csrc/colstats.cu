@@ -185,8 +185,9 @@ template <bool VEC2, bool LOGISTIC>
 __global__ void __launch_bounds__(XB_THREADS)
 xb_kernel(const double *__restrict__ X, long long n, int p, long long ld, const double *__restrict__ b, double b0,
           const double *__restrict__ y, double *__restrict__ eta, double *__restrict__ prob,
-          double *__restrict__ resid, double *__restrict__ w) {
+          double *__restrict__ resid, double *__restrict__ w, const double *__restrict__ b0_dev) {
     extern __shared__ double bs[];
+    if (b0_dev) b0 += *b0_dev;
     for (int j = threadIdx.x; j < p; j += XB_THREADS) bs[j] = b[j];
     __syncthreads();
     const long long r = ((long long)blockIdx.x * XB_THREADS + threadIdx.x) * 2;
@@ -238,11 +239,11 @@ xb_kernel(const double *__restrict__ X, long long n, int p, long long ld, const 
 }
 
 void xb_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const double *b, double b0, const double *y,
-               double *eta, double *prob, double *resid, double *w, bool logistic) {
+               double *eta, double *prob, double *resid, double *w, bool logistic, const double *b0_dev) {
     const bool vec2 = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     const unsigned grid = (unsigned)((n + 2 * XB_THREADS - 1) / (2 * XB_THREADS));
     const size_t sm = (size_t)p * 8;
-#define OEM_XB(V, L) xb_kernel<V, L><<<grid, XB_THREADS, sm, cx.stream>>>(X, n, p, ld, b, b0, y, eta, prob, resid, w)
+#define OEM_XB(V, L) xb_kernel<V, L><<<grid, XB_THREADS, sm, cx.stream>>>(X, n, p, ld, b, b0, y, eta, prob, resid, w, b0_dev)
     if (vec2 && logistic) OEM_XB(true, true);
     else if (vec2) OEM_XB(true, false);
     else if (logistic) OEM_XB(false, true);

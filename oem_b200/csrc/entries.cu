@@ -409,7 +409,7 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
         out3.download(h3.data(), h3.size(), cx.stream);
         cx.sync();
         for (int c = 0; c < nc; ++c) tot[c] = h3[c] * h3[nc + c];          // count * mean = sum
-        if (cx.allreduce) {
+        if (cx.distributed()) {
             DBuf<double> dt(nc);
             dt.upload(tot.data(), nc, cx.stream);
             cx.all_reduce(dt.p, nc);
@@ -670,6 +670,30 @@ int oemb200_xb_logistic(const double *x_dev, int64_t n, int p, int64_t ldx, cons
                         double *ms_out) {
     return guarded([&] {
         OEM_PHASE_TIMED(xb_launch(cx, x_dev, n, p, ldx, b_dev, b0, y_dev, nullptr, prob_dev, resid_dev, w_dev, true));
+    });
+}
+int oemb200_logit_slab_pass(const double *x_dev, int64_t n, int p, int64_t ldx, const double *b_dev, double b0,
+                            const double *y_dev, double *prob_dev, double *w_dev, double *grad_dev, int reps, void *stream,
+                            double *ms_out, double *ms_relayout_out) {
+    return guarded([&] {
+        if (!x_dev || !b_dev || !y_dev || !grad_dev || n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "logit_slab_pass: bad arguments");
+        if (!logit_slab_rows(p)) fail(OEMB200_EUNSUPPORTED, "the slab kernel covers 128 <= p <= 2048 (p = %d)", p);
+        oemb200_opts o_; phase_ctx_opts(o_, stream);
+        Ctx cx(&o_);
+        cudaEvent_t e0, e1, e2;
+        OEM_CUDA(cudaEventCreate(&e0)); OEM_CUDA(cudaEventCreate(&e1)); OEM_CUDA(cudaEventCreate(&e2));
+        DBuf<double> slabs(logit_slab_doubles(n, p)), d_b0(1);
+        OEM_CUDA(cudaMemcpyAsync(d_b0.p, &b0, 8, cudaMemcpyHostToDevice, cx.stream));
+        OEM_CUDA(cudaEventRecord(e0, cx.stream));
+        logit_slab_relayout(cx, x_dev, n, p, ldx, slabs.p);
+        OEM_CUDA(cudaEventRecord(e1, cx.stream));
+        const int nrep = reps < 1 ? 1 : reps;
+        for (int r = 0; r < nrep; ++r) logit_slab_launch(cx, slabs.p, n, p, b_dev, d_b0.p, y_dev, prob_dev, w_dev, grad_dev);
+        OEM_CUDA(cudaEventRecord(e2, cx.stream));
+        cx.sync();
+        if (ms_relayout_out) *ms_relayout_out = elapsed_ms(e0, e1);
+        if (ms_out) *ms_out = elapsed_ms(e1, e2) / nrep;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     });
 }
 int oemb200_top_eig(const double *xx_dev, int q, double *lambda_max_out, int *steps_out, void *stream) {

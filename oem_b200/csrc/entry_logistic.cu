@@ -1,14 +1,19 @@
 // entry_logistic.cu -- host driver of oem_fit_logistic_dense (src/oem_logistic_dense.cpp:29-313,
 // solver src/oem_logistic_dense.h:721-1036) on the sm_100a kernels.
 //
-// Per IRLS iteration the data passes are the two HBM-bound sweeps the reference performs:
-//   prob = sigma(X (beta o w) + beta0)        -> xb_kernel        (oem_logistic_dense.h:864-949)
-//   grad = [sum(y-prob), X'(y-prob) o w] / n  -> colstats_kernel  (oem_logistic_dense.h:970-992)
-// plus, when the Hessian bound is (re)built, X'WX on the FP64 tensor pipe with the row weight fused
-// into the fragment load (gram_syrk_kernel<WEIGHT>) and the Lanczos eigenvalue inside the path kernel.
-// Row-sharded runs all-reduce the (p+1)-vector gradient and the Hessian bundle.
-// The reference's quirks are kept: the data pass is skipped on the
-// first IRLS iteration of a warm lambda, W is clamped at index = IRLS counter, eigen factor 1.0005.
+// Per IRLS iteration the reference makes two passes over X:
+//   prob = sigma(X (beta o w) + beta0)        (oem_logistic_dense.h:864-949)
+//   grad = [sum(y-prob), X'(y-prob) o w] / n  (oem_logistic_dense.h:970-992)
+// Here both come out of ONE sweep of a row-slab copy of X (logit_slab.cu; built once per fit), or, for shapes the
+// slab kernel does not cover, out of the two HBM-bound sweeps xb_kernel + colstats_kernel.  When the Hessian bound is
+// (re)built, X'WX runs on the FP64 tensor pipe with the row weight fused into the fragment load
+// (gram_syrk_kernel<WEIGHT>) and the Lanczos eigenvalue inside the path kernel.
+//
+// The IRLS state never leaves the device: the iterate, the gradient, XY = XX beta + grad and the inner OEM loop are
+// chained kernels on one stream; row-sharded runs sum the (p+1)-vector gradient in stream order (comm.cu); the only
+// host round trip per IRLS iteration is ONE stream synchronisation that reads the stop-rule flag from pinned memory.
+// The reference's quirks are kept: the data pass is skipped on the first IRLS
+// iteration of a warm lambda, W is clamped at index = IRLS counter, eigen factor 1.0005.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -42,6 +47,80 @@ __global__ void logistic_loss_kernel(const double *__restrict__ y, const double 
     }
 }
 
+// b = beta[icpt:] o colsq_inv, b0 = beta[0]: the coefficients the data pass multiplies raw X with (:875-890)
+__global__ void irls_coef_kernel(const double *__restrict__ beta, const double *__restrict__ cinv, int p, int icpt,
+                                 double *__restrict__ b, double *__restrict__ b0) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < p) b[j] = cinv ? beta[icpt + j] * cinv[j] : beta[icpt + j];
+    if (j == 0) *b0 = icpt ? beta[0] : 0.0;
+}
+
+// two-sweep route: [X'r (p) | . | . | sum r, .] of colstats / vecsum -> the (p+1)-vector [sum r, X'r] the slab kernel emits
+__global__ void irls_pack_grad_kernel(const double *__restrict__ stats, int p, double *__restrict__ g) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < p) g[1 + j] = stats[j];
+    if (j == 0) g[0] = stats[3 * (size_t)p];
+}
+
+// XY = XX beta + grad with grad = [g0 / n, (g_j / n) o colsq_inv] (oem_logistic_dense.h:970-999).  One warp per row.
+__global__ void irls_xy_kernel(int q, int icpt, const double *__restrict__ XX, const double *__restrict__ beta,
+                               const double *__restrict__ g, const double *__restrict__ cinv, double n_tot,
+                               double *__restrict__ XY) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= q) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int c = lane; c < q; c += 32) s = fma(XX[(size_t)r * q + c], beta[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        double gr;
+        if (icpt && r == 0) gr = g[0] / n_tot;
+        else {
+            const int j = r - icpt;
+            gr = g[1 + j] / n_tot;
+            if (cinv) gr *= cinv[j];
+        }
+        XY[r] = s + gr;
+    }
+}
+
+// stopRule(beta_new, beta_prev, irls_tol) (src/utils.cpp:537-549) on the device; the verdict goes to pinned host
+// memory, the inner loop's iteration count is accumulated for the statistics.  One CTA.
+__global__ void irls_stop_kernel(const double *__restrict__ cur, const double *__restrict__ prev, int q, double tol,
+                                 const int *__restrict__ niter, long long *__restrict__ iters_total,
+                                 volatile int *__restrict__ host_flag) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    int v = 0;
+    for (int i = threadIdx.x; i < q; i += blockDim.x) {
+        const double ac = fabs(cur[i]), ap = fabs(prev[i]);
+        if ((ac > 1e-13 && ap <= 1e-13) || (ac <= 1e-13 && ap > 1e-13)) v = 1;
+        else if (ac > 1e-13 && ap > 1e-13 && fabs((cur[i] - prev[i]) / prev[i]) > tol) v = 1;
+    }
+    if (v) bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *iters_total += niter[0];
+        *host_flag = bad ? 0 : 1;
+        __threadfence_system();
+    }
+}
+
+namespace {
+struct PinnedFlag {
+    int *p = nullptr;
+    PinnedFlag() { OEM_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&p), 64, cudaHostAllocMapped)); *p = 0; }
+    ~PinnedFlag() { if (p) cudaFreeHost(p); }
+};
+struct ScratchHolder {
+    PathScratch *s;
+    ScratchHolder() : s(path_scratch_create()) {}
+    ~ScratchHolder() { path_scratch_destroy(s); }
+};
+}  // namespace
+
 void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s,
                   const oemb200_opts *o, oemb200_result *res) {
     check_common(s, o, res, "binomial");
@@ -71,7 +150,11 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     tm.stop(t_c);
     const double nd = (double)n;
     OEM_CUDA(cudaMemcpyAsync(nobs, &nd, 8, cudaMemcpyHostToDevice, cx.stream));
-    cx.all_reduce(b0.p, (int64_t)nb0);
+    {
+        const size_t t_ar = tm.start(&cx.st.ms_allreduce);
+        cx.all_reduce(b0.p, (int64_t)nb0);
+        tm.stop(t_ar);
+    }
     std::vector<double> h0(nb0);
     b0.download(h0.data(), nb0, cx.stream);
     cx.sync();
@@ -92,15 +175,48 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     for (int j = 0; j < p; ++j) lmax = std::max(lmax, std::fabs(XY0[icpt + j]));
     su.build_lambdas(s, lmax, /*logistic_fudge=*/true);
 
+    // ---- data-pass route.  Every route ends in the same (p+1)-vector all-reduce, so ranks may differ in their choice.
+    //      slab (default where it applies): X re-laid out once, one HBM sweep per pass (logit_slab.cu)
+    //      sweeps: xb_kernel + colstats_kernel, two HBM sweeps per pass (small / very wide p, or no room for the copy)
+    const char *route_env = getenv("OEMB200_LOGIT_ROUTE");
+    bool slab = logit_slab_rows(p) != 0 && !(route_env && strcmp(route_env, "sweeps") == 0);
+    DBuf<double> slabs;
+    if (slab) {
+        size_t free_b = 0, total_b = 0;
+        OEM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = logit_slab_doubles(n, p) * 8;
+        if (need + 3 * (size_t)(n + 2) * 8 + (1ull << 30) > free_b) slab = false;      // no room for the second copy of X
+    }
+    if (slab) {
+        const size_t t_r = tm.start(&cx.st.ms_relayout);
+        slabs.alloc(logit_slab_doubles(n, p));
+        logit_slab_relayout(cx, X.p, n, p, X.ld, slabs.p);
+        tm.stop(t_r);
+    }
+
     // ---- device state ----
     std::vector<double> pf(q, 0.0);
     for (int j = 0; j < p; ++j) pf[icpt + j] = s->penalty_factor[j];
-    DBuf<double> d_pf(q), d_b(p), d_beta(q), d_grad(q), d_XY(q), d_XX((size_t)q * q), d_d(1), d_lam(1);
-    DBuf<double> d_prob(n + (n & 1)), d_res(n + (n & 1)), d_W(n + (n & 1));
-    DBuf<double> d_beta_out(q), d_beta_final(q);
+    const int L = su.Lmax;
+    DBuf<double> d_pf(q), d_cinv(p), d_b(p), d_b0(2), d_g((size_t)p + 2), d_XY(q), d_XX((size_t)q * q), d_d(1);
+    DBuf<double> d_iter(2 * (size_t)q), d_path((size_t)su.P * L * q), d_lams((size_t)su.P * L);
+    DBuf<double> d_prob(n + (n & 1)), d_res, d_W(n + (n & 1));
+    DBuf<long long> d_iters_total(1);
     DBuf<int> d_niter(1), d_lz(1);
+    if (!slab) d_res.alloc(n + (n & 1));
     d_prob.zero(cx.stream);
+    d_W.zero(cx.stream);
+    d_iters_total.zero(cx.stream);
+    d_path.zero(cx.stream);
     d_pf.upload(pf.data(), q, cx.stream);
+    d_cinv.upload(cinv.data(), p, cx.stream);
+    {
+        std::vector<double> lam_flat((size_t)su.P * L, 0.0);
+        for (int pp = 0; pp < su.P; ++pp)
+            for (size_t i = 0; i < su.lam[pp].size() && (int)i < L; ++i) lam_flat[(size_t)pp * L + i] = su.lam[pp][i];
+        d_lams.upload(lam_flat.data(), lam_flat.size(), cx.stream);
+        cx.sync();                                  // lam_flat is a host temporary
+    }
     DBuf<int> g_unique, g_ptr, g_idx, g_cover;
     DBuf<double> g_w;
     if (su.any_group) {
@@ -115,49 +231,47 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     const size_t nbh = (size_t)p * p + 3 * (size_t)p + 2;
     DBuf<double> bh(nbh), d_nobs(1);
     d_nobs.upload(&n_tot, 1, cx.stream);
-    DBuf<double> gradb(3 * (size_t)p + 2);   // [stats 3p | sum r, sum r^2]
-    DBuf<double> d_losspart(1024), gfused((size_t)p + 1);
-    // Default: two HBM-bound sweeps (xb_kernel + colstats_kernel), each at ~100 % of the measured HBM bandwidth.
-    // OEMB200_LOGIT_FUSED=1 selects the single-HBM-sweep kernel (logit_fused.cu): it reads X from HBM once but
-    // streams it over the L2 fabric twice and is bound there (measured 4.2 ms vs 4.65 ms per pass at config 4).
-    const bool fused = getenv("OEMB200_LOGIT_FUSED") != nullptr && logit_fused_supported(X.p, n, p, X.ld);
+    DBuf<double> gradb(3 * (size_t)p + 2);   // two-sweep route: [stats 3p | sum r, sum r^2]
+    DBuf<double> d_losspart(1024);
+    PinnedFlag flag;
+    ScratchHolder scratch;
 
-    const int L = su.Lmax;
     fill_common_outputs(su, res);
     memset(res->beta, 0, sizeof(double) * (size_t)su.P * (p + 1) * L);
-    std::vector<double> beta(q, 0.0), beta_prev(q), hgrad(3 * (size_t)p + 2), hb(p), gvec(q);
     double dval = 0.0;
+    const double *cinv_dev = stdz ? d_cinv.p : nullptr;
 
     for (int pp = 0; pp < su.P; ++pp) {
-        std::fill(beta.begin(), beta.end(), 0.0);              // init(): beta = 0, on_lam_1 = true
+        double *cur = d_iter.p, *nxt = d_iter.p + q;
+        OEM_CUDA(cudaMemsetAsync(cur, 0, sizeof(double) * q, cx.stream));      // init(): beta = 0, on_lam_1 = true
         for (int i = 0; i < su.nlam_run[pp]; ++i) {
             const bool on_lam_1 = (i == 0);
-            const double lam = su.lam[pp][i];
             int it = 0;
             bool broke = false;
             for (it = 0; it < o->irls_maxit; ++it) {
-                beta_prev = beta;
                 bool rebuilt = false;
                 if (!(it == 0 && !on_lam_1)) {
-                    for (int j = 0; j < p; ++j) hb[j] = stdz ? beta[icpt + j] * cinv[j] : beta[icpt + j];
-                    d_b.upload(hb.data(), p, cx.stream);
-                    if (fused) {
-                        // one kernel, X read from HBM once: prob, W and the gradient sums [sum r, X'r]
+                    const bool need_w = (it == 0 && on_lam_1) || o->hessian_full;
+                    irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p);
+                    cx.st.kernel_launches += 1;
+                    if (slab) {
+                        // one kernel, one HBM sweep: prob, W and the gradient sums [sum r, X'r]
                         const size_t t1 = tm.start(&cx.st.ms_irls_xb);
-                        logit_fused_launch(cx, X.p, n, p, X.ld, d_b.p, icpt ? beta[0] : 0.0, yv.p, d_prob.p, d_W.p, gfused.p);
+                        logit_slab_launch(cx, slabs.p, n, p, d_b.p, d_b0.p, yv.p, d_prob.p, d_W.p, d_g.p);
                         tm.stop(t1);
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (3.0 * n + 2.0 * p);
                     } else {
                         const size_t t1 = tm.start(&cx.st.ms_irls_xb);
-                        xb_launch(cx, X.p, n, p, X.ld, d_b.p, icpt ? beta[0] : 0.0, yv.p, nullptr, d_prob.p, d_res.p, d_W.p, true);
+                        xb_launch(cx, X.p, n, p, X.ld, d_b.p, 0.0, yv.p, nullptr, d_prob.p, d_res.p, d_W.p, true, d_b0.p);
                         tm.stop(t1);
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
+                        cx.st.data_passes += 1;
                     }
-                    if (o->rank == 0 && it < n) {            // W(i) clamp, sic (oem_logistic_dense.h:953-959)
+                    if (cx.rank == 0 && it < n) {            // W(i) clamp, sic (oem_logistic_dense.h:953-959)
                         clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, it, 1e-5);
                         cx.st.kernel_launches += 1;
                     }
-                    if ((it == 0 && on_lam_1) || o->hessian_full) {
+                    if (need_w) {
                         // X'WX / n with the intercept border (oem_logistic_dense.h:458-522)
                         double *G = bh.p, *st = G + (size_t)p * p, *ws = st + 3 * (size_t)p;
                         gram_launch(cx, X.p, n, p, X.ld, {RowSegment{0, n, 0}}, 1, nullptr, d_W.p, G, false);
@@ -165,7 +279,9 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                         colstats_launch(cx, X.p, n, p, X.ld, d_W.p, nullptr, nullptr, st, false);
                         vecsum_launch(cx, d_W.p, n, 0.0, ws, false);
                         tm.stop(tc);
+                        const size_t t_ar = tm.start(&cx.st.ms_allreduce);
                         cx.all_reduce(bh.p, (int64_t)nbh);
+                        tm.stop(t_ar);
                         // border = (W'X) o w, corner = sum W, divisor n; uncentred scale from the DATA colsq:
                         // assemble_aug derives w from stats row 2, so put sum x^2 there
                         OEM_CUDA(cudaMemcpyAsync(st + 2 * (size_t)p, stats0 + 2 * (size_t)p, (size_t)p * 8,
@@ -174,38 +290,25 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                                             nullptr, nullptr);
                         rebuilt = true;
                     }
-                    if (fused) {
-                        cx.all_reduce(gfused.p, (int64_t)p + 1);
-                        gfused.download(hgrad.data(), (size_t)p + 1, cx.stream);
-                        cx.sync();
-                        // same layout as the two-kernel route below: hgrad[j] = X'r, hgrad[3p] = sum r
-                        const double sr = hgrad[0];
-                        for (int j = 0; j < p; ++j) hgrad[j] = hgrad[j + 1];
-                        hgrad[3 * (size_t)p] = sr;
-                    } else {
+                    if (!slab) {
                         const size_t t2 = tm.start(&cx.st.ms_irls_xtr);
                         colstats_launch(cx, X.p, n, p, X.ld, d_res.p, nullptr, nullptr, gradb.p, false);
                         vecsum_launch(cx, d_res.p, n, 0.0, gradb.p + 3 * (size_t)p, false);
+                        irls_pack_grad_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(gradb.p, p, d_g.p);
                         tm.stop(t2);
+                        cx.st.kernel_launches += 1;
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
-                        cx.all_reduce(gradb.p, (int64_t)(3 * (size_t)p + 2));
-                        gradb.download(hgrad.data(), hgrad.size(), cx.stream);
-                        cx.sync();
                     }
-                    if (icpt) gvec[0] = hgrad[3 * (size_t)p] / n_tot;
-                    for (int j = 0; j < p; ++j) {
-                        double g = hgrad[j] / n_tot;
-                        if (stdz) g *= cinv[j];
-                        gvec[icpt + j] = g;
+                    if (cx.distributed()) {
+                        const size_t t_ar = tm.start(&cx.st.ms_allreduce);
+                        cx.all_reduce(d_g.p, (int64_t)p + 1);
+                        tm.stop(t_ar);
                     }
-                    d_grad.upload(gvec.data(), q, cx.stream);
-                    d_beta.upload(beta.data(), q, cx.stream);
-                    symv_add_launch(cx, q, d_XX.p, d_beta.p, d_grad.p, d_XY.p);     // XY = XX beta + grad (:999)
-                } else {
-                    d_beta.upload(beta.data(), q, cx.stream);
+                    // XY = XX beta + grad (:999)
+                    irls_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p);
+                    cx.st.kernel_launches += 1;
                 }
                 // inner OEM loop: one chain, one lambda, warm start (oem_logistic_dense.h:1010-1022)
-                d_lam.upload(&lam, 1, cx.stream);
                 PathProblem pr;
                 pr.q = q; pr.ngram = 1; pr.XX = d_XX.p; pr.XY = d_XY.p; pr.d = d_d.p;
                 pr.compute_eig = rebuilt; pr.eig_factor = 1.0005; pr.eig_tol = 1e-10;
@@ -213,29 +316,27 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                 c.gram = 0; c.penalty = su.pen[pp]; c.nlam = 1; c.lam_off = 0; c.alpha = su.alpha;
                 c.gamma = su.gamma[pp]; c.tau = su.tau; c.out_off = 0;
                 pr.chains.push_back(c);
-                pr.lambdas = d_lam.p; pr.Lmax = 1; pr.pen_fact = d_pf.p;
+                pr.lambdas = d_lams.p + (size_t)pp * L + i; pr.Lmax = 1; pr.pen_fact = d_pf.p;
                 pr.ngroups = su.any_group ? (int)su.unique.size() : 0;
                 pr.ngidx = su.any_group ? (int)su.idx.size() : 0;
                 pr.unique_groups = g_unique.p; pr.grp_ptr = g_ptr.p; pr.grp_idx = g_idx.p;
                 pr.group_weights = g_w.p; pr.grp_cover = g_cover.p;
-                pr.beta_init = d_beta.p; pr.beta_final = d_beta_final.p;
+                pr.beta_init = cur; pr.beta_final = nullptr;
                 pr.maxit = o->maxit; pr.tol = o->tol;
-                pr.beta_out = d_beta_out.p; pr.niter_out = d_niter.p; pr.lanczos_steps = d_lz.p;
+                pr.beta_out = nxt; pr.niter_out = d_niter.p; pr.lanczos_steps = d_lz.p;
+                pr.scratch = scratch.s;
                 const size_t t3 = tm.start(&cx.st.ms_path);
                 path_launch(cx, pr);
                 tm.stop(t3);
-                d_beta_out.download(beta.data(), q, cx.stream);
-                int hn = 0;
-                d_niter.download(&hn, 1, cx.stream);
-                if (rebuilt) d_d.download(&dval, 1, cx.stream);
-                cx.sync();
-                cx.st.total_oem_iters += hn;
-                if (stop_rule_host(beta, beta_prev, o->irls_tol)) { broke = true; break; }
+                irls_stop_kernel<<<1, 256, 0, cx.stream>>>(nxt, cur, q, o->irls_tol, d_niter.p, d_iters_total.p, flag.p);
+                cx.st.kernel_launches += 1;
+                cx.sync();                                   // the one host round trip of the IRLS iteration
+                std::swap(cur, nxt);                         // cur = the new iterate
+                if (*flag.p) { broke = true; break; }
             }
             res->niter[(size_t)pp * L + i] = (broke ? it : o->irls_maxit) + 1;
-            double *out = res->beta + ((size_t)pp * L + i) * (p + 1);
-            if (icpt) out[0] = beta[0];
-            for (int j = 0; j < p; ++j) out[1 + j] = stdz ? beta[icpt + j] * cinv[j] : beta[icpt + j];
+            OEM_CUDA(cudaMemcpyAsync(d_path.p + ((size_t)pp * L + i) * q, cur, sizeof(double) * q, cudaMemcpyDeviceToDevice,
+                                     cx.stream));
             if (s->compute_loss && res->loss) {
                 logistic_loss_kernel<<<1024, 256, 0, cx.stream>>>(yv.p, d_prob.p, n, d_losspart.p);
                 cx.st.kernel_launches += 1;
@@ -249,6 +350,22 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
             }
         }
     }
+    // ---- bring the path back, un-scale (get_beta, oem_logistic_dense.h:1038-1055) ----
+    std::vector<double> hpath((size_t)su.P * L * q);
+    long long iters_total = 0;
+    d_path.download(hpath.data(), hpath.size(), cx.stream);
+    d_iters_total.download(&iters_total, 1, cx.stream);
+    d_d.download(&dval, 1, cx.stream);
+    cx.sync();
+    cx.st.d2h_bytes += (int64_t)hpath.size() * 8;
+    cx.st.total_oem_iters += iters_total;
+    for (int pp = 0; pp < su.P; ++pp)
+        for (int i = 0; i < su.nlam_run[pp]; ++i) {
+            const double *raw = &hpath[((size_t)pp * L + i) * q];
+            double *out = res->beta + ((size_t)pp * L + i) * (p + 1);
+            if (icpt) out[0] = raw[0];
+            for (int j = 0; j < p; ++j) out[1 + j] = stdz ? raw[icpt + j] * cinv[j] : raw[icpt + j];
+        }
     *res->d = dval;
     finish_stats(cx, tm, t_total, res);
 }

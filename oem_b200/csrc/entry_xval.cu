@@ -206,7 +206,7 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
     std::vector<double> h3(3 * (size_t)nc);
     out3.download(h3.data(), h3.size(), cx.stream);
     cx.sync();
-    if (cx.allreduce) {
+    if (cx.distributed()) {
         // cross-rank merge with sum all-reduces only: first (count, sum) -> global mean, then M2 about it
         std::vector<double> a(2 * (size_t)nc);
         for (int c = 0; c < nc; ++c) { a[c] = h3[c]; a[nc + c] = h3[c] * h3[nc + c]; }
@@ -253,7 +253,7 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
         cx.sync();
         std::vector<double> tot(nc);
         for (int c = 0; c < nc; ++c) tot[c] = h3[c] * h3[nc + c];
-        if (cx.allreduce) {
+        if (cx.distributed()) {
             DBuf<double> dt(nc);
             dt.upload(tot.data(), nc, cx.stream);
             cx.all_reduce(dt.p, nc);

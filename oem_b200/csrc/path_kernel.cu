@@ -39,6 +39,7 @@
 // and the stop rule avoid FP64-pipe work for the (many) coordinates that are and stay zero.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 #include "runtime.h"
 
 namespace oemb200 {
@@ -56,6 +57,16 @@ struct ChainDev {
 };
 
 enum { MODE_SINGLE = 0, MODE_CLUSTER = 1, MODE_GLOBAL = 2 };
+
+struct PathScratch {
+    std::vector<unsigned char> key;      // what the tables below were built from
+    DBuf<ChainDev> chains;
+    DBuf<int> tptr, tidx, gflags;
+    DBuf<double> ubuf, A;
+    DBuf<unsigned> bar;
+};
+PathScratch *path_scratch_create() { return new PathScratch(); }
+void path_scratch_destroy(PathScratch *s) { delete s; }
 
 struct PathArgs {
     int q, qs, ngram, team_size, cpc, cpc_pad, max_ct, Lmax, maxit, accelerate, compute_eig, a_in_smem, ngroups, mode;
@@ -1291,17 +1302,39 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     const bool a_in_smem = (size_t)cpc_pad * qs * 8 + fixed_bytes <= smem_cap;
     const size_t smem_bytes = fixed_bytes + (a_in_smem ? (size_t)cpc_pad * qs * 8 : 0);
 
-    DBuf<ChainDev> d_chains(std::max<size_t>(1, cd.size()));
-    DBuf<int> d_tptr(tptr.size()), d_tidx(std::max<size_t>(1, tidx.size()));
-    DBuf<double> d_ubuf;
-    DBuf<unsigned> d_bar(G);
-    DBuf<double> d_A;
-    DBuf<int> d_gflags;
-    if (mode == MODE_GLOBAL) { d_ubuf.alloc((size_t)G * 2 * max_ct * q); d_gflags.alloc((size_t)G * 2 * team); d_gflags.zero(cx.stream); }
-    if (!a_in_smem) d_A.alloc((size_t)G * team * cpc_pad * qs);
-    if (!cd.empty()) d_chains.upload(cd.data(), cd.size(), cx.stream);
-    d_tptr.upload(tptr.data(), tptr.size(), cx.stream);
-    if (!tidx.empty()) d_tidx.upload(tidx.data(), tidx.size(), cx.stream);
+    // device tables: rebuilt unless the caller's scratch already holds exactly this layout
+    PathScratch local_scratch;
+    PathScratch &S = pp.scratch ? *pp.scratch : local_scratch;
+    std::vector<unsigned char> key;
+    {
+        auto put = [&](const void *ptr, size_t bytes) {
+            const unsigned char *b = static_cast<const unsigned char *>(ptr);
+            key.insert(key.end(), b, b + bytes);
+        };
+        const int geo[10] = {q, qs, G, team, cpc_pad, max_ct, mode, a_in_smem ? 1 : 0, (int)cd.size(), cx.device};
+        put(geo, sizeof geo);
+        if (!cd.empty()) put(cd.data(), cd.size() * sizeof(ChainDev));
+        put(tptr.data(), tptr.size() * sizeof(int));
+        if (!tidx.empty()) put(tidx.data(), tidx.size() * sizeof(int));
+    }
+    if (S.key != key) {
+        S.chains.alloc(std::max<size_t>(1, cd.size()));
+        S.tptr.alloc(tptr.size());
+        S.tidx.alloc(std::max<size_t>(1, tidx.size()));
+        S.bar.alloc(G);
+        S.ubuf.release(); S.gflags.release(); S.A.release();
+        if (mode == MODE_GLOBAL) { S.ubuf.alloc((size_t)G * 2 * max_ct * q); S.gflags.alloc((size_t)G * 2 * team); }
+        if (!a_in_smem) S.A.alloc((size_t)G * team * cpc_pad * qs);
+        if (!cd.empty()) S.chains.upload(cd.data(), cd.size(), cx.stream);
+        S.tptr.upload(tptr.data(), tptr.size(), cx.stream);
+        if (!tidx.empty()) S.tidx.upload(tidx.data(), tidx.size(), cx.stream);
+        S.key = key;
+    }
+    DBuf<ChainDev> &d_chains = S.chains;
+    DBuf<int> &d_tptr = S.tptr, &d_tidx = S.tidx, &d_gflags = S.gflags;
+    DBuf<double> &d_ubuf = S.ubuf, &d_A = S.A;
+    DBuf<unsigned> &d_bar = S.bar;
+    if (mode == MODE_GLOBAL) d_gflags.zero(cx.stream);
     d_bar.zero(cx.stream);
 
     PathArgs a;

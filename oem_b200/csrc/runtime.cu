@@ -31,7 +31,10 @@ Ctx::Ctx(const oemb200_opts *o) {
     // ordered after whatever the host program queued there (e.g. torch kernels that produced a device-resident X).
     stream = (o && o->stream) ? static_cast<cudaStream_t>(o->stream) : cudaStreamLegacy;
     own_stream = false;
-    if (o) { allreduce = o->allreduce; allreduce_ctx = o->allreduce_ctx; }
+    if (o) {
+        allreduce = o->allreduce; allreduce_ctx = o->allreduce_ctx; comm = o->comm;
+        rank = o->rank; world = o->world > 0 ? o->world : 1;
+    }
     tm = new PhaseTimers(stream);
 }
 
@@ -113,9 +116,16 @@ void pool_release_all() {
 }
 
 void Ctx::all_reduce(double *dev_buf, int64_t count) {
-    if (!allreduce) return;
-    const int rc = allreduce(dev_buf, count, stream, allreduce_ctx);
-    if (rc != 0) fail(OEMB200_ECOMM, "all-reduce callback failed with code %d", rc);
+    if (comm) {
+        comm_all_reduce(comm, dev_buf, count, stream);
+    } else if (allreduce) {
+        const int rc = allreduce(dev_buf, count, stream, allreduce_ctx);
+        if (rc != 0) fail(OEMB200_ECOMM, "all-reduce callback failed with code %d", rc);
+    } else {
+        return;
+    }
+    st.allreduce_calls += 1;
+    st.allreduce_doubles += count;
 }
 
 bool is_device_ptr(const void *p) {

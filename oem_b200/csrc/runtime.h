@@ -47,11 +47,15 @@ struct Ctx {
     oemb200_stats st;              // accumulated by the launchers
     oemb200_allreduce_fn allreduce = nullptr;
     void *allreduce_ctx = nullptr;
+    oemb200_comm *comm = nullptr;  // in-library communicator (comm.cu); wins over the callback
+    int rank = 0, world = 1;
     PhaseTimers *tm = nullptr;     // created with the context, collected by finish()
 
     explicit Ctx(const oemb200_opts *o);
     ~Ctx();
-    void sync() { OEM_CUDA(cudaStreamSynchronize(stream)); }
+    void sync() { st.host_syncs += 1; OEM_CUDA(cudaStreamSynchronize(stream)); }
+    bool distributed() const { return comm != nullptr || allreduce != nullptr; }
+    // in-place sum over ranks, ordered on `stream`; no-op in single-process runs
     void all_reduce(double *dev_buf, int64_t count);
     void finish();                 // sync the stream, fold the event timings into st
 };
@@ -101,6 +105,9 @@ struct DBuf {
 
 bool is_device_ptr(const void *p);
 
+// ---------------- comm.cu ----------------
+void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream);
+
 // ---------------- gram_syrk.cu ----------------
 struct RowSegment { int64_t row0, row1; int out; };   // rows [row0,row1) accumulate into Gram #out
 // G[out] (q x q col-major, full symmetric; nout matrices, stride q*q) (+)= X_seg' diag(w) X_seg with
@@ -124,8 +131,9 @@ void affine_launch(Ctx &cx, const double *v, int64_t n, double shift, double div
 // y += a * x
 void axpy_launch(Ctx &cx, int64_t n, double a, const double *x, double *y);
 // eta = X b + b0 (+ logistic epilogue: prob, resid = y - prob, w = prob (1 - prob))
+// b0_dev (optional): a device scalar added to b0 (the IRLS loop keeps its intercept on the device)
 void xb_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const double *b, double b0, const double *y,
-               double *eta, double *prob, double *resid, double *w, bool logistic);
+               double *eta, double *prob, double *resid, double *w, bool logistic, const double *b0_dev = nullptr);
 
 // ---------------- path_kernel.cu ----------------
 struct ChainDesc {          // one warm-started lambda path: (Gram, penalty)
@@ -136,6 +144,12 @@ struct ChainDesc {          // one warm-started lambda path: (Gram, penalty)
     double alpha, gamma, tau;
     int out_off;            // chain slot in beta_out / niter_out (units of chains)
 };
+// device tables of a generic path launch (chain descriptors, team maps, exchange buffers, barrier words); a caller
+// that launches the same chain layout many times (the logistic IRLS loop) keeps one and skips the re-uploads
+struct PathScratch;
+PathScratch *path_scratch_create();
+void path_scratch_destroy(PathScratch *s);
+
 struct PathProblem {
     int q = 0;              // dimension of beta
     int ngram = 0;          // number of Grams (teams)
@@ -164,6 +178,7 @@ struct PathProblem {
     double *beta_out = nullptr;    // device, nchains x Lmax x q  (raw iterates)
     int *niter_out = nullptr;      // device, nchains x Lmax
     int *lanczos_steps = nullptr;  // device, ngram (may be NULL)
+    PathScratch *scratch = nullptr;   // optional, see above
 };
 void path_launch(Ctx &cx, const PathProblem &pp);
 
@@ -185,11 +200,13 @@ void scale_sym_launch(Ctx &cx, int p, const double *sinv, const double *XXin, co
 // y = M x + add for a symmetric q x q M
 void symv_add_launch(Ctx &cx, int q, const double *M, const double *x, const double *add, double *y);
 
-// ---------------- logit_fused.cu ----------------
-bool logit_fused_supported(const double *X, int64_t n, int p, int64_t ld);
-// prob, w (may be NULL) and grad_out[0] = sum (y - prob), grad_out[1 + j] = sum_i x_ij (y_i - prob_i), one sweep of X
-void logit_fused_launch(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, const double *b, double b0,
-                        const double *y, double *prob, double *w, double *grad_out);
+// ---------------- logit_slab.cu ----------------
+int logit_slab_rows(int p);                       // rows per slab (0: the slab route does not apply to this p)
+size_t logit_slab_doubles(int64_t n, int p);      // size of the re-laid-out copy
+void logit_slab_relayout(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, double *slabs);
+// one pass over the slabs: prob, w (may be NULL), grad_out[0] = sum (y - prob), grad_out[1 + j] = sum_i x_ij (y_i - prob_i)
+void logit_slab_launch(Ctx &cx, const double *slabs, int64_t n, int p, const double *b, const double *b0_dev,
+                       const double *y, double *prob, double *w, double *grad_out);
 
 // ---------------- cvscore.cu ----------------
 // order[i]: for every tile of fold_gather_tile_rows() source rows, the tile-local row indices grouped by fold

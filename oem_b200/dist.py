@@ -1,10 +1,15 @@
 """Row-sharded multi-process plumbing: one process per GPU, torch.distributed for the rendezvous,
-NCCL (over NVLink / NVSwitch) for the one exchange step of the path -- the sum all-reduce of the
-packed sufficient statistics [Gram | X'y | column sums | counts].
+NVLink / NVSwitch for the one exchange step of the path -- the sum all-reduce of the packed sufficient
+statistics [Gram | X'y | column sums | counts], and of the (p+1)-vector gradient once per IRLS iteration
+of the logistic entry.
 
-The C library never links NCCL; it calls back into `Comm.callback` with a device pointer, a count
-and the CUDA stream the data is ordered on (include/oem_b200.h: oemb200_allreduce_fn).  An R / C++
-host would pass a thin wrapper around ncclAllReduce instead."""
+Two ways to give the library its all-reduce (include/oem_b200.h):
+  * `LibComm` (default for GPU runs): the library owns the communicator (oemb200_comm_create) and issues the
+    collectives itself on its own stream -- ncclAllReduce from the libnccl already loaded in the process for the
+    big bundle, a one-shot NVLink peer-memory kernel for small vectors.  torch.distributed only carries the
+    128-byte NCCL unique id at start-up.
+  * `Comm`: a host callback (`oemb200_allreduce_fn`) bound to torch.distributed.all_reduce; kept as the fallback
+    and for the CPU (gloo) tests of the sharding logic."""
 import ctypes
 
 import numpy as np
@@ -73,6 +78,58 @@ class Comm:
         t = torch.from_numpy(np.ascontiguousarray(arr))
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t.numpy()
+
+
+class LibComm:
+    """In-library communicator (oemb200_comm_*): no Python in the all-reduce path.  Collective constructor: every rank
+    of `group` must create it at the same time (ncclCommInitRank + the IPC exchange of the peer mailboxes)."""
+
+    def __init__(self, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import api
+        L = api.load()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.handle = None
+        self._L = L
+        if self.world <= 1:
+            return
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            api._check(L.oemb200_comm_unique_id(uid.ctypes.data))
+        t = torch.from_numpy(uid)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(self.device)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = t.cpu().numpy().copy()
+        h = ctypes.c_void_p()
+        api._check(L.oemb200_comm_create(uid.ctypes.data, self.rank, self.world, self.device, ctypes.byref(h)))
+        self.handle = h.value
+
+    @property
+    def p2p(self):
+        return bool(self.handle) and bool(self._L.oemb200_comm_p2p_enabled(self.handle))
+
+    def all_reduce(self, tensor, stream=None, timed=False):
+        """In-place sum of a float64 CUDA tensor through the library's communicator; returns microseconds if timed."""
+        from . import api
+        us = ctypes.c_double(0.0)
+        api._check(self._L.oemb200_comm_allreduce(self.handle, tensor.data_ptr(), tensor.numel(),
+                                                  int(stream) if stream else None, ctypes.byref(us) if timed else None))
+        return us.value if timed else None
+
+    def close(self):
+        if self.handle:
+            self._L.oemb200_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class _CudaArrayView:

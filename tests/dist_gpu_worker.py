@@ -19,9 +19,20 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     import oem_b200
-    from oem_b200.dist import Comm, shard_csc_rows, shard_rows
+    from oem_b200.dist import Comm, LibComm, shard_csc_rows, shard_rows
     from oracle import oracle as orc
-    comm = Comm()
+    # default: the in-library communicator (ncclAllReduce / one-shot NVLink peer kernel issued by the library itself);
+    # OEMB200_TEST_COMM=callback exercises the host-callback fallback (torch.distributed.all_reduce)
+    use_cb = os.environ.get("OEMB200_TEST_COMM") == "callback"
+    comm = Comm() if use_cb else LibComm()
+    if not use_cb:
+        # the communicator on its own: small (peer-memory path when available) and large (NCCL) sums, in place
+        for cnt in (1, 7, 1001, 8192, 8193, 1 << 20):
+            t = torch.full((cnt,), float(rank + 1), dtype=torch.float64, device="cuda") + torch.arange(cnt, dtype=torch.float64, device="cuda")
+            comm.all_reduce(t)
+            torch.cuda.synchronize()
+            want = world * (world + 1) / 2 + world * torch.arange(cnt, dtype=torch.float64, device="cuda")
+            assert torch.equal(t, want), (cnt, t[:4], want[:4])
 
     def shard(a, X, y):
         r0, r1 = shard_rows(X.shape[0], rank, world)
@@ -44,14 +55,16 @@ def main():
     got = oem_b200.oem_fit_dense(*sa, comm=comm)
     if rank == 0:
         assert_same_fit(got, ref)
-    # logistic
-    Xb, yb = binomial_problem(104, 6000, 30)
-    a = args_xy(Xb, yb, "binomial", ["lasso"], nlambda=10, lmin_ratio=1e-2)
-    ref = orc.oem_fit_logistic_dense(*a) if rank == 0 else None
-    sa, _, _ = shard(a, Xb, yb)
-    got = oem_b200.oem_fit_logistic_dense(*sa, comm=comm)
-    if rank == 0:
-        assert_same_fit(got, ref)
+    # logistic: two-sweep route (p = 30) and slab route (p = 200), one (p+1)-vector all-reduce per data pass
+    for nb, pb in ((6000, 30), (6001, 200)):
+        Xb, yb = binomial_problem(104, nb, pb)
+        a = args_xy(Xb, yb, "binomial", ["lasso"], nlambda=10, lmin_ratio=1e-2)
+        ref = orc.oem_fit_logistic_dense(*a) if rank == 0 else None
+        sa, _, _ = shard(a, Xb, yb)
+        got = oem_b200.oem_fit_logistic_dense(*sa, comm=comm)
+        assert got["stats"]["allreduce_calls"] >= got["stats"]["data_passes"] + 1
+        if rank == 0:
+            assert_same_fit(got, ref)
     # xval
     rng = np.random.default_rng(3)
     foldid = 1 + rng.permutation(9000) % 5
@@ -86,7 +99,10 @@ def main():
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert lo.item() == hi.item()
     if rank == 0:
-        print(f"DIST_OK world={world} allreduce_calls={comm.calls} doubles={comm.doubles}")
+        how = f"callback calls={comm.calls}" if use_cb else f"libcomm p2p={comm.p2p}"
+        print(f"DIST_OK world={world} {how}")
+    if not use_cb:
+        comm.close()
     dist.destroy_process_group()
 
 

@@ -122,18 +122,61 @@ def test_logistic(lib, oracle, hessian):
         assert np.allclose(lg, lr, rtol=1e-9)
 
 
-@pytest.mark.parametrize("n,p,intercept,standardize", [(4000, 40, True, True), (3001, 17, False, True), (6002, 130, True, False)])
-def test_logistic_fused_single_sweep_kernel(lib, oracle, monkeypatch, n, p, intercept, standardize):
-    # OEMB200_LOGIT_FUSED=1: the opt-in IRLS data pass that reads X from HBM once (logit_fused.cu) must give the same
-    # path as the default two sweeps; odd n falls back to the two-sweep route through logit_fused_supported (ld parity)
-    monkeypatch.setenv("OEMB200_LOGIT_FUSED", "1")
+@pytest.mark.parametrize("n,p,intercept,standardize,route", [
+    (6002, 130, True, False, None),        # slab route, 16-row slabs, one column per thread
+    (5003, 300, True, True, None),         # 16-row slabs, two columns per thread, ragged last slab
+    (4001, 530, False, True, None),        # 8-row slabs, three columns per thread
+    (3000, 1030, True, True, None),        # 4-row slabs
+    (5003, 300, True, True, "sweeps"),     # same problem through the two-sweep route
+    (3001, 17, False, True, None),         # small p: two sweeps
+])
+def test_logistic_data_pass_routes(lib, oracle, monkeypatch, n, p, intercept, standardize, route):
+    # the IRLS data pass either reads a row-slab copy of X once (logit_slab.cu, 128 <= p <= 2048) or sweeps the
+    # column-major X twice (xb_kernel + colstats_kernel); OEMB200_LOGIT_ROUTE=sweeps forces the latter.  Both must
+    # reproduce the oracle's path.
+    if route:
+        monkeypatch.setenv("OEMB200_LOGIT_ROUTE", route)
     X, y = binomial_problem(300 + p, n, p)
-    a = args_xy(X, y, "binomial", ["lasso", "mcp"], nlambda=10, lmin_ratio=1e-2, intercept=intercept, standardize=standardize,
+    a = args_xy(X, y, "binomial", ["lasso", "mcp"], nlambda=8, lmin_ratio=5e-2, intercept=intercept, standardize=standardize,
                 compute_loss=True)
     got, ref = lib.oem_fit_logistic_dense(*a), oracle.oem_fit_logistic_dense(*a)
     assert_same_fit(got, ref, tol=1e-8)
     for lg, lr in zip(got["loss"], ref["loss"]):
         assert np.allclose(lg, lr, rtol=1e-9)
+    st = got["stats"]
+    expect_slab = route is None and 128 <= p <= 2048
+    assert st["data_passes"] > 0 and (st["ms_relayout"] > 0) == expect_slab
+    assert st["host_syncs"] <= int(sum(np.sum(v) for v in got["niter"])) + 8 * len(got["niter"][0]) + 16
+
+
+@pytest.mark.parametrize("n,p", [(10007, 128), (4100, 512), (9001, 1000), (2050, 2048)])
+def test_logit_slab_pass_matches_fp64_reference(lib, n, p):
+    # the fused single-sweep kernel on its own against torch FP64: prob, W and [sum r, X'r]
+    import ctypes
+    import torch
+    from oem_b200 import api
+    g = torch.Generator(device="cuda").manual_seed(n + p)
+    Xt = torch.randn((p, n + (n & 1)), generator=g, dtype=torch.float64, device="cuda")
+    X = Xt.t()[:n]
+    b = torch.randn(p, generator=g, dtype=torch.float64, device="cuda") / p ** 0.5
+    y = (torch.rand(n, generator=g, dtype=torch.float64, device="cuda") < 0.4).double()
+    prob = torch.empty(n, dtype=torch.float64, device="cuda")
+    w = torch.empty_like(prob)
+    grad = torch.empty(p + 1, dtype=torch.float64, device="cuda")
+    ms, msr = ctypes.c_double(), ctypes.c_double()
+    api._check(api.load().oemb200_logit_slab_pass(X.data_ptr(), n, p, X.stride(1), b.data_ptr(), 0.3, y.data_ptr(), prob.data_ptr(),
+                                                  w.data_ptr(), grad.data_ptr(), 2, None, ctypes.byref(ms), ctypes.byref(msr)))
+    pr = torch.sigmoid(X @ b + 0.3)
+    r = y - pr
+    assert torch.allclose(prob, pr, rtol=0, atol=1e-14)
+    assert torch.allclose(w, pr * (1 - pr), rtol=0, atol=1e-14)
+    ref = torch.cat([r.sum().view(1), X.t() @ r])
+    assert torch.allclose(grad, ref, rtol=1e-12, atol=1e-10 * n ** 0.5)
+    # bit-reproducible run to run
+    grad2 = torch.empty_like(grad)
+    api._check(api.load().oemb200_logit_slab_pass(X.data_ptr(), n, p, X.stride(1), b.data_ptr(), 0.3, y.data_ptr(), None, None,
+                                                  grad2.data_ptr(), 1, None, None, None))
+    assert torch.equal(grad, grad2)
 
 
 def test_errors_mirror_reference(lib):
