@@ -115,7 +115,7 @@ typedef struct oemb200_stats {
     int64_t data_passes;        /* logistic: IRLS data passes over X (fused sigma(X beta) / X'r sweeps) */
     int64_t host_syncs;         /* stream synchronisations the host driver performed inside the call */
     double  ms_relayout;        /* logistic: one-time row-slab re-layout of X */
-    double  ms_ingest_wait;     /* oem_fit_big from host memory: time the compute stream waited for staged chunks */
+    double  ms_ingest_wait;     /* host time spent filling the pinned bounce ring from pageable / mmap'd sources */
 } oemb200_stats;
 
 /*

@@ -57,6 +57,11 @@ def write(x, bk_path, desc_path):
     mm[:] = x
     mm.flush()
     del mm
+    write_descriptor(desc_path, bk_path, n, p)
+
+
+def write_descriptor(desc_path, bk_path, n, p):
+    """The .desc file of an existing .bk backing file (n x p column-major doubles)."""
     with open(desc_path, "w") as f:
         f.write('new("big.matrix.descriptor", description = list(sharedType = "FileBacked", '
                 f'filename = "{os.path.basename(bk_path)}", dirname = "{os.path.dirname(os.path.abspath(bk_path))}/", '

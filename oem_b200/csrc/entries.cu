@@ -46,9 +46,7 @@ void to_device_matrix(Ctx &cx, const double *x, int64_t n, int p, int64_t ldx, D
              "use oem_fit_big (streams row chunks) or shard the rows over more GPUs", need / 1e9, free_b / 1e9);
     m.own.alloc((size_t)m.ld * p);
     if (m.ld != n) m.own.zero(cx.stream);
-    OEM_CUDA(cudaMemcpy2DAsync(m.own.p, (size_t)m.ld * 8, x, (size_t)ldx * 8, (size_t)n * 8, p, cudaMemcpyHostToDevice,
-                               cx.stream));
-    cx.st.h2d_bytes += (int64_t)n * p * 8;
+    h2d_block(cx, x, ldx, n, p, m.own.p, m.ld, cx.stream);      // pageable sources go through the pinned bounce ring
     m.p = m.own.p;
 }
 void to_device_vector(Ctx &cx, const double *v, int64_t n, DevVector &d) {
@@ -133,21 +131,20 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
             OEM_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
         }
         const int64_t nchunks = (n + rows - 1) / rows;
+        const bool pinned_src = is_pinned_host(x);
         auto issue_copy = [&](int64_t c) {
             const int b = (int)(c & 1);
             const int64_t r0 = c * rows, nr = std::min(rows, n - r0);
             if (c >= 2) OEM_CUDA(cudaStreamWaitEvent(cs, freed[b], 0));
-            OEM_CUDA(cudaMemcpy2DAsync(stage[b].p, (size_t)rows * 8, x + r0, (size_t)ldx * 8, (size_t)nr * 8, p,
-                                       cudaMemcpyHostToDevice, cs));
+            h2d_block(cx, x + r0, ldx, nr, p, stage[b].p, rows, cs);
             OEM_CUDA(cudaEventRecord(ready[b], cs));
-            cx.st.h2d_bytes += nr * (int64_t)p * 8;
         };
         const size_t t_h = tm.start(&cx.st.ms_h2d);   // whole streamed pass (copies overlap the kernels)
         issue_copy(0);
+        if (nchunks > 1 && pinned_src) issue_copy(1);
         for (int64_t c = 0; c < nchunks; ++c) {
             const int b = (int)(c & 1);
             const int64_t r0 = c * rows, nr = std::min(rows, n - r0);
-            if (c + 1 < nchunks) issue_copy(c + 1);
             OEM_CUDA(cudaStreamWaitEvent(cx.stream, ready[b], 0));
             if (fused_stats) {
                 gram_launch(cx, stage[b].p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, nullptr, G, c > 0, yv.p + r0, stats);
@@ -156,6 +153,10 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
                 gram_launch(cx, stage[b].p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, nullptr, G, c > 0);
             }
             OEM_CUDA(cudaEventRecord(freed[b], cx.stream));
+            // chunk c's kernels are queued: now stage the copy after next (pinned sources: an asynchronous DMA, queued one
+            // chunk further ahead; pageable sources: the reader threads fill the bounce ring while those kernels run)
+            const int64_t nxt = pinned_src ? c + 2 : c + 1;
+            if (nxt < nchunks) issue_copy(nxt);
         }
         tm.stop(t_h);
         cx.sync();
@@ -594,7 +595,7 @@ int oemb200_stop_rule(const double *cur, const double *prev, int q, double tol) 
     std::vector<double> a(cur, cur + q), b(prev, prev + q);
     return stop_rule_host(a, b, tol) ? 1 : 0;
 }
-void oemb200_release_cache(void) { pool_release_all(); }
+void oemb200_release_cache(void) { pool_release_all(); release_host_stager(); }
 
 int oemb200_fit_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *spec,
                       const oemb200_opts *opts, oemb200_result *res) {

@@ -1,4 +1,5 @@
 // runtime.cu -- device context and small runtime helpers (see runtime.h).
+#include <cstdlib>
 #include <map>
 #include <exception>
 #include "runtime.h"
@@ -102,8 +103,16 @@ void pool_free(void *p) {
     g_owner.erase(ow);
     auto it = g_pool.live.find(p);
     if (it == g_pool.live.end()) { cudaFree(p); return; }
-    // very large blocks (the uploaded copy of X) are not worth caching
-    if (it->second > (size_t(4) << 30)) cudaFree(p);
+    // Blocks up to OEMB200_POOL_MAX_GB (default 64) stay cached: repeated fits re-use the row-slab copy of the logistic
+    // entry (16 GB at configs[3]) and the fold-sorted copy of xval.oem (40 GB at configs[2]) instead of paying a
+    // cudaMalloc + cudaFree pair (each a device-wide synchronisation) per call.  pool_alloc drops the whole cache and
+    // retries when the device runs out of memory; oemb200_release_cache() drops it on request.
+    static const size_t keep_max = [] {
+        const char *e = getenv("OEMB200_POOL_MAX_GB");
+        const double gb = e ? atof(e) : 64.0;
+        return (size_t)(gb * 1073741824.0);
+    }();
+    if (it->second > keep_max) cudaFree(p);
     else g_pool.free_blocks.emplace(it->second, p);
     g_pool.live.erase(it);
 }

@@ -105,6 +105,13 @@ struct DBuf {
 
 bool is_device_ptr(const void *p);
 
+// ---------------- ingest.cu ----------------
+bool is_pinned_host(const void *p);
+// rows [0, nr) x p columns of a column-major HOST block -> device, ordered on `stream`: in place for pinned sources,
+// through the pinned bounce ring + reader threads for pageable / memory-mapped ones.  Adds to cx.st.h2d_bytes.
+void h2d_block(Ctx &cx, const double *src, int64_t ldx, int64_t nr, int p, double *dst, int64_t ld_dst, cudaStream_t stream);
+void release_host_stager();
+
 // ---------------- comm.cu ----------------
 void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream);
 

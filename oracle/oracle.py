@@ -545,25 +545,48 @@ def oem_fit_big(x, y, family, penalty, weights, groups, unique_groups, group_wei
     pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
     if intercept:
         pf = np.concatenate([[0.0], pf])
+    # nslices row slices for X'X (src/oem_big.h:319-361, 738-741): floor(n / nslices) rows each, the last takes the rest
+    nslices = max(1, int(np.ceil(8.0 * float(n) * float(p) / 1e9 / float(o.get("gigs", 4.0)))))
     colsq_inv = np.ones(p)
-    if standardize_:
-        colsq = (X ** 2).sum(axis=0) / (float(n) - 1.0)
-        colsq = np.where(colsq == 0.0, 1.0, colsq)
-        colsq_inv = 1.0 / np.sqrt(colsq)
+    if nslices <= 1:
+        if standardize_:
+            colsq = (X ** 2).sum(axis=0) / (float(n) - 1.0)
+            colsq = np.where(colsq == 0.0, 1.0, colsq)
+            colsq_inv = 1.0 / np.sqrt(colsq)
+        xty = X.T @ Y
+        G = xtx_fn(X) if xtx_fn else X.T @ X
+        colsums = X.sum(axis=0) if intercept else None
+    else:
+        # the same sums without n x p temporaries: column-wise sweeps like the reference's loops (src/oem_big.h:743-837)
+        # in blocks of columns, X'X slice by slice
+        colsq, colsums = np.zeros(p), np.zeros(p)
+        xty = X.T @ Y                                    # X.col(j).dot(Y) for every j: one GEMV, no temporaries
+        if intercept:
+            colsums = np.ones(n) @ X                     # X.col(j).sum()
+        if standardize_:
+            for j in range(p):
+                colsq[j] = np.dot(X[:, j], X[:, j])      # X.col(j).squaredNorm()
+        if standardize_:
+            colsq = colsq / (float(n) - 1.0)
+            colsq = np.where(colsq == 0.0, 1.0, colsq)
+            colsq_inv = 1.0 / np.sqrt(colsq)
+        first = n // nslices
+        G = np.zeros((p, p))
+        for ff in range(nslices):
+            Xs = X[ff * first:(n if ff + 1 == nslices else (ff + 1) * first)]
+            G += xtx_fn(Xs) if xtx_fn else Xs.T @ Xs
     XY = np.zeros(q)
-    XY[q - p:] = X.T @ Y
+    XY[q - p:] = xty
     if intercept:
         XY[0] = Y.sum()
     if standardize_:
         XY[q - p:] *= colsq_inv
     XY /= n
-    G = xtx_fn(X) if xtx_fn else X.T @ X
     if standardize_:
         G = colsq_inv[:, None] * G * colsq_inv[None, :]
     XX = np.zeros((q, q))
     XX[q - p:, q - p:] = G
     if intercept:
-        colsums = X.sum(axis=0)
         if standardize_:
             colsums = colsums * colsq_inv
         XX[0, 1:] = colsums
