@@ -9,6 +9,8 @@
  *   oemb200_xval_dense           replaces  oem_xval_dense           src/oem_xval_dense.cpp:31-52
  *   oemb200_fit_logistic_dense   replaces  oem_fit_logistic_dense   src/oem_logistic_dense.cpp:29-47
  *   oemb200_fit_big              replaces  oem_fit_big / oem_fit_fb_big   src/oem_big.cpp:30-48
+ *   oemb200_fit_sparse           replaces  oem_fit_sparse           src/oem_sparse.cpp:30
+ *   oemb200_fit_logistic_sparse  replaces  oem_fit_logistic_sparse  src/oem_logistic_sparse.cpp:30
  *
  * Argument ORDER and meaning follow the reference's .Call lists (R/oem.R:556-575,
  * R/oem_xtx.R:389-420, R/oem_xval.R:525-548, R/big_oem.R:449-490); SEXPs become plain
@@ -202,6 +204,14 @@ int oemb200_fit_sparse(const int *row_idx, const int *col_ptr, const double *val
                        const double *y, const oemb200_spec *spec, const oemb200_opts *opts,
                        oemb200_result *res);
 
+/* src/oem_logistic_sparse.cpp:30 -- binomial family on a dgCMatrix (slots as in oemb200_fit_sparse), y in {0,1}, n > p, the
+ * reference's ncores <= 1 code path.  standardize = TRUE with or without intercept, and standardize = FALSE without
+ * intercept, follow the reference; intercept = TRUE with standardize = FALSE returns OEMB200_EUNSUPPORTED (the reference
+ * multiplies by a vector it never initialised there, src/oem_logistic_sparse.h:880 vs :737-751). */
+int oemb200_fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p,
+                                const double *y, const oemb200_spec *spec, const oemb200_opts *opts,
+                                oemb200_result *res);
+
 /* predict.oem (R/methods.R:48-119; logistic response R/methods.R:346-366): out (n x nlambda, column-major,
  * ldo >= n, host or device) = newx (n x p) * beta[intercept rows dropped] + beta[0, :].  beta is the host
  * coefficient matrix of one model as the fit entries return it: beta_rows x nlambda column-major with
@@ -216,6 +226,37 @@ int oemb200_predict(const double *x, int64_t n, int p, int64_t ldx, const double
 int oemb200_predict_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p,
                            const double *beta, int beta_rows, int nlambda, int type, double *out, int64_t ldo,
                            const oemb200_opts *opts, oemb200_stats *stats);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident design matrix (SURVEY.md 8b "Ownership").  The reference copies / maps x inside every .Call
+ * (src/oem_dense.cpp:61-67; src/oem_big.cpp:52-64 wraps the big.matrix external pointer without copying); an R host
+ * cannot hold a device pointer, so without a handle every fit would re-upload x.  oemb200_matrix_create uploads an
+ * n x p column-major FP64 matrix ONCE (pageable sources through the pinned bounce ring) -- or streams the raw
+ * column-major doubles of a bigmemory backing file (.bk) -- and the *_h entries run the same drivers on it with no
+ * host -> device traffic for x.  The handle also keeps the row-slab copy the logistic entry builds on first use, so
+ * repeated binomial fits skip the re-layout too.  An Rcpp shim wraps the handle in an XPtr with
+ * oemb200_matrix_destroy as its finalizer, exactly like the reference passes `x@address`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct oemb200_matrix oemb200_matrix;
+int oemb200_matrix_create(const double *x, int64_t n, int p, int64_t ldx, const oemb200_opts *opts,
+                          oemb200_matrix **out);
+int oemb200_matrix_create_from_file(const char *bk_path, int64_t n, int p, const oemb200_opts *opts,
+                                    oemb200_matrix **out);
+int oemb200_matrix_destroy(oemb200_matrix *m);
+/* any output pointer may be NULL; h2d_bytes = bytes uploaded when the handle was created */
+int oemb200_matrix_info(const oemb200_matrix *m, int64_t *n, int *p, int64_t *ld, const double **dev_ptr,
+                        int64_t *h2d_bytes, double *ms_upload);
+int oemb200_fit_dense_h(const oemb200_matrix *x, const double *y, const oemb200_spec *spec,
+                        const oemb200_opts *opts, oemb200_result *res);
+int oemb200_fit_big_h(const oemb200_matrix *x, const double *y, const oemb200_spec *spec,
+                      const oemb200_opts *opts, oemb200_result *res);
+int oemb200_fit_logistic_dense_h(const oemb200_matrix *x, const double *y, const oemb200_spec *spec,
+                                 const oemb200_opts *opts, oemb200_result *res);
+int oemb200_xval_dense_h(const oemb200_matrix *x, const double *y, const oemb200_spec *spec, int nfolds,
+                         const int *foldid, const char *type_measure, const oemb200_opts *opts,
+                         oemb200_result *res);
+int oemb200_predict_h(const oemb200_matrix *x, const double *beta, int beta_rows, int nlambda, int type,
+                      double *out, int64_t ldo, const oemb200_opts *opts, oemb200_stats *stats);
 
 /* ------------------------------------------------------------------------------------------
  * Phase-level entries (device pointers only) used by bench.py for the roofline numbers and by

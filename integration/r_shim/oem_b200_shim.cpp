@@ -158,6 +158,49 @@ RcppExport SEXP oem_fit_sparse(SEXP x_, SEXP y_, OEM_COMMON_SEXPS) {
     END_RCPP
 }
 
+// src/oem_logistic_sparse.cpp:30-48 -- binomial family on a dgCMatrix (R/oem.R:605-625)
+RcppExport SEXP oem_fit_logistic_sparse(SEXP x_, SEXP y_, OEM_COMMON_SEXPS) {
+    BEGIN_RCPP
+    S4 x(x_);
+    IntegerVector xi = x.slot("i"), xp = x.slot("p"), dim = x.slot("Dim");
+    NumericVector xx = x.slot("x"), y(y_);
+    Call c(OEM_COMMON_ARGS);
+    Result res(c, dim[1] + 1, false);
+    check(oemb200_fit_logistic_sparse(xi.begin(), xp.begin(), xx.begin(), dim[0], dim[1], y.begin(), &c.s, &c.o, &res.r));
+    return res.pack(c, false);
+    END_RCPP
+}
+
+// Device-resident design matrix (include/oem_b200.h: oemb200_matrix_*): `oem_b200_matrix(x)` uploads an R matrix once and
+// returns an external pointer whose finalizer frees the device copy -- the same mechanism as the `x@address` pointer of a
+// big.matrix (src/oem_big.cpp:52-64).  oem_fit_dense / oem_fit_logistic_dense / oem_xval_dense below accept either a
+// plain matrix or such a pointer in `x_`, so `oem(xd, y, ...)` refits without re-uploading x.
+static void matrix_finalizer(oemb200_matrix *m) { oemb200_matrix_destroy(m); }
+typedef XPtr<oemb200_matrix, PreserveStorage, matrix_finalizer> MatrixPtr;
+RcppExport SEXP oem_b200_matrix(SEXP x_) {
+    BEGIN_RCPP
+    NumericMatrix x(x_);
+    oemb200_opts o;
+    oemb200_default_opts(&o);
+    oemb200_matrix *m = NULL;
+    check(oemb200_matrix_create(x.begin(), x.nrow(), x.ncol(), x.nrow(), &o, &m));
+    return MatrixPtr(m, true);
+    END_RCPP
+}
+RcppExport SEXP oem_fit_dense_h(SEXP x_, SEXP y_, OEM_COMMON_SEXPS) {
+    BEGIN_RCPP
+    MatrixPtr x(x_);
+    NumericVector y(y_);
+    int64_t n = 0; int p = 0;
+    check(oemb200_matrix_info(x.get(), &n, &p, NULL, NULL, NULL, NULL));
+    Call c(OEM_COMMON_ARGS);
+    Result res(c, p + 1, false);
+    if (c.family == "binomial") check(oemb200_fit_logistic_dense_h(x.get(), y.begin(), &c.s, &c.o, &res.r));
+    else check(oemb200_fit_dense_h(x.get(), y.begin(), &c.s, &c.o, &res.r));
+    return res.pack(c, false);
+    END_RCPP
+}
+
 // src/oem_big.cpp:30-64 and src/oem_fb_big.cpp -- x is big.matrix@address (an external pointer to a BigMatrix); its
 // matrix() is the (possibly memory-mapped) n x p column-major payload the reference wraps at oem_big.cpp:64.
 #ifdef OEM_B200_WITH_BIGMEMORY

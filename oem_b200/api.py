@@ -97,6 +97,7 @@ def load():
     L.oemb200_fit_dense.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
     L.oemb200_fit_big.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
     L.oemb200_fit_sparse.argtypes = [vp, vp, vp, i64, ci, vp, sp, op, rp]
+    L.oemb200_fit_logistic_sparse.argtypes = [vp, vp, vp, i64, ci, vp, sp, op, rp]
     L.oemb200_fit_logistic_dense.argtypes = [vp, i64, ci, i64, vp, sp, op, rp]
     L.oemb200_xtx.argtypes = [vp, vp, ci, sp, vp, ci, op, rp]
     L.oemb200_xval_dense.argtypes = [vp, i64, ci, i64, vp, sp, ci, vp, ctypes.c_char_p, op, rp]
@@ -106,6 +107,16 @@ def load():
     L.oemb200_top_eig.argtypes = [vp, ci, ctypes.POINTER(dbl), ctypes.POINTER(ci), vp]
     L.oemb200_logit_slab_pass.argtypes = [vp, i64, ci, i64, vp, dbl, vp, vp, vp, vp, ci, vp, ctypes.POINTER(dbl),
                                           ctypes.POINTER(dbl)]
+    L.oemb200_matrix_create.argtypes = [vp, i64, ci, i64, op, ctypes.POINTER(vp)]
+    L.oemb200_matrix_create_from_file.argtypes = [ctypes.c_char_p, i64, ci, op, ctypes.POINTER(vp)]
+    L.oemb200_matrix_destroy.argtypes = [vp]
+    L.oemb200_matrix_info.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ci), ctypes.POINTER(i64), ctypes.POINTER(vp),
+                                      ctypes.POINTER(i64), ctypes.POINTER(dbl)]
+    L.oemb200_fit_dense_h.argtypes = [vp, vp, sp, op, rp]
+    L.oemb200_fit_big_h.argtypes = [vp, vp, sp, op, rp]
+    L.oemb200_fit_logistic_dense_h.argtypes = [vp, vp, sp, op, rp]
+    L.oemb200_xval_dense_h.argtypes = [vp, vp, sp, ci, vp, ctypes.c_char_p, op, rp]
+    L.oemb200_predict_h.argtypes = [vp, vp, ci, ci, ci, vp, i64, op, ctypes.POINTER(Stats)]
     L.oemb200_comm_unique_id.argtypes = [vp]
     L.oemb200_comm_create.argtypes = [vp, ci, ci, ci, ctypes.POINTER(vp)]
     L.oemb200_comm_from_nccl.argtypes = [vp, ci, ci, ci, ctypes.POINTER(vp)]
@@ -123,10 +134,12 @@ def load():
 
 EXPORTS = ["oemb200_last_error", "oemb200_version", "oemb200_device_count", "oemb200_default_opts",
            "oemb200_penalty_id", "oemb200_nlambda_max", "oemb200_fit_dense", "oemb200_xtx", "oemb200_xval_dense",
-           "oemb200_fit_logistic_dense", "oemb200_fit_big", "oemb200_fit_sparse", "oemb200_gram", "oemb200_colstats",
+           "oemb200_fit_logistic_dense", "oemb200_fit_big", "oemb200_fit_sparse", "oemb200_fit_logistic_sparse", "oemb200_gram", "oemb200_colstats",
            "oemb200_xb_logistic", "oemb200_top_eig", "oemb200_lambda_grid", "oemb200_stop_rule",
            "oemb200_release_cache", "oemb200_predict", "oemb200_predict_sparse", "oemb200_logit_slab_pass",
-           "oemb200_comm_unique_id", "oemb200_comm_create", "oemb200_comm_from_nccl", "oemb200_comm_destroy",
+           "oemb200_matrix_create", "oemb200_matrix_create_from_file", "oemb200_matrix_destroy", "oemb200_matrix_info",
+           "oemb200_fit_dense_h", "oemb200_fit_big_h", "oemb200_fit_logistic_dense_h", "oemb200_xval_dense_h",
+           "oemb200_predict_h", "oemb200_comm_unique_id", "oemb200_comm_create", "oemb200_comm_from_nccl", "oemb200_comm_destroy",
            "oemb200_comm_allreduce", "oemb200_comm_p2p_enabled"]
 
 
@@ -150,6 +163,43 @@ def _check(rc):
 
 def _is_torch_cuda(a):
     return type(a).__module__.startswith("torch") and getattr(a, "is_cuda", False)
+
+
+class DeviceMatrix:
+    """Device-resident design matrix (oemb200_matrix_*): uploaded once, then passed as `x` to oem_fit_dense / oem_fit_big /
+    oem_fit_logistic_dense / oem_xval_dense / predict_matrix, which run on it without re-uploading.  `x` is a numpy array /
+    np.memmap (host), a column-major CUDA tensor (copied on the device), or the path of a bigmemory backing file (.bk: raw
+    column-major doubles) together with shape=(n, p)."""
+
+    def __init__(self, x, shape=None, opts=None):
+        L = load()
+        o = opts if isinstance(opts, Opts) else make_opts(opts)
+        h = ctypes.c_void_p()
+        if isinstance(x, (str, bytes, os.PathLike)):
+            if shape is None:
+                raise ValueError("shape=(n, p) is required with a backing-file path")
+            _check(L.oemb200_matrix_create_from_file(os.fsencode(x), int(shape[0]), int(shape[1]), ctypes.byref(o), ctypes.byref(h)))
+        else:
+            keep = _Keep()
+            xp, n, p, ld = _matrix_arg(x, keep)
+            _check(L.oemb200_matrix_create(xp, n, p, ld, ctypes.byref(o), ctypes.byref(h)))
+        self.handle = h.value
+        n, p, ld, ptr, nb, ms = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_double()
+        _check(L.oemb200_matrix_info(self.handle, ctypes.byref(n), ctypes.byref(p), ctypes.byref(ld), ctypes.byref(ptr),
+                                     ctypes.byref(nb), ctypes.byref(ms)))
+        self.shape = (n.value, p.value)
+        self.ld, self.data_ptr, self.h2d_bytes, self.ms_upload = ld.value, ptr.value, nb.value, ms.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            load().oemb200_matrix_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class _Keep:
@@ -305,7 +355,15 @@ def _run_xy(fn_name, x, y, family, penalty, weights, groups, unique_groups, grou
             extra=None):
     L = load()
     keep = _Keep()
-    xp, n, p, ld = _matrix_arg(x, keep)
+    handle = isinstance(x, DeviceMatrix)
+    if handle:
+        if not x.handle:
+            raise ValueError("DeviceMatrix has been closed")
+        (n, p), xargs = x.shape, [x.handle]
+        fn_name += "_h"
+    else:
+        xp, n, p, ld = _matrix_arg(x, keep)
+        xargs = [xp, n, p, ld]
     yp, ny = _vector_arg(y, keep)
     if ny != n:
         raise ValueError("length of y must equal nrow(x)")
@@ -313,12 +371,12 @@ def _run_xy(fn_name, x, y, family, penalty, weights, groups, unique_groups, grou
                       lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss)
     o = opts if isinstance(opts, Opts) else make_opts(opts, comm)
     Lmax = L.oemb200_nlambda_max(ctypes.byref(spec))
-    out = _Out(len(penalty), Lmax, p + 1, xval=(fn_name == "oemb200_xval_dense"))
+    out = _Out(len(penalty), Lmax, p + 1, xval=fn_name.startswith("oemb200_xval_dense"))
     fn = getattr(L, fn_name)
     if extra is None:
-        rc = fn(xp, n, p, ld, yp, ctypes.byref(spec), ctypes.byref(o), ctypes.byref(out.res))
+        rc = fn(*xargs, yp, ctypes.byref(spec), ctypes.byref(o), ctypes.byref(out.res))
     else:
-        rc = fn(xp, n, p, ld, yp, ctypes.byref(spec), *extra(keep), ctypes.byref(o), ctypes.byref(out.res))
+        rc = fn(*xargs, yp, ctypes.byref(spec), *extra(keep), ctypes.byref(o), ctypes.byref(out.res))
     _check(rc)
     return out.as_dict()
 
@@ -369,9 +427,18 @@ def _int_array_arg(a, keep):
     return a.ctypes.data if a.size else None
 
 
+def oem_fit_logistic_sparse(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+                            lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss, opts,
+                            comm=None):
+    """src/oem_logistic_sparse.cpp:30-330 (x = dgCMatrix: scipy.sparse matrix or its (i, p, x, dim) slots)."""
+    return oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
+                          lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss, opts,
+                          comm=comm, _entry="oemb200_fit_logistic_sparse")
+
+
 def oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_weights, lambda_, nlambda,
                    lmin_ratio, alpha, gamma, tau, penalty_factor, standardize, intercept, compute_loss, opts,
-                   comm=None):
+                   comm=None, _entry="oemb200_fit_sparse"):
     """src/oem_sparse.cpp:30-264 (x = dgCMatrix: scipy.sparse matrix or its (i, p, x, dim) slots)."""
     L = load()
     keep = _Keep()
@@ -386,7 +453,7 @@ def oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_
     o = opts if isinstance(opts, Opts) else make_opts(opts, comm)
     Lmax = L.oemb200_nlambda_max(ctypes.byref(spec))
     out = _Out(len(penalty), Lmax, p + 1, xval=False)
-    _check(L.oemb200_fit_sparse(rip, cpp, vp_, n, p, yp, ctypes.byref(spec), ctypes.byref(o), ctypes.byref(out.res)))
+    _check(getattr(L, _entry)(rip, cpp, vp_, n, p, yp, ctypes.byref(spec), ctypes.byref(o), ctypes.byref(out.res)))
     return out.as_dict()
 
 
@@ -440,7 +507,10 @@ def predict_matrix(newx, beta, response=False, opts=None, out=None, return_stats
     L = load()
     keep = _Keep()
     sparse = isinstance(newx, tuple) or type(newx).__module__.startswith("scipy.sparse")
-    if sparse:
+    handle = isinstance(newx, DeviceMatrix)
+    if handle:
+        n, p = newx.shape
+    elif sparse:
         ri, cp, vals, n, p = _csc_slots(newx)
         rip, cpp = _int_array_arg(ri, keep), _int_array_arg(cp, keep)
         vp_, _ = _vector_arg(vals, keep) if (_is_torch_cuda(vals) or np.asarray(vals).size) else (None, 0)
@@ -459,7 +529,10 @@ def predict_matrix(newx, beta, response=False, opts=None, out=None, return_stats
         if not _is_torch_cuda(out) or tuple(out.shape) != (n, nl) or (out.stride(0) != 1 and n > 1):
             raise ValueError("out must be a column-major float64 cuda tensor of shape (n, nlambda)")
         res, op_, ldo = out, out.data_ptr(), max(out.stride(1) if nl > 1 else n, n)
-    if sparse:
+    if handle:
+        _check(L.oemb200_predict_h(newx.handle, b.ctypes.data, rows, nl, 1 if response else 0, op_, ldo, ctypes.byref(o),
+                                   ctypes.byref(st)))
+    elif sparse:
         _check(L.oemb200_predict_sparse(rip, cpp, vp_, n, p, b.ctypes.data, rows, nl, 1 if response else 0, op_, ldo,
                                         ctypes.byref(o), ctypes.byref(st)))
     else:

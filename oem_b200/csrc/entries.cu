@@ -123,13 +123,25 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
         DBuf<double> stage[2];
         stage[0].alloc((size_t)rows * p);
         stage[1].alloc((size_t)rows * p);
-        cudaStream_t cs;
-        OEM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-        cudaEvent_t ready[2], freed[2];
-        for (int b = 0; b < 2; ++b) {
-            OEM_CUDA(cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
-            OEM_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
-        }
+        // copy stream + ping-pong events, released on every exit path (a throwing launch included)
+        struct CopyLane {
+            cudaStream_t s = nullptr;
+            cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+            CopyLane() {
+                OEM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+                for (int b = 0; b < 2; ++b) {
+                    OEM_CUDA(cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
+                    OEM_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
+                }
+            }
+            ~CopyLane() {
+                if (s) cudaStreamSynchronize(s);
+                for (int b = 0; b < 2; ++b) { if (ready[b]) cudaEventDestroy(ready[b]); if (freed[b]) cudaEventDestroy(freed[b]); }
+                if (s) cudaStreamDestroy(s);
+            }
+        } lane;
+        cudaStream_t cs = lane.s;
+        cudaEvent_t *ready = lane.ready, *freed = lane.freed;
         const int64_t nchunks = (n + rows - 1) / rows;
         const bool pinned_src = is_pinned_host(x);
         auto issue_copy = [&](int64_t c) {
@@ -160,8 +172,6 @@ static void fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
         }
         tm.stop(t_h);
         cx.sync();
-        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ready[b]); cudaEventDestroy(freed[b]); }
-        cudaStreamDestroy(cs);
     }
     const double nd = (double)n;
     OEM_CUDA(cudaMemcpyAsync(nobs, &nd, 8, cudaMemcpyHostToDevice, cx.stream));
@@ -432,6 +442,8 @@ static void fit_xtx(const double *xtx, const double *xty, int p, const oemb200_s
     check_common(s, o, res, "gaussian");
     if (p < 1 || !xtx || !xty) fail(OEMB200_EINVAL, "xtx / xty missing");
     if (n_sf != 0 && n_sf != p) fail(OEMB200_EINVAL, "scale_factor must have length p");
+    if (n_sf != 0 && (!scale_factor || is_device_ptr(scale_factor)))
+        fail(OEMB200_EINVAL, "scale_factor must be a host vector (it is read on the host)");
     Ctx cx(o);
     PhaseTimers &tm = *cx.tm;
     const size_t t_total = tm.start(&cx.st.ms_total);
@@ -475,9 +487,11 @@ static void fit_xtx(const double *xtx, const double *xty, int p, const oemb200_s
 }
 
 void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s,
-                  const oemb200_opts *o, oemb200_result *res);
+                  const oemb200_opts *o, oemb200_result *res, SlabCache *cache);
 void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
                 const oemb200_spec *s, const oemb200_opts *o, oemb200_result *res);
+void fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
+                         const oemb200_spec *s, const oemb200_opts *o, oemb200_result *res);
 void predict_sparse_entry(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *beta,
                           int nrows, int L, int type, double *out, int64_t ldo, const oemb200_opts *o, oemb200_stats *stats);
 void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s, int nfolds,
@@ -613,9 +627,13 @@ int oemb200_fit_sparse(const int *row_idx, const int *col_ptr, const double *val
                        const oemb200_spec *spec, const oemb200_opts *opts, oemb200_result *res) {
     return guarded([&] { fit_sparse(row_idx, col_ptr, values, n, p, y, spec, opts, res); });
 }
+int oemb200_fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
+                                const oemb200_spec *spec, const oemb200_opts *opts, oemb200_result *res) {
+    return guarded([&] { fit_logistic_sparse(row_idx, col_ptr, values, n, p, y, spec, opts, res); });
+}
 int oemb200_fit_logistic_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y,
                                const oemb200_spec *spec, const oemb200_opts *opts, oemb200_result *res) {
-    return guarded([&] { fit_logistic(x, n, p, ldx, y, spec, opts, res); });
+    return guarded([&] { fit_logistic(x, n, p, ldx, y, spec, opts, res, nullptr); });
 }
 int oemb200_xval_dense(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *spec,
                        int nfolds, const int *foldid, const char *type_measure, const oemb200_opts *opts,
@@ -632,6 +650,190 @@ int oemb200_predict_sparse(const int *row_idx, const int *col_ptr, const double 
                            int beta_rows, int nlambda, int type, double *out, int64_t ldo, const oemb200_opts *opts,
                            oemb200_stats *stats) {
     return guarded([&] { predict_sparse_entry(row_idx, col_ptr, values, n, p, beta, beta_rows, nlambda, type, out, ldo, opts, stats); });
+}
+
+// ---------------- device-resident matrix handle ----------------
+}  // extern "C"
+
+struct oemb200_matrix {
+    double *dev = nullptr;
+    int64_t n = 0, ld = 0;
+    int p = 0, device = 0;
+    int64_t h2d_bytes = 0;
+    double ms_upload = 0.0;
+    mutable SlabCache slab;      // built by the first logistic fit on the handle
+};
+
+namespace {
+oemb200_matrix *matrix_alloc(Ctx &cx, int64_t n, int p) {
+    if (n < 1 || p < 1) fail(OEMB200_EINVAL, "matrix: bad dimensions n=%lld p=%d", (long long)n, p);
+    oemb200_matrix *m = new oemb200_matrix();
+    m->n = n; m->p = p; m->ld = n + (n & 1); m->device = cx.device;
+    const size_t bytes = (size_t)m->ld * p * 8;
+    if (cudaMalloc(reinterpret_cast<void **>(&m->dev), bytes) != cudaSuccess) {
+        cudaGetLastError();
+        pool_release_all();
+        if (cudaMalloc(reinterpret_cast<void **>(&m->dev), bytes) != cudaSuccess) {
+            cudaGetLastError();
+            delete m;
+            fail(OEMB200_ECUDA, "matrix: cudaMalloc of %.2f GB failed", bytes / 1e9);
+        }
+    }
+    if (m->ld != n) OEM_CUDA(cudaMemsetAsync(m->dev, 0, bytes, cx.stream));
+    return m;
+}
+// upload in row chunks of `gigs` GB so that the bounce ring (pageable sources) overlaps its DMA with the next fill
+void matrix_upload(Ctx &cx, oemb200_matrix *m, const double *x, int64_t ldx, double gigs) {
+    cudaEvent_t e0, e1;
+    OEM_CUDA(cudaEventCreate(&e0)); OEM_CUDA(cudaEventCreate(&e1));
+    OEM_CUDA(cudaEventRecord(e0, cx.stream));
+    if (is_device_ptr(x)) {
+        OEM_CUDA(cudaMemcpy2DAsync(m->dev, (size_t)m->ld * 8, x, (size_t)ldx * 8, (size_t)m->n * 8, m->p, cudaMemcpyDeviceToDevice, cx.stream));
+    } else {
+        int64_t rows = (int64_t)((gigs > 0 ? gigs : 1.0) * 1e9 / (8.0 * m->p));
+        rows = std::max<int64_t>(1024, rows);
+        for (int64_t r0 = 0; r0 < m->n; r0 += rows)
+            h2d_block(cx, x + r0, ldx, std::min(rows, m->n - r0), m->p, m->dev + r0, m->ld, cx.stream);
+    }
+    OEM_CUDA(cudaEventRecord(e1, cx.stream));
+    cx.sync();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    m->ms_upload = ms;
+    m->h2d_bytes = cx.st.h2d_bytes;
+}
+void check_handle(const oemb200_matrix *m) {
+    if (!m || !m->dev) fail(OEMB200_EINVAL, "matrix handle is NULL or destroyed");
+}
+// the *_h entries run on the handle's device
+struct HandleOpts {
+    oemb200_opts o;
+    HandleOpts(const oemb200_matrix *m, const oemb200_opts *in) {
+        if (!in) fail(OEMB200_EINVAL, "opts must not be NULL");
+        o = *in;
+        if (o.device >= 0 && o.device != m->device)
+            fail(OEMB200_EINVAL, "opts.device = %d but the matrix lives on device %d", o.device, m->device);
+        o.device = m->device;
+    }
+};
+}  // namespace
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+extern "C" {
+
+int oemb200_matrix_create(const double *x, int64_t n, int p, int64_t ldx, const oemb200_opts *opts, oemb200_matrix **out) {
+    return guarded([&] {
+        if (!x || !out || !opts) fail(OEMB200_EINVAL, "matrix_create: x / opts / out must not be NULL");
+        if (ldx < n) fail(OEMB200_EINVAL, "matrix_create: ldx < n");
+        Ctx cx(opts);
+        oemb200_matrix *m = matrix_alloc(cx, n, p);
+        try {
+            matrix_upload(cx, m, x, ldx, opts->gigs);
+        } catch (...) {
+            cudaFree(m->dev);
+            delete m;
+            throw;
+        }
+        *out = m;
+    });
+}
+
+int oemb200_matrix_create_from_file(const char *bk_path, int64_t n, int p, const oemb200_opts *opts, oemb200_matrix **out) {
+    return guarded([&] {
+        if (!bk_path || !out || !opts) fail(OEMB200_EINVAL, "matrix_create_from_file: path / opts / out must not be NULL");
+        if (n < 1 || p < 1) fail(OEMB200_EINVAL, "matrix_create_from_file: bad dimensions n=%lld p=%d", (long long)n, p);
+        // the backing file of a bigmemory file-backed matrix: raw column-major doubles, no header (R/big_oem.R:87-90)
+        const int fd = open(bk_path, O_RDONLY);
+        if (fd < 0) fail(OEMB200_EINVAL, "cannot open %s", bk_path);
+        struct stat sb;
+        const size_t need = (size_t)n * p * 8;
+        if (fstat(fd, &sb) != 0 || (size_t)sb.st_size < need) {
+            close(fd);
+            fail(OEMB200_EINVAL, "%s holds %lld bytes, an %lld x %d matrix of doubles needs %zu", bk_path,
+                 (long long)sb.st_size, (long long)n, p, need);
+        }
+        void *map = mmap(nullptr, need, PROT_READ, MAP_SHARED, fd, 0);
+        close(fd);
+        if (map == MAP_FAILED) fail(OEMB200_EINVAL, "cannot map %s", bk_path);
+        madvise(map, need, MADV_SEQUENTIAL);
+        oemb200_matrix *m = nullptr;
+        try {
+            Ctx cx(opts);
+            m = matrix_alloc(cx, n, p);
+            matrix_upload(cx, m, static_cast<const double *>(map), n, opts->gigs);
+        } catch (...) {
+            munmap(map, need);
+            if (m) { cudaFree(m->dev); delete m; }
+            throw;
+        }
+        munmap(map, need);
+        *out = m;
+    });
+}
+
+int oemb200_matrix_destroy(oemb200_matrix *m) {
+    return guarded([&] {
+        if (!m) return;
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(m->device);
+        if (m->slab.slabs) cudaFree(m->slab.slabs);
+        if (m->dev) cudaFree(m->dev);
+        if (prev >= 0) cudaSetDevice(prev);
+        cudaGetLastError();
+        delete m;
+    });
+}
+
+int oemb200_matrix_info(const oemb200_matrix *m, int64_t *n, int *p, int64_t *ld, const double **dev_ptr, int64_t *h2d_bytes,
+                        double *ms_upload) {
+    return guarded([&] {
+        check_handle(m);
+        if (n) *n = m->n;
+        if (p) *p = m->p;
+        if (ld) *ld = m->ld;
+        if (dev_ptr) *dev_ptr = m->dev;
+        if (h2d_bytes) *h2d_bytes = m->h2d_bytes;
+        if (ms_upload) *ms_upload = m->ms_upload;
+    });
+}
+
+int oemb200_fit_dense_h(const oemb200_matrix *x, const double *y, const oemb200_spec *spec, const oemb200_opts *opts,
+                        oemb200_result *res) {
+    return guarded([&] { check_handle(x); HandleOpts h(x, opts); fit_dense(x->dev, x->n, x->p, x->ld, y, spec, &h.o, res); });
+}
+int oemb200_fit_big_h(const oemb200_matrix *x, const double *y, const oemb200_spec *spec, const oemb200_opts *opts,
+                      oemb200_result *res) {
+    return guarded([&] { check_handle(x); HandleOpts h(x, opts); fit_big(x->dev, x->n, x->p, x->ld, y, spec, &h.o, res); });
+}
+int oemb200_fit_logistic_dense_h(const oemb200_matrix *x, const double *y, const oemb200_spec *spec, const oemb200_opts *opts,
+                                 oemb200_result *res) {
+    return guarded([&] {
+        check_handle(x);
+        HandleOpts h(x, opts);
+        fit_logistic(x->dev, x->n, x->p, x->ld, y, spec, &h.o, res, &x->slab);
+    });
+}
+int oemb200_xval_dense_h(const oemb200_matrix *x, const double *y, const oemb200_spec *spec, int nfolds, const int *foldid,
+                         const char *type_measure, const oemb200_opts *opts, oemb200_result *res) {
+    return guarded([&] {
+        check_handle(x);
+        HandleOpts h(x, opts);
+        fit_xval(x->dev, x->n, x->p, x->ld, y, spec, nfolds, foldid, type_measure, &h.o, res);
+    });
+}
+int oemb200_predict_h(const oemb200_matrix *x, const double *beta, int beta_rows, int nlambda, int type, double *out,
+                      int64_t ldo, const oemb200_opts *opts, oemb200_stats *stats) {
+    return guarded([&] {
+        check_handle(x);
+        HandleOpts h(x, opts);
+        predict_entry(x->dev, x->n, x->p, x->ld, beta, beta_rows, nlambda, type, out, ldo, &h.o, stats);
+    });
 }
 
 // ---------------- phase-level entries ----------------

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include "host_common.h"
 
 namespace oemb200 {
@@ -55,11 +56,11 @@ __global__ void irls_coef_kernel(const double *__restrict__ beta, const double *
     if (j == 0) *b0 = icpt ? beta[0] : 0.0;
 }
 
-// two-sweep route: [X'r (p) | . | . | sum r, .] of colstats / vecsum -> the (p+1)-vector [sum r, X'r] the slab kernel emits
-__global__ void irls_pack_grad_kernel(const double *__restrict__ stats, int p, double *__restrict__ g) {
+// X'r (p values at xr) and sum r (at sr) of the column sweeps -> the (p+1)-vector [sum r, X'r] the slab kernel emits
+__global__ void irls_pack_grad_kernel(const double *__restrict__ xr, const double *__restrict__ sr, int p, double *__restrict__ g) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < p) g[1 + j] = stats[j];
-    if (j == 0) g[0] = stats[3 * (size_t)p];
+    if (j < p) g[1 + j] = xr[j];
+    if (j == 0) g[0] = sr[0];
 }
 
 // XY = XX beta + grad with grad = [g0 / n, (g_j / n) o colsq_inv] (oem_logistic_dense.h:970-999).  One warp per row.
@@ -122,7 +123,7 @@ struct ScratchHolder {
 }  // namespace
 
 void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *y, const oemb200_spec *s,
-                  const oemb200_opts *o, oemb200_result *res) {
+                  const oemb200_opts *o, oemb200_result *res, SlabCache *cache) {
     check_common(s, o, res, "binomial");
     if (n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
     const int icpt = s->intercept ? 1 : 0, q = p + icpt;
@@ -180,17 +181,30 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     //      sweeps: xb_kernel + colstats_kernel, two HBM sweeps per pass (small / very wide p, or no room for the copy)
     const char *route_env = getenv("OEMB200_LOGIT_ROUTE");
     bool slab = logit_slab_rows(p) != 0 && !(route_env && strcmp(route_env, "sweeps") == 0);
-    DBuf<double> slabs;
-    if (slab) {
+    DBuf<double> slabs_own;
+    const double *slabs_p = nullptr;
+    if (slab && cache && cache->slabs && cache->rt == logit_slab_rows(p)) {
+        slabs_p = cache->slabs;                                                       // built by an earlier fit on this handle
+    } else if (slab) {
         size_t free_b = 0, total_b = 0;
         OEM_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const size_t need = logit_slab_doubles(n, p) * 8;
         if (need + 3 * (size_t)(n + 2) * 8 + (1ull << 30) > free_b) slab = false;      // no room for the second copy of X
     }
-    if (slab) {
+    if (slab && !slabs_p) {
         const size_t t_r = tm.start(&cx.st.ms_relayout);
-        slabs.alloc(logit_slab_doubles(n, p));
-        logit_slab_relayout(cx, X.p, n, p, X.ld, slabs.p);
+        double *dst = nullptr;
+        if (cache) {       // the handle owns the copy (plain cudaMalloc: it outlives this call and this thread's pool)
+            if (cache->slabs) { cudaFree(cache->slabs); cache->slabs = nullptr; }
+            OEM_CUDA(cudaMalloc(reinterpret_cast<void **>(&dst), logit_slab_doubles(n, p) * 8));
+            cache->slabs = dst;
+            cache->rt = logit_slab_rows(p);
+        } else {
+            slabs_own.alloc(logit_slab_doubles(n, p));
+            dst = slabs_own.p;
+        }
+        logit_slab_relayout(cx, X.p, n, p, X.ld, dst);
+        slabs_p = dst;
         tm.stop(t_r);
     }
 
@@ -257,7 +271,7 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                     if (slab) {
                         // one kernel, one HBM sweep: prob, W and the gradient sums [sum r, X'r]
                         const size_t t1 = tm.start(&cx.st.ms_irls_xb);
-                        logit_slab_launch(cx, slabs.p, n, p, d_b.p, d_b0.p, yv.p, d_prob.p, d_W.p, d_g.p);
+                        logit_slab_launch(cx, slabs_p, n, p, d_b.p, d_b0.p, yv.p, d_prob.p, d_W.p, d_g.p);
                         tm.stop(t1);
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (3.0 * n + 2.0 * p);
                     } else {
@@ -294,7 +308,7 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                         const size_t t2 = tm.start(&cx.st.ms_irls_xtr);
                         colstats_launch(cx, X.p, n, p, X.ld, d_res.p, nullptr, nullptr, gradb.p, false);
                         vecsum_launch(cx, d_res.p, n, 0.0, gradb.p + 3 * (size_t)p, false);
-                        irls_pack_grad_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(gradb.p, p, d_g.p);
+                        irls_pack_grad_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(gradb.p, gradb.p + 3 * (size_t)p, p, d_g.p);
                         tm.stop(t2);
                         cx.st.kernel_launches += 1;
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
@@ -353,6 +367,268 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     // ---- bring the path back, un-scale (get_beta, oem_logistic_dense.h:1038-1055) ----
     std::vector<double> hpath((size_t)su.P * L * q);
     long long iters_total = 0;
+    d_path.download(hpath.data(), hpath.size(), cx.stream);
+    d_iters_total.download(&iters_total, 1, cx.stream);
+    d_d.download(&dval, 1, cx.stream);
+    cx.sync();
+    cx.st.d2h_bytes += (int64_t)hpath.size() * 8;
+    cx.st.total_oem_iters += iters_total;
+    for (int pp = 0; pp < su.P; ++pp)
+        for (int i = 0; i < su.nlam_run[pp]; ++i) {
+            const double *raw = &hpath[((size_t)pp * L + i) * q];
+            double *out = res->beta + ((size_t)pp * L + i) * (p + 1);
+            if (icpt) out[0] = raw[0];
+            for (int j = 0; j < p; ++j) out[1 + j] = stdz ? raw[icpt + j] * cinv[j] : raw[icpt + j];
+        }
+    *res->d = dval;
+    finish_stats(cx, tm, t_total, res);
+}
+
+// ================================================================================================
+// oem_fit_logistic_sparse  (src/oem_logistic_sparse.cpp:30-330, solver src/oem_logistic_sparse.h:458-545, 727-1100)
+// ================================================================================================
+// dgCMatrix design, n > p, the reference's `ncores <= 1` code path.  Same IRLS skeleton as the dense entry, with the
+// sparse solver's own conventions (restated in oracle.oem_fit_logistic_sparse):
+//   * X'WX and d are rebuilt on EVERY data pass (compute_XtX_d_update_A is unconditional, :958-961);
+//   * the intercept column is the constant `intval`, fixed at the first pass (:470-491): xxdiag = mean(diag(X block)),
+//     intval = sqrt((xxdiag / sum W) / n), XX(0,0) = xxdiag, border = (X'W o colsq_inv) * intval;
+//   * eta of the (standardize, intercept) branch adds beta(0) without intval (:875-876); grad(0) = sum(y - prob) / n;
+//   * get_beta() multiplies the member beta(0) by intval in place (:1040-1043).
+// intercept && !standardize multiplies beta by a colsq_inv that the reference never initialised (:880 vs :737-751):
+// there is no behaviour to match, so that combination is rejected.
+// Data passes: CSR SpMV with the logistic epilogue, the weighted sparse Gram (or densified DMMA tiles from ~6 % density),
+// per-column sums over the CSC slots; one all-reduce of [X'WX | X'W | sum W | X'r | sum r] per pass in sharded runs.
+
+__global__ void diag_gather_kernel(const double *__restrict__ G, int p, double *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < p) out[j] = G[(size_t)j * p + j];
+}
+
+// XX (q x q) = [[xxdiag, ((X'W) o cinv) intval], [., cinv G cinv]] / n
+__global__ void logit_sparse_assemble_kernel(int p, int icpt, const double *__restrict__ G, const double *__restrict__ xw,
+                                             const double *__restrict__ cinv, double intval, double xxdiag, double n_tot,
+                                             double *__restrict__ XX) {
+    const int q = p + icpt;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)q * q) return;
+    const int r = (int)(e % q), c = (int)(e / q);
+    double v;
+    if (icpt && r == 0 && c == 0) v = xxdiag;
+    else if (icpt && (r == 0 || c == 0)) {
+        const int j = (r == 0 ? c : r) - 1;
+        double t = xw[j];
+        if (cinv) t *= cinv[j];
+        v = t * intval;
+    } else {
+        const int jr = r - icpt, jc = c - icpt;
+        v = G[(size_t)jc * p + jr];
+        if (cinv) v = (cinv[jr] * v) * cinv[jc];
+    }
+    XX[e] = v / n_tot;
+}
+
+__global__ void scale_first_kernel(double *v, double f) { v[0] *= f; }
+
+void fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p, const double *y,
+                         const oemb200_spec *s, const oemb200_opts *o, oemb200_result *res) {
+    check_common(s, o, res, "binomial");
+    if (n < 1 || p < 1 || !col_ptr || !y) fail(OEMB200_EINVAL, "bad sparse input: n=%lld p=%d", (long long)n, p);
+    if (n >= (1ll << 31)) fail(OEMB200_EINVAL, "sparse: more than 2^31-1 rows per call; shard the rows");
+    const int icpt = s->intercept ? 1 : 0, q = p + icpt;
+    const bool stdz = s->standardize != 0;
+    if (icpt && !stdz)
+        fail(OEMB200_EUNSUPPORTED, "oem_fit_logistic_sparse with intercept = TRUE and standardize = FALSE reads an uninitialised "
+                                   "colsq_inv in the reference (src/oem_logistic_sparse.h:880): no defined behaviour to reproduce");
+    Ctx cx(o);
+    PhaseTimers &tm = *cx.tm;
+    const size_t t_total = tm.start(&cx.st.ms_total);
+    Setup su;
+    su.parse(s, q, q, /*zero_w0=*/true);
+
+    const size_t t_h = tm.start(&cx.st.ms_h2d);
+    std::unique_ptr<SparseDesign, void (*)(SparseDesign *)> sd(sparse_design_create(cx, row_idx, col_ptr, values, n, p),
+                                                               sparse_design_destroy);
+    DevVector yv;
+    to_device_vector(cx, y, n, yv);
+    tm.stop(t_h);
+
+    // ---- init_oem: colsq, X'y (:727-806) ----
+    const size_t nb0 = 3 * (size_t)p + 1;
+    DBuf<double> b0(nb0);
+    const size_t t_c = tm.start(&cx.st.ms_colstats);
+    sparse_colstats_launch(cx, sd.get(), yv.p, b0.p);
+    tm.stop(t_c);
+    const double nd = (double)n;
+    OEM_CUDA(cudaMemcpyAsync(b0.p + 3 * (size_t)p, &nd, 8, cudaMemcpyHostToDevice, cx.stream));
+    {
+        const size_t t_ar = tm.start(&cx.st.ms_allreduce);
+        cx.all_reduce(b0.p, (int64_t)nb0);
+        tm.stop(t_ar);
+    }
+    std::vector<double> h0(nb0);
+    b0.download(h0.data(), nb0, cx.stream);
+    cx.sync();
+    const double n_tot = h0[nb0 - 1];
+    if (!(n_tot > q)) fail(OEMB200_EUNSUPPORTED, "n <= p sparse logistic branch (XWX' form, src/oem_logistic_sparse.h:504-509) is outside the hot path");
+    std::vector<double> cinv(p, 1.0);
+    if (stdz)
+        for (int j = 0; j < p; ++j) {
+            double sq = h0[2 * (size_t)p + j] / (n_tot - 1.0);
+            if (sq == 0.0) sq = 1.0;
+            cinv[j] = 1.0 / std::sqrt(sq);
+        }
+    double lmax = 0.0;      // compute_lambda_zero: the X entries of XY = (X'y o colsq_inv) / n only (:808-818)
+    for (int j = 0; j < p; ++j) {
+        double v = h0[(size_t)p + j];
+        if (stdz) v *= cinv[j];
+        lmax = std::max(lmax, std::fabs(v / n_tot));
+    }
+    su.build_lambdas(s, lmax, /*logistic_fudge=*/true);
+
+    // ---- device state ----
+    std::vector<double> pf(q, 0.0);
+    for (int j = 0; j < p; ++j) pf[icpt + j] = s->penalty_factor[j];
+    const int L = su.Lmax;
+    const size_t pp2 = (size_t)p * p;
+    // per-pass bundle: [G p*p | statsW 3p | sum W, sum W^2 | statsR 3p | sum r, sum r^2]
+    const size_t nbp = pp2 + 6 * (size_t)p + 4;
+    DBuf<double> bundle(nbp);
+    double *G = bundle.p, *statsW = G + pp2, *ws = statsW + 3 * (size_t)p, *statsR = ws + 2, *rs = statsR + 3 * (size_t)p;
+    DBuf<double> d_pf(q), d_cinv(p), d_b(p), d_b0(2), d_g((size_t)p + 2), d_XY(q), d_XX((size_t)q * q), d_d(1), d_diag(p);
+    DBuf<double> d_iter(2 * (size_t)q), d_path((size_t)su.P * L * q), d_lams((size_t)su.P * L);
+    DBuf<double> d_prob(n + 2), d_res(n + 2), d_W(n + 2), d_losspart(1024);
+    DBuf<long long> d_iters_total(1);
+    DBuf<int> d_niter(1), d_lz(1);
+    d_prob.zero(cx.stream);
+    d_iters_total.zero(cx.stream);
+    d_path.zero(cx.stream);
+    d_pf.upload(pf.data(), q, cx.stream);
+    d_cinv.upload(cinv.data(), p, cx.stream);
+    {
+        std::vector<double> lam_flat((size_t)su.P * L, 0.0);
+        for (int pp = 0; pp < su.P; ++pp)
+            for (size_t i = 0; i < su.lam[pp].size() && (int)i < L; ++i) lam_flat[(size_t)pp * L + i] = su.lam[pp][i];
+        d_lams.upload(lam_flat.data(), lam_flat.size(), cx.stream);
+        cx.sync();
+    }
+    DBuf<int> g_unique, g_ptr, g_idx, g_cover;
+    DBuf<double> g_w;
+    if (su.any_group) {
+        g_unique.alloc(su.unique.size()); g_unique.upload(su.unique.data(), su.unique.size(), cx.stream);
+        g_ptr.alloc(su.ptr.size());       g_ptr.upload(su.ptr.data(), su.ptr.size(), cx.stream);
+        g_idx.alloc(std::max<size_t>(1, su.idx.size()));
+        if (!su.idx.empty()) g_idx.upload(su.idx.data(), su.idx.size(), cx.stream);
+        g_w.alloc(su.gw.size());          g_w.upload(su.gw.data(), su.gw.size(), cx.stream);
+        g_cover.alloc(q);                 g_cover.upload(su.cover.data(), q, cx.stream);
+    }
+    PinnedFlag flag;
+    ScratchHolder scratch;
+    fill_common_outputs(su, res);
+    memset(res->beta, 0, sizeof(double) * (size_t)su.P * (p + 1) * L);
+    const double *cinv_dev = stdz ? d_cinv.p : nullptr;
+    double xxdiag = 0.0, intval = 0.0;
+
+    for (int pp = 0; pp < su.P; ++pp) {
+        double *cur = d_iter.p, *nxt = d_iter.p + q;
+        OEM_CUDA(cudaMemsetAsync(cur, 0, sizeof(double) * q, cx.stream));
+        for (int i = 0; i < su.nlam_run[pp]; ++i) {
+            const bool on_lam_1 = (i == 0);
+            int it = 0;
+            bool broke = false;
+            for (it = 0; it < o->irls_maxit; ++it) {
+                bool rebuilt = false;
+                if (!(it == 0 && !on_lam_1)) {
+                    irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p);
+                    cx.st.kernel_launches += 1;
+                    const size_t t1 = tm.start(&cx.st.ms_irls_xb);
+                    sparse_xb_logistic_launch(cx, sd.get(), d_b.p, d_b0.p, yv.p, d_prob.p, d_res.p, d_W.p);
+                    tm.stop(t1);
+                    cx.st.data_passes += 1;
+                    if (cx.rank == 0 && it < n) {            // W(i) clamp, sic (:948-954)
+                        clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, it, 1e-5);
+                        cx.st.kernel_launches += 1;
+                    }
+                    sparse_gram_launch(cx, sd.get(), d_W.p, G);                                   // X'WX
+                    const size_t t2 = tm.start(&cx.st.ms_irls_xtr);
+                    sparse_colstats_launch(cx, sd.get(), d_W.p, statsW);                          // row 1: X'W
+                    vecsum_launch(cx, d_W.p, n, 0.0, ws, false);
+                    sparse_colstats_launch(cx, sd.get(), d_res.p, statsR);                        // row 1: X'(y - prob)
+                    vecsum_launch(cx, d_res.p, n, 0.0, rs, false);
+                    tm.stop(t2);
+                    if (cx.distributed()) {
+                        const size_t t_ar = tm.start(&cx.st.ms_allreduce);
+                        cx.all_reduce(bundle.p, (int64_t)nbp);
+                        tm.stop(t_ar);
+                    }
+                    if (icpt && xxdiag <= 0.0) {
+                        // fixed once, from the first X'WX: xxdiag = mean(diag(scaled X block)), intval (:485-489)
+                        diag_gather_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(G, p, d_diag.p);
+                        cx.st.kernel_launches += 1;
+                        std::vector<double> hd(p);
+                        double hws[2];
+                        d_diag.download(hd.data(), p, cx.stream);
+                        OEM_CUDA(cudaMemcpyAsync(hws, ws, 16, cudaMemcpyDeviceToHost, cx.stream));
+                        cx.sync();
+                        double tr = 0.0;
+                        for (int j = 0; j < p; ++j) tr += stdz ? (cinv[j] * hd[j]) * cinv[j] : hd[j];
+                        xxdiag = tr / p;
+                        intval = std::sqrt((xxdiag / hws[0]) / n_tot);
+                    }
+                    logit_sparse_assemble_kernel<<<(unsigned)(((size_t)q * q + 255) / 256), 256, 0, cx.stream>>>(
+                        p, icpt, G, statsW + (size_t)p, cinv_dev, intval, xxdiag, n_tot, d_XX.p);
+                    irls_pack_grad_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(statsR + (size_t)p, rs, p, d_g.p);
+                    irls_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p);
+                    cx.st.kernel_launches += 3;
+                    rebuilt = true;
+                }
+                PathProblem pr;
+                pr.q = q; pr.ngram = 1; pr.XX = d_XX.p; pr.XY = d_XY.p; pr.d = d_d.p;
+                pr.compute_eig = rebuilt; pr.eig_factor = 1.0005; pr.eig_tol = 1e-10;
+                ChainDesc c;
+                c.gram = 0; c.penalty = su.pen[pp]; c.nlam = 1; c.lam_off = 0; c.alpha = su.alpha;
+                c.gamma = su.gamma[pp]; c.tau = su.tau; c.out_off = 0;
+                pr.chains.push_back(c);
+                pr.lambdas = d_lams.p + (size_t)pp * L + i; pr.Lmax = 1; pr.pen_fact = d_pf.p;
+                pr.ngroups = su.any_group ? (int)su.unique.size() : 0;
+                pr.ngidx = su.any_group ? (int)su.idx.size() : 0;
+                pr.unique_groups = g_unique.p; pr.grp_ptr = g_ptr.p; pr.grp_idx = g_idx.p;
+                pr.group_weights = g_w.p; pr.grp_cover = g_cover.p;
+                pr.beta_init = cur; pr.beta_final = nullptr;
+                pr.maxit = o->maxit; pr.tol = o->tol;
+                pr.beta_out = nxt; pr.niter_out = d_niter.p; pr.lanczos_steps = d_lz.p;
+                pr.scratch = scratch.s;
+                const size_t t3 = tm.start(&cx.st.ms_path);
+                path_launch(cx, pr);
+                tm.stop(t3);
+                irls_stop_kernel<<<1, 256, 0, cx.stream>>>(nxt, cur, q, o->irls_tol, d_niter.p, d_iters_total.p, flag.p);
+                cx.st.kernel_launches += 1;
+                cx.sync();
+                std::swap(cur, nxt);
+                if (*flag.p) { broke = true; break; }
+            }
+            res->niter[(size_t)pp * L + i] = (broke ? it : o->irls_maxit) + 1;
+            if (icpt) {                                      // get_beta(): beta(0) *= intval, in place (:1040-1043)
+                scale_first_kernel<<<1, 1, 0, cx.stream>>>(cur, intval);
+                cx.st.kernel_launches += 1;
+            }
+            OEM_CUDA(cudaMemcpyAsync(d_path.p + ((size_t)pp * L + i) * q, cur, sizeof(double) * q, cudaMemcpyDeviceToDevice,
+                                     cx.stream));
+            if (s->compute_loss && res->loss) {
+                logistic_loss_kernel<<<1024, 256, 0, cx.stream>>>(yv.p, d_prob.p, n, d_losspart.p);
+                cx.st.kernel_launches += 1;
+                DBuf<double> tot(2);
+                vecsum_launch(cx, d_losspart.p, 1024, 0.0, tot.p, false);
+                cx.all_reduce(tot.p, 2);
+                double h[2];
+                tot.download(h, 2, cx.stream);
+                cx.sync();
+                res->loss[(size_t)pp * L + i] = h[0];
+            }
+        }
+    }
+    std::vector<double> hpath((size_t)su.P * L * q);
+    long long iters_total = 0;
+    double dval = 0.0;
     d_path.download(hpath.data(), hpath.size(), cx.stream);
     d_iters_total.download(&iters_total, 1, cx.stream);
     d_d.download(&dval, 1, cx.stream);

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include "host_common.h"
 
 namespace oemb200 {
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(256) csr_sort_rows_kernel(const int *__restric
 __global__ void __launch_bounds__(256) sparse_gram_kernel(const int *__restrict__ col_ptr, const int *__restrict__ row_idx,
                                                           const double *__restrict__ val, const int *__restrict__ row_ptr,
                                                           const int *__restrict__ csr_col, const double *__restrict__ csr_val,
-                                                          int p, int nwarps, double *__restrict__ Gpart) {
+                                                          const double *__restrict__ roww, int p, int nwarps,
+                                                          double *__restrict__ Gpart) {
     extern __shared__ double acc[];
     const int j = blockIdx.x, s = blockIdx.y, ns = gridDim.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(256) sparse_gram_kernel(const int *__restrict_
             const int t = chunk + lane;
             const bool own = t < e;
             const int i = own ? row_idx[t] : 0;
-            const double xv = own ? val[t] : 0.0;
+            const double xv = own ? (roww ? val[t] * roww[i] : val[t]) : 0.0;     // X'WX: the row weight rides on x_ij
             const int rs = own ? row_ptr[i] : 0;
             const int m = own ? row_ptr[i + 1] - rs : 0;
             int inc = m;
@@ -325,6 +327,31 @@ __global__ void sum_rows_kernel(const double *__restrict__ partial, int rows, in
     out[c] = t;
 }
 
+// ------------------------------------------------------------------------------------------------ logistic SpMV
+// eta_i = sum_k x_ik b[col_k] + *b0; prob = 1 / (1 + exp(-eta)); resid = y - prob; w = prob (1 - prob)
+// (src/oem_logistic_sparse.h:864-946).  8 lanes per row, fixed-order 3-step butterfly.
+__global__ void __launch_bounds__(256) sparse_xb_logistic_kernel(const int *__restrict__ row_ptr, const int *__restrict__ csr_col,
+                                                                 const double *__restrict__ csr_val, int n,
+                                                                 const double *__restrict__ b, const double *__restrict__ b0,
+                                                                 const double *__restrict__ y, double *__restrict__ prob,
+                                                                 double *__restrict__ resid, double *__restrict__ w) {
+    const int sub = threadIdx.x & 7;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    double e = 0.0;
+    if (i < n)
+        for (int k = row_ptr[i] + sub; k < row_ptr[i + 1]; k += 8) e = fma(csr_val[k], b[csr_col[k]], e);
+    e += __shfl_xor_sync(0xffffffffu, e, 4);
+    e += __shfl_xor_sync(0xffffffffu, e, 2);
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    if (i < n && sub == 0) {
+        e += b0 ? *b0 : 0.0;
+        const double pr = 1.0 / (1.0 + exp(-e));
+        if (prob) prob[i] = pr;
+        if (resid) resid[i] = y[i] - pr;
+        if (w) w[i] = pr * (1.0 - pr);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ driver
 // CSC slots -> CSR copy on the device, rows in ascending column order (count / scan / fill / rank-sort above)
 struct DeviceCsr {
@@ -408,6 +435,104 @@ struct CscInput {
     }
 };
 
+// The design as the kernels need it: validated CSC slots, the CSR copy, sum_i nnz(row i)^2 (route cost model)
+struct SparseDesign {
+    CscInput in;
+    DeviceCsr csr;
+    int64_t n = 0;
+    int p = 0;
+    double row_pairs = 0.0;
+};
+
+SparseDesign *sparse_design_create(Ctx &cx, const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p) {
+    std::unique_ptr<SparseDesign> sd(new SparseDesign());
+    sd->n = n; sd->p = p;
+    sd->in.load(cx, row_idx, col_ptr, values, n, p);
+    sd->csr.build(cx, sd->in.cp, sd->in.ri, sd->in.v, n, p, sd->in.nnz);
+    const int npart = 4 * cx.num_sms;
+    DBuf<double> pairs_part((size_t)npart);
+    row_pairs_kernel<<<npart, 256, 0, cx.stream>>>(sd->csr.row_ptr.p, (int)n, pairs_part.p);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+    std::vector<double> h_pairs(npart);
+    pairs_part.download(h_pairs.data(), npart, cx.stream);
+    cx.sync();
+    for (double v : h_pairs) sd->row_pairs += v;
+    return sd.release();
+}
+void sparse_design_destroy(SparseDesign *sd) { delete sd; }
+int sparse_design_nnz(const SparseDesign *sd) { return sd->in.nnz; }
+
+// stats3p[0*p + j] = sum_i x_ij, [1*p + j] = sum_i x_ij v_i, [2*p + j] = sum_i x_ij^2
+void sparse_colstats_launch(Ctx &cx, const SparseDesign *sd, const double *v, double *stats3p) {
+    csc_colstats_kernel<<<sd->p, 256, 0, cx.stream>>>(sd->in.cp, sd->in.ri, sd->in.v, v, sd->p, stats3p);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+}
+
+void sparse_xb_logistic_launch(Ctx &cx, const SparseDesign *sd, const double *b, const double *b0_dev, const double *y,
+                               double *prob, double *resid, double *w) {
+    const unsigned grid = (unsigned)((sd->n * 8 + 255) / 256);
+    sparse_xb_logistic_kernel<<<grid, 256, 0, cx.stream>>>(sd->csr.row_ptr.p, sd->csr.col.p, sd->csr.val.p, (int)sd->n, b, b0_dev, y,
+                                                          prob, resid, w);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+    cx.st.xb_launches += 1;
+}
+
+// G (p x p, column-major, full) = X' diag(roww) X; roww may be NULL.
+// Route: the sparse kernel costs sum_i nnz(row i)^2 shared-memory multiply-adds at ~8e10 / s (measured: n = 1e6,
+// p = 1000: 1.8 ms at 1 % density, 31 ms at 5 %), the dense route (scatter 2 GB row blocks into a zeroed tile, TMA / DMMA
+// Gram on each) a flat 43 ms at that shape, i.e. n p (p + 1) flops at ~2.4e13 / s all in.  From about 6 % density on the
+// dense route is cheaper (same deterministic result, different rounding).
+void sparse_gram_launch(Ctx &cx, const SparseDesign *sd, const double *roww, double *G) {
+    const int p = sd->p;
+    const int64_t n = sd->n;
+    const size_t pp2 = (size_t)p * p;
+    const char *route_env = getenv("OEMB200_SPARSE_ROUTE");       // "dense" / "sparse" force a route (tests, A/B)
+    bool dense_route = 300.0 * sd->row_pairs > (double)n * p * (p + 1.0) && p >= 64;
+    if (route_env && !strcmp(route_env, "dense")) dense_route = true;
+    if (route_env && !strcmp(route_env, "sparse")) dense_route = false;
+    if (dense_route) {
+        const int64_t align = 2 * gram_kt();
+        int64_t rows = (int64_t)((double)(1ll << 31) / (8.0 * p));
+        rows = std::max<int64_t>(align, rows / align * align);
+        rows = std::min<int64_t>(rows, (n + align - 1) / align * align);
+        DBuf<double> tile((size_t)rows * p);
+        for (int64_t r0 = 0, c = 0; r0 < n; r0 += rows, ++c) {
+            const int64_t nr = std::min(rows, n - r0);
+            tile.zero(cx.stream);
+            csc_densify_kernel<<<p, 256, 0, cx.stream>>>(sd->in.cp, sd->in.ri, sd->in.v, (int)r0, (int)(r0 + nr), (long long)rows, tile.p);
+            OEM_CUDA(cudaGetLastError());
+            cx.st.kernel_launches += 1;
+            gram_launch(cx, tile.p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, roww ? roww + r0 : nullptr, G, c > 0);
+        }
+        return;
+    }
+    int nwarps = 8;
+    while (nwarps > 1 && (size_t)nwarps * p * 8 > cx.smem_optin) nwarps >>= 1;
+    if ((size_t)nwarps * p * 8 > cx.smem_optin) fail(OEMB200_EUNSUPPORTED, "sparse: p = %d exceeds the shared-memory accumulator", p);
+    const int nsplit = std::max(1, std::min(16, (4 * cx.num_sms + p - 1) / p));
+    PhaseTimers &tm = *cx.tm;
+    const size_t t_k = tm.start(&cx.st.ms_gram);
+    DBuf<double> Gpart;
+    double *gout = G;
+    if (nsplit > 1) { Gpart.alloc((size_t)nsplit * pp2); gout = Gpart.p; }
+    const size_t smem = (size_t)nwarps * p * 8;
+    OEM_CUDA(cudaFuncSetAttribute(sparse_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparse_gram_kernel<<<dim3(p, nsplit), 256, smem, cx.stream>>>(sd->in.cp, sd->in.ri, sd->in.v, sd->csr.row_ptr.p, sd->csr.col.p,
+                                                                 sd->csr.val.p, roww, p, nwarps, gout);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+    if (nsplit > 1) {
+        sum_splits_kernel<<<(unsigned)((pp2 + 255) / 256), 256, 0, cx.stream>>>(Gpart.p, nsplit, pp2, G);
+        OEM_CUDA(cudaGetLastError());
+        cx.st.kernel_launches += 1;
+    }
+    cx.st.gram_launches += 1;
+    tm.stop(t_k);
+}
+
 // out[i + c * ldo] = b0[c] + sum_k x_ik Bt[col_k, c] (+ logistic response): one warp per row, lanes over the columns
 __global__ void __launch_bounds__(256) sparse_predict_kernel(const int *__restrict__ row_ptr, const int *__restrict__ csr_col,
                                                              const double *__restrict__ csr_val, int n,
@@ -483,13 +608,12 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
     Setup su;
     su.parse(s, q, /*scan=*/q, /*zero_w0=*/false);      // scans all of `groups` (src/oem_sparse.h:466)
 
-    // ---- inputs to the device ----
+    // ---- inputs to the device, CSC -> CSR ----
     const size_t t_h = tm.start(&cx.st.ms_h2d);
-    CscInput in;
-    in.load(cx, row_idx, col_ptr, values, n, p);
-    const int nnz = in.nnz;
-    const int *d_cp = in.cp, *d_ri = in.ri;
-    const double *d_v = in.v;
+    std::unique_ptr<SparseDesign, void (*)(SparseDesign *)> sd(sparse_design_create(cx, row_idx, col_ptr, values, n, p),
+                                                               sparse_design_destroy);
+    DBuf<int> &row_ptr = sd->csr.row_ptr, &csr_col = sd->csr.col;
+    DBuf<double> &csr_val = sd->csr.val;
     DevVector yv;
     to_device_vector(cx, y, n, yv);
     tm.stop(t_h);
@@ -503,75 +627,11 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
 
     const size_t t_c = tm.start(&cx.st.ms_colstats);
     vecsum_launch(cx, yv.p, n, 0.0, ysum, false);
-    csc_colstats_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, yv.p, p, stats);
-    OEM_CUDA(cudaGetLastError());
-    cx.st.kernel_launches += 1;
+    sparse_colstats_launch(cx, sd.get(), yv.p, stats);
     tm.stop(t_c);
 
-    // ---- CSC -> CSR ----
-    const size_t t_g = tm.start(&cx.st.ms_gram);
-    DeviceCsr csr;
-    csr.build(cx, d_cp, d_ri, d_v, n, p, nnz);
-    DBuf<int> &row_ptr = csr.row_ptr, &csr_col = csr.col;
-    DBuf<double> &csr_val = csr.val;
-    tm.stop(t_g);
-
     // ---- X'X ----
-    // Route: the sparse kernel costs sum_i nnz(row i)^2 shared-memory multiply-adds at ~8e10 / s (measured: n = 1e6,
-    // p = 1000: 1.8 ms at 1 % density, 31 ms at 5 %), the dense route (scatter 2 GB row blocks into a zeroed tile, TMA / DMMA
-    // Gram on each) a flat 43 ms at that shape, i.e. n p (p + 1) flops at ~2.4e13 / s all in.  From about 6 % density on the
-    // dense route is cheaper (same deterministic result, different rounding).
-    const int npart = 4 * cx.num_sms;
-    DBuf<double> pairs_part((size_t)npart);
-    row_pairs_kernel<<<npart, 256, 0, cx.stream>>>(row_ptr.p, (int)n, pairs_part.p);
-    OEM_CUDA(cudaGetLastError());
-    cx.st.kernel_launches += 1;
-    std::vector<double> h_pairs(npart);
-    pairs_part.download(h_pairs.data(), npart, cx.stream);
-    cx.sync();
-    double row_pairs = 0.0;
-    for (double v : h_pairs) row_pairs += v;
-    const char *route_env = getenv("OEMB200_SPARSE_ROUTE");       // "dense" / "sparse" force a route (tests, A/B)
-    bool dense_route = 300.0 * row_pairs > (double)n * p * (p + 1.0) && p >= 64;
-    if (route_env && !strcmp(route_env, "dense")) dense_route = true;
-    if (route_env && !strcmp(route_env, "sparse")) dense_route = false;
-    if (dense_route) {
-        const int64_t align = 2 * gram_kt();
-        int64_t rows = (int64_t)((double)(1ll << 31) / (8.0 * p));
-        rows = std::max<int64_t>(align, rows / align * align);
-        rows = std::min<int64_t>(rows, (n + align - 1) / align * align);
-        DBuf<double> tile((size_t)rows * p);
-        for (int64_t r0 = 0, c = 0; r0 < n; r0 += rows, ++c) {
-            const int64_t nr = std::min(rows, n - r0);
-            tile.zero(cx.stream);
-            csc_densify_kernel<<<p, 256, 0, cx.stream>>>(d_cp, d_ri, d_v, (int)r0, (int)(r0 + nr), (long long)rows, tile.p);
-            OEM_CUDA(cudaGetLastError());
-            cx.st.kernel_launches += 1;
-            gram_launch(cx, tile.p, nr, p, rows, {RowSegment{0, nr, 0}}, 1, nullptr, nullptr, G, c > 0);
-        }
-    }
-    int nwarps = 8;
-    while (nwarps > 1 && (size_t)nwarps * p * 8 > cx.smem_optin) nwarps >>= 1;
-    if ((size_t)nwarps * p * 8 > cx.smem_optin) fail(OEMB200_EUNSUPPORTED, "sparse: p = %d exceeds the shared-memory accumulator", p);
-    const int nsplit = std::max(1, std::min(16, (4 * cx.num_sms + p - 1) / p));
-    if (!dense_route) {
-        const size_t t_k = tm.start(&cx.st.ms_gram);
-        DBuf<double> Gpart;
-        double *gout = G;
-        if (nsplit > 1) { Gpart.alloc((size_t)nsplit * pp2); gout = Gpart.p; }
-        const size_t smem = (size_t)nwarps * p * 8;
-        OEM_CUDA(cudaFuncSetAttribute(sparse_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sparse_gram_kernel<<<dim3(p, nsplit), 256, smem, cx.stream>>>(d_cp, d_ri, d_v, row_ptr.p, csr_col.p, csr_val.p, p, nwarps, gout);
-        OEM_CUDA(cudaGetLastError());
-        cx.st.kernel_launches += 1;
-        if (nsplit > 1) {
-            sum_splits_kernel<<<(unsigned)((pp2 + 255) / 256), 256, 0, cx.stream>>>(Gpart.p, nsplit, pp2, G);
-            OEM_CUDA(cudaGetLastError());
-            cx.st.kernel_launches += 1;
-        }
-        cx.st.gram_launches += 1;
-        tm.stop(t_k);
-    }
+    sparse_gram_launch(cx, sd.get(), nullptr, G);
 
     const double nd = (double)n;
     OEM_CUDA(cudaMemcpyAsync(nobs, &nd, 8, cudaMemcpyHostToDevice, cx.stream));

@@ -66,6 +66,22 @@ struct DevVector { const double *p = nullptr; DBuf<double> own; };
 void to_device_matrix(Ctx &cx, const double *x, int64_t n, int p, int64_t ldx, DevMatrix &m);
 void to_device_vector(Ctx &cx, const double *v, int64_t n, DevVector &d);
 void fill_common_outputs(const Setup &su, oemb200_result *res);
+
+// ---- entry_sparse.cu: a dgCMatrix design on the device (validated CSC slots + CSR copy) and the passes over it ----
+struct SparseDesign;
+SparseDesign *sparse_design_create(Ctx &cx, const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p);
+void sparse_design_destroy(SparseDesign *sd);
+int sparse_design_nnz(const SparseDesign *sd);
+// stats3p[0*p + j] = sum_i x_ij, [1*p + j] = sum_i x_ij v_i, [2*p + j] = sum_i x_ij^2
+void sparse_colstats_launch(Ctx &cx, const SparseDesign *sd, const double *v, double *stats3p);
+// G (p x p) = X' diag(roww) X (roww may be NULL); sparse or densified-tile route by cost model
+void sparse_gram_launch(Ctx &cx, const SparseDesign *sd, const double *roww, double *G);
+// prob / resid = y - prob / w = prob (1 - prob) of eta = X b + *b0_dev (any output may be NULL)
+void sparse_xb_logistic_launch(Ctx &cx, const SparseDesign *sd, const double *b, const double *b0_dev, const double *y,
+                               double *prob, double *resid, double *w);
+
+// row-slab copy of X kept across logistic fits (owned by an oemb200_matrix handle); `rt` = rows per slab it was built with
+struct SlabCache { double *slabs = nullptr; int rt = 0; };
 void finish_stats(Ctx &cx, PhaseTimers &tm, size_t total_id, oemb200_result *res);
 
 }  // namespace oemb200

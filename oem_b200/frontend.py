@@ -171,14 +171,18 @@ def oem(x, y, family="gaussian", penalty=None, weights=(), lambda_=(), nlambda=1
     if family == "binomial" and not hasattr(y, "is_cuda"):
         if np.unique(np.asarray(y)).size > 2:
             raise ValueError("y must be a binary outcome")
-    if is_sparse and family != "gaussian":
-        raise NotImplementedError("oem(family = 'binomial') on a sparse x (oem_fit_logistic_sparse) is outside the hot path")
+    if is_sparse and family != "gaussian" and intercept and not standardize:
+        raise NotImplementedError("oem(family = 'binomial') on a sparse x with intercept = TRUE, standardize = FALSE: the reference "
+                                  "reads an uninitialised vector there (src/oem_logistic_sparse.h:880); no behaviour to reproduce")
     g, ug, gw = _groups(penalty, groups, group_weights, p,
                         explicit_intercept=(intercept and (family != "gaussian" or is_sparse)))      # R/oem.R:300-337
     lam = _lambda_list(lambda_, len(penalty))
     opts = dict(maxit=int(maxit), tol=float(tol), irls_maxit=int(irls_maxit), irls_tol=float(irls_tol), ncores=int(ncores),
                 hessian_type=hessian_type, accelerate=bool(accelerate))
-    fn = api.oem_fit_sparse if is_sparse else api.oem_fit_dense if family == "gaussian" else api.oem_fit_logistic_dense
+    if is_sparse:                                              # R/oem.R:532-553 (gaussian), 605-625 (binomial)
+        fn = api.oem_fit_sparse if family == "gaussian" else api.oem_fit_logistic_sparse
+    else:
+        fn = api.oem_fit_dense if family == "gaussian" else api.oem_fit_logistic_dense
     res = fn(x, y, family, penalty, [], g, ug, gw, lam, int(nlambda), lmr, float(alpha), gamma, float(tau), pf,
              bool(standardize), bool(intercept), bool(compute_loss), opts, comm=comm)
     return _decorate(res, penalty, n, p, family, varnames)

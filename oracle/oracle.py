@@ -813,3 +813,128 @@ def oem_fit_logistic_dense(x, y, family, penalty, weights, groups, unique_groups
         out["loss"].append(loss)
     out["d"] = d
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# oem_fit_logistic_sparse
+# ------------------------------------------------------------------------------------------
+def oem_fit_logistic_sparse(x, y, family, penalty, weights, groups, unique_groups, group_weights,
+                            lambda_, nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor,
+                            standardize_, intercept, compute_loss, opts):
+    """src/oem_logistic_sparse.cpp:30-330, src/oem_logistic_sparse.h:458-545 (compute_XtX_d_update_A), 727-1100
+    (init_oem / solve / get_beta / get_loss): dgCMatrix X, n > p branch, unweighted, the `ncores <= 1` code path.
+
+    Differences from the dense logistic solver that are restated here because they change results:
+      * compute_XtX_d_update_A() is called on EVERY IRLS data pass (no hessian.type test, :958-961), so X'WX and d are
+        rebuilt each time;
+      * the intercept column is the constant `intval`, fixed at the first pass: xxdiag = mean(diag(X-block)) of the
+        first X'WX, intval = sqrt((xxdiag / sum W) / n); XX(0,0) = xxdiag, border = (X'W o colsq_inv) * intval (:470-491);
+      * the linear predictor of the (standardize, intercept) branch adds beta(0) WITHOUT intval (:875-876) and
+        grad(0) = sum(y - prob) / n is not scaled either (:972-973);
+      * get_beta() multiplies the member beta(0) by intval in place (:1040-1043), so the next lambda warm-starts from it;
+      * lambda_max skips the intercept entry (:808-818).
+    intercept && !standardize multiplies beta by a colsq_inv that was never initialised (:880 vs :737-751): undefined in
+    the reference, rejected here."""
+    import scipy.sparse as sp
+    o = _as_opts(opts)
+    if np.asarray(weights).size:
+        raise ValueError("weights not implemented yet.")
+    if intercept and not standardize_:
+        raise NotImplementedError("oem_fit_logistic_sparse with intercept = TRUE, standardize = FALSE reads an "
+                                  "uninitialised vector in the reference (src/oem_logistic_sparse.h:880)")
+    X = sp.csc_matrix(x, dtype=np.float64)
+    Xr = sp.csr_matrix(X)
+    Y = np.asarray(y, dtype=np.float64).ravel()
+    n, p = X.shape
+    q = p + int(intercept)
+    if not n > q:
+        raise NotImplementedError("n <= p sparse logistic branch (XWX' form) is out of scope")
+    pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
+    if intercept:
+        pf = np.concatenate([[0.0], pf])
+    colsq_inv = np.ones(p)
+    if standardize_:
+        colsq = np.asarray(X.multiply(X).sum(axis=0)).ravel() / (float(n) - 1.0)
+        colsq = np.where(colsq == 0.0, 1.0, colsq)
+        colsq_inv = 1.0 / np.sqrt(colsq)
+    XY = np.zeros(q)
+    XY[q - p:] = X.T @ Y                  # XY(0) = sum(Y) * intval with intval still 0 (:768): irrelevant, XY is rebuilt
+    if standardize_:
+        XY[q - p:] *= colsq_inv
+    XY /= n
+    lmax = float(np.abs(XY[q - p:]).max())
+    lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha,
+                         logistic_fudge=True, gamma=_gamma_for(gamma, 0))
+    grp = _Groups(groups, unique_groups, group_weights, scan=q, zero_weight_for_group0=True)
+    s = _Solver(q, pf, grp, o["maxit"], o["tol"])
+    XX, A, d = None, None, None
+    xxdiag, intval = 0.0, 0.0
+    prob = np.zeros(n)
+    out = dict(beta=[], lambda_=[], niter=[], loss=[], d=None)
+    for pp, pen in enumerate(penalty):
+        lam = lams[pp]
+        L = 1 if pen == "ols" else lam.size
+        beta = np.zeros((p + 1, L), order="F")
+        niter = np.zeros(L, dtype=np.int32)
+        loss = np.full(L, 1e99)
+        s.init(pen, alpha, _gamma_for(gamma, pp), tau)
+        for i in range(L):
+            on_lam_1 = (i == 0)
+            it = 0
+            for it in range(o["irls_maxit"]):
+                beta_prev_irls = s.beta.copy()
+                if not (it == 0 and not on_lam_1):
+                    bx = s.beta[q - p:] * colsq_inv if standardize_ else s.beta[q - p:]
+                    eta = Xr @ bx + (s.beta[0] if intercept else 0.0)
+                    prob = 1.0 / (1.0 + np.exp(-eta))
+                    W = prob * (1.0 - prob)
+                    if W[it] < 1e-5:                    # sic: indexed by the IRLS counter (:948-954)
+                        W[it] = 1e-5
+                    XtWX = np.asarray((X.T @ sp.diags(W) @ X).todense())
+                    if standardize_:
+                        XtWX = colsq_inv[:, None] * XtWX * colsq_inv[None, :]
+                    XX = np.zeros((q, q))
+                    XX[q - p:, q - p:] = XtWX
+                    if intercept:
+                        cs = np.asarray(X.T @ W).ravel() * colsq_inv
+                        if xxdiag <= 0:
+                            xxdiag = float(np.diag(XtWX).mean())
+                            intval = np.sqrt((xxdiag / W.sum()) / float(n))
+                        cs = cs * intval
+                        XX[0, 1:] = cs
+                        XX[1:, 0] = cs
+                        XX[0, 0] = xxdiag
+                    XX /= n
+                    d = top_eig(XX) * 1.0005
+                    A = -XX
+                    A[np.diag_indices(q)] += d
+                    presid = Y - prob
+                    grad = np.zeros(q)
+                    grad[q - p:] = np.asarray(X.T @ presid).ravel() / float(n)
+                    if intercept:
+                        grad[0] = presid.sum() / float(n)
+                    if standardize_:
+                        grad[q - p:] *= colsq_inv
+                    XY = XX @ s.beta + grad
+                s.solve(A, XY, d, lam[i])
+                if stop_rule(s.beta, beta_prev_irls, o["irls_tol"]):
+                    break
+            else:
+                it = o["irls_maxit"]
+            niter[i] = it + 1
+            if intercept:
+                s.beta[0] *= intval                     # get_beta(): in place (:1040-1043)
+            res = s.beta.copy()
+            if standardize_:
+                res[q - p:] *= colsq_inv
+            beta[1 - int(intercept):, i] = res
+            if compute_loss:
+                ok = np.where(Y == 1, prob > 1e-5, prob <= 1.0 - 1e-5)
+                pr = np.where(Y == 1, prob, 1.0 - prob)
+                loss[i] = float(np.where(ok, np.log(1.0 / np.where(ok, pr, 1.0)), np.log(1.0 / 1e-5)).sum())
+        out["beta"].append(beta)
+        out["lambda_"].append(lam)
+        out["niter"].append(niter)
+        out["loss"].append(loss)
+    out["d"] = d
+    return out

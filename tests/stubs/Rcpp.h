@@ -70,6 +70,16 @@ struct List {
 template <typename T> T as(const Proxy &) { return T(); }
 
 struct S4 { S4(SEXP) {} Proxy slot(const char *) const { return Proxy(); } };
-template <typename T> struct XPtr { XPtr(SEXP) {} T *operator->() const { return (T *)0; } };
+template <class T> struct PreserveStorage {};
+template <typename T> void standard_delete_finalizer(T *obj) { delete obj; }
+// same template signature as Rcpp's XPtr (storage policy, finalizer)
+template <typename T, template <class> class StoragePolicy = PreserveStorage, void Finalizer(T *) = standard_delete_finalizer<T> >
+struct XPtr {
+    XPtr(SEXP) {}
+    explicit XPtr(T *, bool = true) {}
+    T *operator->() const { return (T *)0; }
+    T *get() const { return (T *)0; }
+    operator SEXP() const { return (SEXP)0; }
+};
 
 }  // namespace Rcpp

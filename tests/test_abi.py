@@ -137,6 +137,6 @@ def test_r_shim_matches_the_c_abi():
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
     src = open(shim).read()
-    for sym in ("oem_fit_dense", "oem_fit_logistic_dense", "oem_fit_sparse", "oem_fit_big", "oem_fit_fb_big", "oem_xtx",
-                "oem_xval_dense"):
+    for sym in ("oem_fit_dense", "oem_fit_logistic_dense", "oem_fit_sparse", "oem_fit_logistic_sparse", "oem_fit_big",
+                "oem_fit_fb_big", "oem_xtx", "oem_xval_dense", "oem_b200_matrix", "oem_fit_dense_h"):
         assert re.search(rf"RcppExport SEXP {sym}\(", src), sym

@@ -125,7 +125,7 @@ def test_big_oem_file_backed_ingest_rate(lib, tmp_path):
     assert isinstance(bigmat, np.memmap)
     r = fe.big_oem(bigmat, y, penalty=["lasso"], nlambda=20, gigs=0.25)
     r = fe.big_oem(bigmat, y, penalty=["lasso"], nlambda=20, gigs=0.25)          # second call: ring and pools warm
-    Xd = torch.from_numpy(np.ascontiguousarray(np.asarray(bigmat).T)).cuda().t()
+    Xd = torch.from_numpy(np.array(np.asarray(bigmat).T, order="C")).cuda().t()
     rd = lib.oem_fit_big(Xd, torch.from_numpy(y).cuda(), "gaussian", ["lasso"], [], [], [], [], [], 20, 1e-4, 1.0, 3.0, 0.5,
                          np.ones(p), True, True, False, dict(maxit=500, tol=1e-7))
     assert np.max(np.abs(r["beta"]["lasso"] - rd["beta"][0])) <= 1e-10

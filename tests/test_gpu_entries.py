@@ -179,6 +179,76 @@ def test_logit_slab_pass_matches_fp64_reference(lib, n, p):
     assert torch.equal(grad, grad2)
 
 
+def test_logistic_cuda_path_matches_independent_coordinate_descent(lib):
+    # the CUDA path itself (slab route, p = 130) against the independent coordinate-descent binomial lasso of
+    # tests/independent_cd.py at tight tolerances: agreement at 1e-7, like oem vs glmnet in the reference's README
+    from independent_cd import binomial_lasso_cd
+    X, y = binomial_problem(78, 2500, 130)
+    a = args_xy(X, y, "binomial", ["lasso"], standardize=False, intercept=True, nlambda=5, lmin_ratio=0.2,
+                opts=dict(tol=1e-13, maxit=50000, irls_tol=1e-12, irls_maxit=5000))
+    r = lib.oem_fit_logistic_dense(*a)
+    B, lam = r["beta"][0], r["lambda_"][0]
+    assert r["stats"]["ms_relayout"] > 0
+    b0, b = 0.0, np.zeros(130)
+    for i in range(1, 5):
+        b0, b, _ = binomial_lasso_cd(X, y, lam[i], b0=b0, b=b, tol=1e-12)
+        assert abs(B[0, i] - b0) <= 1e-7 and np.max(np.abs(B[1:, i] - b)) <= 1e-7
+        assert np.array_equal(B[1:, i] != 0, b != 0)
+
+
+def test_device_matrix_handle_fits_without_reupload(lib, oracle, tmp_path):
+    # oemb200_matrix_create: x is uploaded once; every *_h entry then runs with zero host -> device traffic for x
+    # (device-resident y: h2d_bytes == 0; host y: 8 n bytes), and repeated logistic fits reuse the handle's slab copy
+    import torch
+    X, y = gaussian_problem(211, 6000, 140, mean_x=0.1)
+    Xh = lib.DeviceMatrix(X)
+    assert Xh.shape == X.shape and Xh.h2d_bytes == X.nbytes
+    a = args_xy(X, y, "gaussian", ["lasso", "mcp"], nlambda=15)
+    ref = oracle.oem_fit_dense(*a)
+    a[0] = Xh
+    g1 = lib.oem_fit_dense(*a)
+    assert_same_fit(g1, ref)
+    assert g1["stats"]["h2d_bytes"] == 8 * X.shape[0]
+    a[1] = torch.from_numpy(y).cuda()
+    g2 = lib.oem_fit_dense(*a)
+    assert g2["stats"]["h2d_bytes"] == 0
+    assert all(np.array_equal(b1, b2) for b1, b2 in zip(g1["beta"], g2["beta"]))
+    assert_same_fit(lib.oem_fit_big(*a), oracle.oem_fit_big(*args_xy(X, y, "gaussian", ["lasso", "mcp"], nlambda=15)))
+    # xval + predict on the handle
+    rng = np.random.default_rng(5)
+    foldid = 1 + rng.permutation(X.shape[0]) % 4
+    xa = xval_args(X, y, ["lasso"], foldid, 4, nlambda=12)
+    refx = oracle.oem_xval_dense(*xa)
+    xa[0] = Xh
+    gx = lib.oem_xval_dense(*xa)
+    assert_same_fit(gx, refx)
+    assert np.allclose(gx["cvm"][0], refx["cvm"][0], rtol=1e-9)
+    pred = lib.predict_matrix(Xh, g1["beta"][0])
+    assert np.allclose(pred, X @ g1["beta"][0][1:] + g1["beta"][0][0], rtol=0, atol=1e-10)
+    # logistic: the first fit builds the slab copy, the second one finds it
+    Xb, yb = binomial_problem(212, 5000, 200)
+    Xbh = lib.DeviceMatrix(Xb)
+    ab = args_xy(Xb, yb, "binomial", ["lasso"], nlambda=8, lmin_ratio=5e-2)
+    refb = oracle.oem_fit_logistic_dense(*ab)
+    ab[0] = Xbh
+    l1 = lib.oem_fit_logistic_dense(*ab)
+    l2 = lib.oem_fit_logistic_dense(*ab)
+    assert_same_fit(l1, refb)
+    assert l1["stats"]["ms_relayout"] > 0 and l2["stats"]["ms_relayout"] == 0
+    assert np.array_equal(l1["beta"][0], l2["beta"][0])
+    # from a bigmemory backing file (.bk = raw column-major doubles)
+    from oem_b200 import bigmatrix
+    bk, desc = str(tmp_path / "m.bk"), str(tmp_path / "m.desc")
+    bigmatrix.write(X, bk, desc)
+    Xf = lib.DeviceMatrix(bk, shape=X.shape)
+    a[0] = Xf
+    g3 = lib.oem_fit_dense(*a)
+    assert all(np.array_equal(b1, b3) for b1, b3 in zip(g1["beta"], g3["beta"]))
+    Xf.close(); Xh.close(); Xbh.close()
+    with pytest.raises(ValueError, match="closed"):
+        lib.oem_fit_dense(*a)
+
+
 def test_errors_mirror_reference(lib):
     X, y = gaussian_problem(1, 100, 5)
     a = args_xy(X, y, "binomial", ["lasso"])

@@ -106,3 +106,48 @@ def test_xval_closed_form_at_lambda_max(lib):
     assert abs(out["cvm"][0][0] / cvm0 - 1.0) < 1e-4
     assert abs(out["cvsd"][0][0] / cvsd0 - 1.0) < 1e-3
     assert np.all(np.diff(out["lambda_"][0]) < 0) and np.argmin(out["cvm"][0]) > 0
+
+
+def test_logistic_kkt_and_null_model_at_config3_scale(lib):
+    """BASELINE configs[3] at full size (n = 2e6 x p = 1000, 16 GB; the CPU oracle cannot run it): the returned binomial-lasso
+    path must satisfy, in independent torch FP64 arithmetic on the same device-resident data,
+      * the null model at lambda_max: all slopes zero, intercept = logit(mean(y));
+      * the KKT conditions of -(1/n) loglik + lambda ||b~||_1 in the solver's (scaled) variables b~_j = b_j / w_j,
+        w_j = 1 / sqrt(sum_i x_ij^2 / (n - 1)): |w_j x_j'(y - prob) / n| <= lambda off the support, = lambda sign(b_j) on it,
+        and sum(y - prob) = 0 for the unpenalised intercept."""
+    import torch
+    n, p = 2_000_000, 1000
+    g = torch.Generator(device="cuda").manual_seed(104)
+    Xt = torch.empty((p, n), dtype=torch.float64, device="cuda")
+    for j in range(0, p, 50):
+        Xt[j:j + 50].normal_(generator=g)
+    coef = torch.tensor([.15, .15, -.15, -.15, .25], dtype=torch.float64, device="cuda")
+    eta = Xt[:5].t() @ coef
+    y = (torch.rand(n, generator=g, dtype=torch.float64, device="cuda") < torch.sigmoid(eta)).double()
+    X = Xt.t()
+    L = 12
+    r = lib.oem_fit_logistic_dense(X, y, "binomial", ["lasso"], [], [], [], [], [], L, 1e-2, 1.0, 3.0, 0.5, np.ones(p), True, True,
+                                   False, dict(maxit=2000, tol=1e-10, irls_tol=1e-8, irls_maxit=200))
+    B, lam = r["beta"][0], r["lambda_"][0]
+    st = r["stats"]
+    assert st["ms_relayout"] > 0 and st["data_passes"] > 0
+    ybar = float(y.mean())
+    assert np.all(B[1:, 0] == 0.0) and abs(B[0, 0] - np.log(ybar / (1 - ybar))) < 1e-8
+    w = 1.0 / torch.sqrt((Xt * Xt).sum(dim=1) / (n - 1.0))
+    worst = 0.0
+    for i in (3, 7, 11):
+        b = torch.from_numpy(B[1:, i].copy()).cuda()
+        prob = torch.sigmoid(X @ b + float(B[0, i]))
+        res = y - prob
+        grad = (Xt @ res) / n * w
+        act = b != 0
+        assert int(act.sum()) >= 5
+        assert abs(float(res.mean())) < 1e-7
+        on = float((grad[act] - lam[i] * torch.sign(b[act])).abs().max())
+        off = float(grad[~act].abs().max())
+        worst = max(worst, on / lam[i])
+        assert on < 2e-6 * lam[0], (i, on, lam[i])
+        assert off <= lam[i] * (1 + 1e-6), (i, off, lam[i])
+    gbs = 8.0 * n * p * st["data_passes"] / (st["ms_irls_xb"] / 1e3) / 1e9
+    print(f"configs[3]-scale logistic: {st['data_passes']} data passes, {st['ms_irls_xb'] / st['data_passes']:.3f} ms each "
+          f"({gbs:.0f} GB/s algorithmic), worst KKT residual on the support = {worst:.2e} x lambda")

@@ -100,8 +100,8 @@ def test_sparse_frontend_and_errors(lib, oracle):
                                 3.0, 0.5, np.ones(40), True, True, False, dict(maxit=500, tol=1e-7))
     for i, pen in enumerate(["lasso", "grp.lasso"]):
         assert np.max(np.abs(r["beta"][pen] - ref["beta"][i])) <= 1e-8
-    with pytest.raises(NotImplementedError):
-        fe.oem(X, (y > 0).astype(float), family="binomial", penalty="lasso")
+    with pytest.raises(NotImplementedError, match="uninitialised"):      # the one combination the reference leaves undefined
+        fe.oem(X, (y > 0).astype(float), family="binomial", penalty="lasso", standardize=False)
     Xw, yw = sparse_problem(3, 30, 40, density=0.3)
     with pytest.raises(lib.OemB200Error) as ei:           # n <= p: XX' branch
         lib.oem_fit_sparse(*args_xy(Xw, yw, "gaussian", ["lasso"]))
@@ -141,3 +141,61 @@ def test_sparse_predict(lib):
     assert np.max(np.abs(pr - (nb[0][None, :] + X @ nb[1:]))) <= 1e-12
     with pytest.raises(api.OemB200Error, match="columns"):
         api.predict_matrix(X, B[:-2])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# oem_fit_logistic_sparse (src/oem_logistic_sparse.cpp:30): the three flag combinations the reference defines
+# ------------------------------------------------------------------------------------------------------------------
+def _sparse_binomial(seed, n, p, density):
+    X, _ = sparse_problem(seed, n, p, density=density)
+    rng = np.random.default_rng(seed + 1)
+    b = np.zeros(p)
+    b[:min(6, p)] = [1.0, -1.0, 0.8, -0.8, 0.5, -0.5][:min(6, p)]
+    y = (rng.uniform(size=n) < 1.0 / (1.0 + np.exp(-(X @ b) + 0.3))).astype(np.float64)
+    return X, y
+
+
+@pytest.mark.parametrize("standardize,intercept", [(True, True), (True, False), (False, False)])
+def test_logistic_sparse_matches_oracle(lib, oracle, standardize, intercept):
+    X, y = _sparse_binomial(90 + 2 * standardize + intercept, 5000, 40, 0.08)
+    g, ug = _groups(40, 5, intercept)
+    a = args_xy(X, y, "binomial", ["lasso", "mcp", "grp.lasso", "scad.net"], groups=g, unique_groups=ug, alpha=0.7, nlambda=10,
+                lmin_ratio=2e-2, standardize=standardize, intercept=intercept, compute_loss=True)
+    got, ref = lib.oem_fit_logistic_sparse(*a), oracle.oem_fit_logistic_sparse(*a)
+    assert_same_fit(got, ref, tol=1e-8)
+    for lg, lr in zip(got["loss"], ref["loss"]):
+        assert np.allclose(lg[:len(lr)], lr, rtol=1e-9)
+    assert got["stats"]["gram_launches"] >= got["stats"]["data_passes"] > 0       # X'WX is rebuilt on every data pass
+
+
+@pytest.mark.parametrize("route", ["sparse", "dense"])
+def test_logistic_sparse_gram_routes_and_device_slots(lib, oracle, monkeypatch, route):
+    import torch
+    monkeypatch.setenv("OEMB200_SPARSE_ROUTE", route)
+    X, y = _sparse_binomial(97, 6000, 130, 0.03)
+    a = args_xy(X, y, "binomial", ["lasso"], nlambda=8, lmin_ratio=5e-2)
+    ref = oracle.oem_fit_logistic_sparse(*a)
+    assert_same_fit(lib.oem_fit_logistic_sparse(*a), ref, tol=1e-8)
+    a[0] = (torch.from_numpy(X.indices.astype(np.int32)).cuda(), torch.from_numpy(X.indptr.astype(np.int32)).cuda(),
+            torch.from_numpy(X.data).cuda(), X.shape)
+    a[1] = torch.from_numpy(y).cuda()
+    assert_same_fit(lib.oem_fit_logistic_sparse(*a), ref, tol=1e-8)
+
+
+def test_logistic_sparse_rejects_the_undefined_combination(lib):
+    X, y = _sparse_binomial(98, 500, 10, 0.2)
+    a = args_xy(X, y, "binomial", ["lasso"], nlambda=5, standardize=False, intercept=True)
+    with pytest.raises(lib.OemB200Error, match="uninitialised"):
+        lib.oem_fit_logistic_sparse(*a)
+    a = args_xy(X, y, "gaussian", ["lasso"], nlambda=5)
+    with pytest.raises(lib.OemB200Error, match="family"):
+        lib.oem_fit_logistic_sparse(*a)
+
+
+def test_frontend_oem_binomial_on_sparse_x(lib, oracle):
+    from oem_b200 import frontend as fe
+    X, y = _sparse_binomial(99, 4000, 30, 0.1)
+    r = fe.oem(X, y, family="binomial", penalty=["lasso"], nlambda=8, lambda_min_ratio=0.05)
+    ref = oracle.oem_fit_logistic_sparse(X, y, "binomial", ["lasso"], [], [], [], [], [[]], 8, 0.05, 1.0, 3.0, 0.5, np.ones(30),
+                                         True, True, False, dict(maxit=500, tol=1e-7, irls_maxit=100, irls_tol=1e-3))
+    assert np.max(np.abs(r["beta"]["lasso"] - ref["beta"][0])) <= 1e-8
