@@ -352,7 +352,10 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
     memset(res->beta, 0, sizeof(double) * (size_t)su.P * (p + 1) * L);
     DBuf<double> d_b, d_eta, d_l2;
     // losses of all (penalty, lambda) columns in ONE pass over X when the TMA can address it (else per-lambda sweeps)
+    // (which route a rank takes depends on its local pointer alignment; both routes end in ONE all-reduce of the same P x L
+    // vector, so ranks may differ)
     const bool loss_gemm = s->compute_loss && res->loss && !(X.ld & 1) && !(reinterpret_cast<uintptr_t>(X.p) & 15);
+    std::vector<double> loss_local((size_t)su.P * L, 0.0);
     for (int pp = 0; pp < su.P; ++pp)
         for (int i = 0; i < su.nlam_run[pp]; ++i) {
             const double *raw = &pb.h_beta[((size_t)pp * L + i) * p];
@@ -387,11 +390,10 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
                 affine_launch(cx, d_eta.p, n, 0.0, -1.0, d_eta.p);
                 axpy_launch(cx, n, 1.0, yuse, d_eta.p);
                 vecsum_launch(cx, d_eta.p, n, 0.0, d_l2.p, false);
-                cx.all_reduce(d_l2.p, 2);
                 double h[2];
                 d_l2.download(h, 2, cx.stream);
                 cx.sync();
-                res->loss[(size_t)pp * L + i] = h[1];
+                loss_local[(size_t)pp * L + i] = h[1];      // summed over ranks below, in the same one all-reduce as the GEMM route
             }
         }
     if (loss_gemm) {
@@ -416,19 +418,21 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
         db0.upload(hb0.data(), hb0.size(), cx.stream);
         std::vector<std::array<int64_t, 3>> cs{{0, n, n}};
         cvscore_launch(cx, X.p, n, p, X.ld, yuse, nullptr, 1, cs, dB.p, db0.p, nc, false, out3.p);
-        std::vector<double> h3(3 * (size_t)nc), tot(nc);
+        std::vector<double> h3(3 * (size_t)nc);
         out3.download(h3.data(), h3.size(), cx.stream);
         cx.sync();
-        for (int c = 0; c < nc; ++c) tot[c] = h3[c] * h3[nc + c];          // count * mean = sum
+        for (int c = 0; c < nc; ++c) loss_local[c] = h3[c] * h3[nc + c];   // count * mean = sum
+    }
+    if (s->compute_loss && res->loss) {
         if (cx.distributed()) {
-            DBuf<double> dt(nc);
-            dt.upload(tot.data(), nc, cx.stream);
-            cx.all_reduce(dt.p, nc);
-            dt.download(tot.data(), nc, cx.stream);
+            DBuf<double> dt(loss_local.size());
+            dt.upload(loss_local.data(), loss_local.size(), cx.stream);
+            cx.all_reduce(dt.p, (int64_t)loss_local.size());
+            dt.download(loss_local.data(), loss_local.size(), cx.stream);
             cx.sync();
         }
         for (int pp = 0; pp < su.P; ++pp)
-            for (int i = 0; i < su.nlam_run[pp]; ++i) res->loss[(size_t)pp * L + i] = tot[pp * L + i];
+            for (int i = 0; i < su.nlam_run[pp]; ++i) res->loss[(size_t)pp * L + i] = loss_local[(size_t)pp * L + i];
     }
     *res->d = pb.h_d[0];
     finish_stats(cx, tm, t_total, res);

@@ -446,8 +446,8 @@ void fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *v
     su.parse(s, q, q, /*zero_w0=*/true);
 
     const size_t t_h = tm.start(&cx.st.ms_h2d);
-    std::unique_ptr<SparseDesign, void (*)(SparseDesign *)> sd(sparse_design_create(cx, row_idx, col_ptr, values, n, p),
-                                                               sparse_design_destroy);
+    std::unique_ptr<SparseDesign, void (*)(SparseDesign *)> sd(nullptr, sparse_design_destroy);
+    collective_guard(cx, [&] { sd.reset(sparse_design_create(cx, row_idx, col_ptr, values, n, p)); });   // dgCMatrix checks are per rank
     DevVector yv;
     to_device_vector(cx, y, n, yv);
     tm.stop(t_h);

@@ -610,8 +610,8 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
 
     // ---- inputs to the device, CSC -> CSR ----
     const size_t t_h = tm.start(&cx.st.ms_h2d);
-    std::unique_ptr<SparseDesign, void (*)(SparseDesign *)> sd(sparse_design_create(cx, row_idx, col_ptr, values, n, p),
-                                                               sparse_design_destroy);
+    std::unique_ptr<SparseDesign, void (*)(SparseDesign *)> sd(nullptr, sparse_design_destroy);
+    collective_guard(cx, [&] { sd.reset(sparse_design_create(cx, row_idx, col_ptr, values, n, p)); });   // dgCMatrix checks are per rank
     DBuf<int> &row_ptr = sd->csr.row_ptr, &csr_col = sd->csr.col;
     DBuf<double> &csr_val = sd->csr.val;
     DevVector yv;

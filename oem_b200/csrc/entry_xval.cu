@@ -60,6 +60,7 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
         fold_dev = d_fold.p;
     }
     tm.stop(t_h);
+    collective_guard(cx, [&] {          // fold ids are validated per rank: agree before the first data all-reduce
     if (!fold_bucket_device(cx, fold_dev, n, F, align, d_dest.p, d_order.p, cnt, off)) {
         if (is_device_ptr(foldid)) fail(OEMB200_EUNSUPPORTED, "xval: more than 64 folds needs foldid on the host");
         std::vector<int> dest(n), order(n);
@@ -85,6 +86,7 @@ void fit_xval(const double *x, int64_t n, int p, int64_t ldx, const double *y, c
         d_order.upload(order.data(), n, cx.stream);
         cx.sync();
     }
+    });
     const int64_t npad = std::max<int64_t>(off[F], align);
     if (npad >= (1ll << 31)) fail(OEMB200_EUNSUPPORTED, "xval: more than 2^31 rows per rank; shard the rows");
     DBuf<double> Xs((size_t)npad * p), ys(npad), ws, yws;

@@ -654,7 +654,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         const double inv = 1.0 / sqrt(ss);
         for (int i = threadIdx.x; i < q; i += PK_THREADS) v[i] *= inv;
         __syncthreads();
-        double beta_prev = 0.0, theta = 0.0, lo_hint = -1e300;
+        double beta_prev = 0.0, theta = 0.0, lo_hint = -1e300, res_last = 0.0;
+        bool capped = false;
         int k = 0;
         const long long tl0 = clock64();
         long long ttri = 0;
@@ -688,7 +689,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                 theta = misc[0];
                 lo_hint = misc[2];
                 const double res = beta_k * misc[1];
+                res_last = res;
                 conv = breakdown || k >= kmax || (res <= a.eig_tol * fabs(theta));
+                // step cap reached before the Ritz value converged (q > LZ_MAX with a clustered top spectrum): an
+                // unconverged Ritz value UNDER-estimates lambda_max, and d = factor * theta is the only margin that keeps
+                // A = dI - XX positive semi-definite (1.0005 for the logistic entries), so the residual bound is added below
+                capped = !breakdown && k >= kmax && k < q && !(res <= a.eig_tol * fabs(theta));
                 __syncthreads();
             }
             if (!conv) {
@@ -701,7 +707,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                 __syncthreads();
             }
         }
-        dval = theta * a.eig_factor;
+        dval = (capped ? theta + res_last : theta) * a.eig_factor;
         if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { a.prof[4] += clock64() - tl0; a.prof[5] += ttri; a.prof[6] += k; }
         if (rank == 0 && threadIdx.x == 0) {
             a.d[team] = dval;

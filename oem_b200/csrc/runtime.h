@@ -105,6 +105,32 @@ struct DBuf {
 
 bool is_device_ptr(const void *p);
 
+// Rank-local validation in front of a collective: runs f(); in row-sharded runs the ranks then agree (one 1-value
+// all-reduce) on whether anybody failed, so that a rank with bad inputs cannot leave its peers waiting in the next
+// data all-reduce.  The failing rank rethrows its own error, the others report OEMB200_ECOMM.
+template <typename F>
+void collective_guard(Ctx &cx, F &&f) {
+    int code = 0;
+    std::string msg;
+    try {
+        f();
+    } catch (const Error &e) {
+        code = e.code;
+        msg = e.what();
+    }
+    if (cx.distributed()) {
+        DBuf<double> flag(1);
+        double h = code ? 1.0 : 0.0;
+        flag.upload(&h, 1, cx.stream);
+        cx.sync();
+        cx.all_reduce(flag.p, 1);
+        flag.download(&h, 1, cx.stream);
+        cx.sync();
+        if (h > 0.0 && !code) fail(OEMB200_ECOMM, "another rank rejected its inputs; this rank stops before the next collective");
+    }
+    if (code) throw Error(code, msg);
+}
+
 // ---------------- ingest.cu ----------------
 bool is_pinned_host(const void *p);
 // rows [0, nr) x p columns of a column-major HOST block -> device, ordered on `stream`: in place for pinned sources,

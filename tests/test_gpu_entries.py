@@ -196,6 +196,27 @@ def test_logistic_cuda_path_matches_independent_coordinate_descent(lib):
         assert np.array_equal(B[1:, i] != 0, b != 0)
 
 
+def test_top_eig_step_cap_keeps_the_majorisation_safe(lib):
+    # q > 512 (the Lanczos step cap) with a tightly clustered top spectrum: the Ritz value may not reach 1e-10 within the cap.
+    # An unconverged Ritz value under-estimates lambda_max, so the kernel adds the residual bound: the returned value must
+    # never fall below the true top eigenvalue (d = 1.0005 * it is the only margin the logistic entries have) and stay close.
+    import ctypes
+    import torch
+    from oem_b200 import api
+    q = 900
+    g = torch.Generator(device="cuda").manual_seed(9)
+    Q, _ = torch.linalg.qr(torch.randn(q, q, generator=g, dtype=torch.float64, device="cuda"))
+    ev = torch.cat([torch.rand(q - 200, generator=g, dtype=torch.float64, device="cuda") * 0.9,
+                    1.0 - 1e-7 * torch.rand(200, generator=g, dtype=torch.float64, device="cuda")])
+    XX = (Q * ev) @ Q.t()
+    XX = 0.5 * (XX + XX.t())
+    true = float(torch.linalg.eigvalsh(XX)[-1])
+    out, steps = ctypes.c_double(), ctypes.c_int()
+    api._check(api.load().oemb200_top_eig(XX.data_ptr(), q, ctypes.byref(out), ctypes.byref(steps), None))
+    assert out.value >= true * (1 - 1e-13), (out.value, true, steps.value)
+    assert out.value <= true * (1 + 1e-6), (out.value, true, steps.value)
+
+
 def test_device_matrix_handle_fits_without_reupload(lib, oracle, tmp_path):
     # oemb200_matrix_create: x is uploaded once; every *_h entry then runs with zero host -> device traffic for x
     # (device-resident y: h2d_bytes == 0; host y: 8 n bytes), and repeated logistic fits reuse the handle's slab copy
