@@ -152,6 +152,33 @@ def example_vignette_bigmat(fe):
     return {"maxdiff_big_vs_oem_lasso": _pair(d, g["maxdiff_big_vs_oem_lasso"])}
 
 
+def example_logistic_dense_vs_sparse(fe):
+    """man/oem.Rd:186-209 -> docs/reference/oem.html: the ONE number the reference prints for its binomial entries,
+    max |oem(dense, family = "binomial") - oem(sparse, family = "binomial")| = 6.647085e-05 (intercept = FALSE, grp.lasso,
+    10 lambdas, irls.tol 1e-3, tol 1e-8): oem_fit_logistic_dense (upper-bound Hessian) against oem_fit_logistic_sparse
+    (Hessian rebuilt every IRLS pass) on the same data.  true.beta and x come from the seeded R stream; xs goes through
+    Matrix::rsparsematrix and ys through rbinom, which are not restated, so a statistically equivalent stand-in (same
+    shape, density and value distribution; ys drawn with the example's own recycled probabilities) is used and only the
+    ORDER of the difference is comparable.  Returns (our max |diff|, printed value)."""
+    import scipy.sparse as sps
+    g = printed()["oem_rd"]["maxdiff_logistic_dense_vs_sparse_grp_lasso"]["values"][0]
+    r = RStream(123)
+    n_obs, n_vars = 10000, 50
+    true_beta = np.concatenate([r.runif(15, -0.25, 0.25), np.zeros(n_vars - 15)])
+    x = r.matrix_rnorm(n_obs, n_vars)
+    rng = np.random.default_rng(123)
+    xs = sps.random(2 * n_obs, n_vars, density=0.01, random_state=np.random.RandomState(123), format="csc",
+                    data_rvs=rng.standard_normal)
+    prob = 1.0 / (1.0 + np.exp(-(x @ true_beta)))
+    ys = (rng.uniform(size=2 * n_obs) < np.tile(prob, 2)).astype(np.float64)      # rbinom(n.obs * 2, 1, prob) recycles prob
+    groups = np.repeat(np.arange(1, 6), 10)
+    kw = dict(family="binomial", penalty="grp.lasso", intercept=False, nlambda=10, groups=groups, irls_tol=1e-3, tol=1e-8)
+    res_gr = fe.oem(xs.toarray(), ys, **kw)
+    res_gr_s = fe.oem(xs, ys, **kw)
+    d = float(np.max(np.abs(np.asarray(res_gr["beta"]["grp.lasso"]) - np.asarray(res_gr_s["beta"]["grp.lasso"]))))
+    return d, g
+
+
 def assert_printed(results, units=0.51):
     """|got - printed| <= `units` of the last printed digit (0.5 = correct rounding; + 2 % for the decimal -> binary
     conversion of the printed value itself)."""

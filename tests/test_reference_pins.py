@@ -34,6 +34,7 @@ def test_fixture_shape():
                                                     "xval_oem_lasso", "xval_oem_mcp")] == [100, 100, 25, 25, 25, 25]
     assert g["logLik"]["oem_lasso"]["unit"] == 1e-3
     assert g["vignette_bigmat"]["maxdiff_big_vs_oem_lasso"]["values"] == [1.534783e-05]
+    assert g["oem_rd"]["maxdiff_logistic_dense_vs_sparse_grp_lasso"]["values"] == [6.647085e-05]
 
 
 class _OracleApi:
@@ -102,7 +103,21 @@ def test_oracle_vignette_bigmat(fe_oracle):
     ex.assert_printed(ex.example_vignette_bigmat(fe_oracle))
 
 
+def test_oracle_logistic_dense_vs_sparse_order(fe_oracle):
+    # the reference's only printed binomial number (6.647085e-05): the two logistic entries differ at the IRLS tolerance
+    # level, not at rounding level and not grossly -- same order for the restated pair (inputs are a stand-in, see the example)
+    d, printed_value = ex.example_logistic_dense_vs_sparse(fe_oracle)
+    assert printed_value == 6.647085e-05
+    assert printed_value / 50 < d < printed_value * 50, d
+
+
 # ------------------------------------------------------------ GPU: the CUDA path against the same printed outputs
+@pytest.mark.gpu
+def test_gpu_logistic_dense_vs_sparse_order(fe_gpu):
+    d, printed_value = ex.example_logistic_dense_vs_sparse(fe_gpu)
+    assert printed_value / 50 < d < printed_value * 50, d
+
+
 @pytest.mark.gpu
 def test_gpu_predict_oem(fe_gpu):
     ex.assert_printed(ex.example_predict_oem(fe_gpu))

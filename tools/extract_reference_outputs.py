@@ -8,6 +8,7 @@ Sources (rendered by pkgdown / knitr from the seeded examples in man/*.Rd and th
   docs/reference/logLik.html            logLik of oem() (100 lambdas), cv.oem()'s oem fit (25), xval.oem() (25); lasso + mcp
   docs/reference/oem.xtx.html           max |oem - oem.xtx| (rounding-level identity)
   vignettes/oem_vignette.html           max |big.oem - oem| on the seeded bigmemory example
+  docs/reference/oem.html               max |dense - sparse| for the gaussian and the BINOMIAL entries (orders of magnitude)
 Only printed OUTPUT values are copied (they are data, like golden vectors), never source code.
 """
 import html
@@ -103,6 +104,15 @@ def main():
     out["vignette_bigmat"] = {
         "source": "vignettes/oem_vignette.html (vignettes/oem_vignette.Rmd:398-428)",
         "maxdiff_big_vs_oem_lasso": _entry([m.group(1)]),
+    }
+    t = example_text(f"{REF}/docs/reference/oem.html")
+    out["oem_rd"] = {
+        "source": "docs/reference/oem.html (man/oem.Rd:138-211): rsparsematrix inputs are not reproducible, orders of magnitude only",
+        "maxdiff_dense_vs_sparse_lasso": printed_after(t, "max(abs(fit$beta[[1]] - fits$beta[[1]]))"),
+        "maxdiff_dense_vs_sparse_grp_lasso": printed_after(t, "max(abs(fit$beta[[2]] - fits$beta[[2]]))"),
+        # the one number the reference prints for its binomial entries: oem_fit_logistic_dense against
+        # oem_fit_logistic_sparse on the same data (intercept = FALSE, grp.lasso, 10 lambdas, irls.tol 1e-3, tol 1e-8)
+        "maxdiff_logistic_dense_vs_sparse_grp_lasso": printed_after(t, "max(abs(res.gr$beta[[1]] - res.gr.s$beta[[1]]))"),
     }
     for k, v in out.items():
         if isinstance(v, dict):
