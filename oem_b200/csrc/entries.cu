@@ -233,6 +233,7 @@ static void fit_dense(const double *x, int64_t n, int p, int64_t ldx, const doub
     const size_t t_total = tm.start(&cx.st.ms_total);
     Setup su;
     su.parse(s, p, p, false);
+    path_check_fits(cx, p, su.P, su.Lmax, su.any_group ? (int)su.unique.size() : 0, (int)su.idx.size());
 
     const size_t t_h = tm.start(&cx.st.ms_h2d);
     DevMatrix X;

@@ -61,9 +61,10 @@ enum { MODE_SINGLE = 0, MODE_CLUSTER = 1, MODE_GLOBAL = 2 };
 struct PathScratch {
     std::vector<unsigned char> key;      // what the tables below were built from
     DBuf<ChainDev> chains;
-    DBuf<int> tptr, tidx, gflags;
+    DBuf<int> tptr, tidx;
     DBuf<double> ubuf, A;
-    DBuf<unsigned> bar;
+    DBuf<unsigned> bar;                  // [ngram barrier words | ngram x 2 x team violation flags]
+    size_t nflags = 0;
 };
 PathScratch *path_scratch_create() { return new PathScratch(); }
 void path_scratch_destroy(PathScratch *s) { delete s; }
@@ -1163,6 +1164,30 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathA
     if (NC > 1) cluster_sync_all();      // no member may exit while peers can still write its shared memory
 }
 
+// Shared memory every member of a generic path launch needs besides its slice of A: the ping-pong iterates of all the
+// team's chains, XY, per-lambda tables, the Lanczos tridiagonal, group tables.
+static size_t path_fixed_smem_bytes(int q, int max_ct, int Lmax, int ng, int ngidx) {
+    const int nvec = std::max(max_ct, 2);
+    const int q4 = (q + 3) / 4 * 4;
+    const int qs = q4 + (((4 - q4) % 16) + 16) % 16;
+    return ((size_t)2 * nvec * qs + 2 * (size_t)q + (size_t)max_ct * std::max(Lmax, 1) + ng + PK_PART * 64 + 16 +
+            3 * LZ_MAX + PK_MAXCT + 3 * PK_MAXCT + 8 + 8 * PK_MAXCT) * 8 +
+           ((size_t)7 * PK_MAXCT + 20 + (ng ? 2 * (size_t)ng + 1 + ngidx + q : 0)) * 4 + 16;
+}
+
+// Entry drivers call this BEFORE their passes over X: a beta dimension the path kernel cannot hold (p in the several
+// thousands -- the n <= p use of oem_fit_dense is where that happens) is refused up front instead of after a p x p Gram
+// has been allocated and computed.
+void path_check_fits(Ctx &cx, int q, int chains_per_gram, int Lmax, int ngroups, int ngidx) {
+    const int ct = std::max(1, std::min(chains_per_gram, PK_MAXCT));
+    if (chains_per_gram > PK_MAXCT) fail(OEMB200_EUNSUPPORTED, "path: more than %d penalties in one call", PK_MAXCT);
+    const size_t need = path_fixed_smem_bytes(q, ct, Lmax, ngroups, ngroups ? ngidx : 0);
+    if (need > cx.smem_optin)
+        fail(OEMB200_EUNSUPPORTED, "beta has %d coefficients: with %d penalties per call and %d lambdas the path kernel needs %zu bytes "
+             "of shared memory per CTA (%zu available); fit fewer penalties per call or reduce p (about %d coefficients fit)", q, ct,
+             std::max(Lmax, 1), need, cx.smem_optin, (int)((cx.smem_optin - 16000) / (8 * (2 * std::max(ct, 2) + 2))));
+}
+
 // ---------------------------------------------------------------------------------------------
 void path_launch(Ctx &cx, const PathProblem &pp) {
     const int q = pp.q, G = pp.ngram;
@@ -1268,9 +1293,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     const int ng = pp.ngroups, ngidx = ng ? pp.ngidx : 0;
     auto fixed_for = [&](int nbuf) {
         (void)nbuf;     // two ping-pong buffers in every mode
-        return ((size_t)2 * nvec * qs + 2 * (size_t)q + (size_t)max_ct * std::max(pp.Lmax, 1) + ng + PK_PART * 64 + 16 +
-                3 * LZ_MAX + PK_MAXCT + 3 * PK_MAXCT + 8 + 8 * PK_MAXCT) * 8 +
-               ((size_t)7 * PK_MAXCT + 20 + (ng ? 2 * (size_t)ng + 1 + ngidx + q : 0)) * 4 + 16;
+        return path_fixed_smem_bytes(q, max_ct, pp.Lmax, ng, ngidx);
     };
     size_t fixed_bytes = fixed_for(1);
     const size_t smem_cap = cx.smem_optin;
@@ -1291,10 +1314,19 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     }
     void *kern = mode == MODE_SINGLE ? (void *)oem_path_kernel<MODE_SINGLE>
                : mode == MODE_CLUSTER ? (void *)oem_path_kernel<MODE_CLUSTER> : (void *)oem_path_kernel<MODE_GLOBAL>;
-    OEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    // the attribute and the occupancy answer are per (kernel, device): asked once, not on every launch of an IRLS loop
+    static int per_sm_cache[3][64];
+    static bool attr_set[3][64];
+    const int dslot = cx.device & 63;
+    if (!attr_set[mode][dslot]) {
+        OEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        int ps = 0;
+        OEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, kern, PK_THREADS, smem_cap));
+        per_sm_cache[mode][dslot] = ps;
+        attr_set[mode][dslot] = true;
+    }
     if (mode == MODE_GLOBAL) {
-        int per_sm = 0;
-        OEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PK_THREADS, smem_cap));
+        const int per_sm = per_sm_cache[mode][dslot];
         const int max_ctas = std::max(1, per_sm) * cx.num_sms;
         if (G > max_ctas) fail(OEMB200_EUNSUPPORTED, "path: %d Grams exceed the %d co-resident CTAs", G, max_ctas);
         team = std::max(1, std::min(max_ctas / G, (q + 7) / 8));       // at least one 8-column MMA atom per member
@@ -1327,9 +1359,11 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         S.chains.alloc(std::max<size_t>(1, cd.size()));
         S.tptr.alloc(tptr.size());
         S.tidx.alloc(std::max<size_t>(1, tidx.size()));
-        S.bar.alloc(G);
-        S.ubuf.release(); S.gflags.release(); S.A.release();
-        if (mode == MODE_GLOBAL) { S.ubuf.alloc((size_t)G * 2 * max_ct * q); S.gflags.alloc((size_t)G * 2 * team); }
+        // barrier words and violation flags share one allocation so that one memset clears both before a launch
+        S.ubuf.release(); S.A.release();
+        S.nflags = mode == MODE_GLOBAL ? (size_t)G * 2 * team : 0;
+        S.bar.alloc((size_t)G + S.nflags);
+        if (mode == MODE_GLOBAL) S.ubuf.alloc((size_t)G * 2 * max_ct * q);
         if (!a_in_smem) S.A.alloc((size_t)G * team * cpc_pad * qs);
         if (!cd.empty()) S.chains.upload(cd.data(), cd.size(), cx.stream);
         S.tptr.upload(tptr.data(), tptr.size(), cx.stream);
@@ -1337,10 +1371,10 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         S.key = key;
     }
     DBuf<ChainDev> &d_chains = S.chains;
-    DBuf<int> &d_tptr = S.tptr, &d_tidx = S.tidx, &d_gflags = S.gflags;
+    DBuf<int> &d_tptr = S.tptr, &d_tidx = S.tidx;
     DBuf<double> &d_ubuf = S.ubuf, &d_A = S.A;
     DBuf<unsigned> &d_bar = S.bar;
-    if (mode == MODE_GLOBAL) d_gflags.zero(cx.stream);
+    int *const d_gflags_p = S.nflags ? reinterpret_cast<int *>(S.bar.p + G) : nullptr;
     d_bar.zero(cx.stream);
 
     PathArgs a;
@@ -1356,7 +1390,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     a.unique_groups = pp.unique_groups; a.grp_ptr = pp.grp_ptr; a.grp_idx = pp.grp_idx; a.grp_cover = pp.grp_cover;
     a.group_weights = pp.group_weights; a.post_scale = pp.post_scale; a.beta_init = pp.beta_init;
     a.beta_final = pp.beta_final; a.beta_out = pp.beta_out; a.niter_out = pp.niter_out;
-    a.lanczos_steps = pp.lanczos_steps; a.ubuf = d_ubuf.p; a.barriers = d_bar.p; a.gflags = d_gflags.p;
+    a.lanczos_steps = pp.lanczos_steps; a.ubuf = d_ubuf.p; a.barriers = d_bar.p; a.gflags = d_gflags_p;
 
     DBuf<long long> d_prof;
     const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;

@@ -1,6 +1,7 @@
 // runtime.cu -- device context and small runtime helpers (see runtime.h).
 #include <cstdlib>
 #include <map>
+#include <vector>
 #include <exception>
 #include "runtime.h"
 
@@ -53,6 +54,31 @@ void Ctx::finish() {
         delete tm;
         tm = new PhaseTimers(stream);
     }
+}
+
+// ---- per-thread, per-device free list of timing events ----
+namespace {
+thread_local std::map<int, std::vector<cudaEvent_t>> g_events;
+}
+cudaEvent_t event_acquire() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto &fl = g_events[dev];
+    if (!fl.empty()) {
+        cudaEvent_t e = fl.back();
+        fl.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    OEM_CUDA(cudaEventCreate(&e));
+    return e;
+}
+void event_release(cudaEvent_t e) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto &fl = g_events[dev];
+    if (fl.size() < 4096) fl.push_back(e);
+    else cudaEventDestroy(e);
 }
 
 // ---- thread-local caching allocator ----

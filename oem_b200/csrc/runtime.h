@@ -14,16 +14,22 @@ namespace oemb200 {
 
 // CUDA-event phase timer: adds elapsed ms to *acc when stopped (after a stream sync at the end
 // of the call: see PhaseTimers::collect()).
+// Timing events come from a per-thread, per-device free list (event_acquire / event_release in runtime.cu): the IRLS loop
+// of the logistic entries opens ~1000 timed phases per fit, and a cudaEventCreate / cudaEventDestroy pair per phase boundary
+// was a measurable part of the host-bound gap between its small kernels.
+cudaEvent_t event_acquire();
+void event_release(cudaEvent_t e);
+
 struct PhaseTimers {
     struct Rec { cudaEvent_t a, b; double *acc; };
     std::vector<Rec> recs;
     cudaStream_t s;
     explicit PhaseTimers(cudaStream_t s_) : s(s_) {}
     PhaseTimers(const PhaseTimers &) = delete;
-    ~PhaseTimers() { for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
+    ~PhaseTimers() { for (auto &r : recs) { event_release(r.a); event_release(r.b); } }
     size_t start(double *acc) {
         Rec r; r.acc = acc;
-        OEM_CUDA(cudaEventCreate(&r.a)); OEM_CUDA(cudaEventCreate(&r.b));
+        r.a = event_acquire(); r.b = event_acquire();
         OEM_CUDA(cudaEventRecord(r.a, s));
         recs.push_back(r);
         return recs.size() - 1;
@@ -214,6 +220,8 @@ struct PathProblem {
     PathScratch *scratch = nullptr;   // optional, see above
 };
 void path_launch(Ctx &cx, const PathProblem &pp);
+// throws OEMB200_EUNSUPPORTED if a beta of dimension q (chains_per_gram penalties, Lmax lambdas) cannot be held by the path kernel
+void path_check_fits(Ctx &cx, int q, int chains_per_gram, int Lmax, int ngroups, int ngidx);
 
 // ---------------- assemble.cu ----------------
 // oem_big / logistic / xval convention: explicit intercept border, uncentred scaling.

@@ -217,6 +217,21 @@ def test_top_eig_step_cap_keeps_the_majorisation_safe(lib):
     assert out.value <= true * (1 + 1e-6), (out.value, true, steps.value)
 
 
+def test_wide_p_is_refused_up_front(lib):
+    # n <= p is served by the p x p Gram route; a p the path kernel cannot hold must fail cleanly BEFORE the Gram is
+    # allocated (status 4, a message that says what fits), not with an out-of-memory or a launch error afterwards
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.normal(size=(50, 9000)))
+    y = rng.normal(size=50)
+    a = args_xy(X, y, "gaussian", ["lasso", "mcp", "scad"], nlambda=5)
+    with pytest.raises(lib.OemB200Error, match="coefficients") as ei:
+        lib.oem_fit_dense(*a)
+    assert ei.value.code == 4
+    X = np.asfortranarray(rng.normal(size=(60, 2500)))            # wide but within the limit: the n <= p branch works
+    got = lib.oem_fit_dense(*args_xy(X, rng.normal(size=60), "gaussian", ["lasso"], nlambda=5, lmin_ratio=0.5))
+    assert got["beta"][0].shape == (2501, 5)
+
+
 def test_device_matrix_handle_fits_without_reupload(lib, oracle, tmp_path):
     # oemb200_matrix_create: x is uploaded once; every *_h entry then runs with zero host -> device traffic for x
     # (device-resident y: h2d_bytes == 0; host y: 8 n bytes), and repeated logistic fits reuse the handle's slab copy
