@@ -570,7 +570,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         const int j = c0 + jl;
         double *dst = Amine + (size_t)jl * qs;
         const double *src = XXg + (size_t)j * q;
-        for (int i = lane; i < qs; i += 32) dst[i] = (j < c1 && i < q) ? src[i] : 0.0;
+        // eight loads in flight per lane: one L2 round trip per 256 rows instead of one per 32 (this copy was ~10 us of
+        // every launch of the logistic inner loop at q = 1001)
+        for (int i0 = lane; i0 < qs; i0 += 32 * 8) {
+            double tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 32 * u;
+                tmp[u] = (j < c1 && i < q) ? __ldg(src + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 32 * u;
+                if (i < qs) dst[i] = tmp[u];
+            }
+        }
     }
     for (int e = threadIdx.x; e < 2 * nvec * qs; e += PK_THREADS) B0[e] = 0.0;
     for (int j = threadIdx.x; j < q; j += PK_THREADS) {
@@ -1330,6 +1344,10 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         const int max_ctas = std::max(1, per_sm) * cx.num_sms;
         if (G > max_ctas) fail(OEMB200_EUNSUPPORTED, "path: %d Grams exceed the %d co-resident CTAs", G, max_ctas);
         team = std::max(1, std::min(max_ctas / G, (q + 7) / 8));       // at least one 8-column MMA atom per member
+        if (const char *e = getenv("OEMB200_PATH_MIN_CPC")) {          // experiment: fewer, fatter members (exchange traffic ~ team size)
+            const int mc = std::max(8, atoi(e));
+            team = std::max(1, std::min(team, (q + mc - 1) / mc));
+        }
     }
     int cpc = (q + team - 1) / team;
     if (mode == MODE_GLOBAL) {
