@@ -102,7 +102,6 @@ struct oemb200_comm {
     bool p2p = false;
     void *mailbox_base = nullptr;                       // local allocation (cudaMalloc): data then flags
     void *peer_base[oemb200::P2P_MAX_WORLD] = {};       // every rank's allocation mapped here (own entry = mailbox_base)
-    unsigned long long epoch = 0;                       // collectives issued so far (same on every rank)
     int64_t calls_nccl = 0, calls_p2p = 0;
 };
 
@@ -111,13 +110,15 @@ namespace oemb200 {
 namespace {
 constexpr size_t kSlotDoubles = (size_t)OEMB200_P2P_MAX_DOUBLES;
 inline size_t mailbox_data_bytes(int world) { return 2 * (size_t)world * kSlotDoubles * 8; }
-inline size_t mailbox_total_bytes(int world) { return mailbox_data_bytes(world) + 2 * (size_t)P2P_MAX_WORLD * 8; }
+// data | 2 x 16 flags | this rank's own epoch counter (never written by peers)
+inline size_t mailbox_total_bytes(int world) { return mailbox_data_bytes(world) + 2 * (size_t)P2P_MAX_WORLD * 8 + 64; }
 
 struct P2pArgs {
     double *peer_data[P2P_MAX_WORLD];
     unsigned long long *peer_flags[P2P_MAX_WORLD];
     int rank, world;
-    unsigned long long epoch;
+    unsigned long long *epoch_dev;     // this rank's count of EXECUTED collectives (skipped launches do not advance it)
+    const int *skip;                   // optional: no-op when *skip != 0 (the flag is identical on every rank)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -137,7 +138,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // buf (count doubles, 16-byte aligned when count > 1) <- sum over ranks, in rank order.  One CTA.
 __global__ void __launch_bounds__(P2P_THREADS, 1)
 p2p_allreduce_kernel(const P2pArgs a, double *__restrict__ buf, int count) {
-    const int slot = (int)(a.epoch & 1ull);
+    if (a.skip && *a.skip) return;
+    // the epoch lives on the device: ranks skip the same launches, so their counters agree, and two consecutive EXECUTED
+    // collectives always use different mailbox slots even when predicated launches were enqueued between them
+    const unsigned long long epoch = *a.epoch_dev + 1ull;
+    const int slot = (int)(epoch & 1ull);
     const size_t my_off = ((size_t)slot * a.world + a.rank) * kSlotDoubles;
     const int pairs = count >> 1;
     // 1. push: my vector into slot [epoch & 1][my rank] of every rank's mailbox (NVLink stores; own mailbox included)
@@ -150,12 +155,12 @@ p2p_allreduce_kernel(const P2pArgs a, double *__restrict__ buf, int count) {
     __threadfence_system();
     __syncthreads();
     // 2. raise my flag in every rank
-    if (threadIdx.x < a.world) st_release_sys(a.peer_flags[threadIdx.x] + slot * P2P_MAX_WORLD + a.rank, a.epoch);
+    if (threadIdx.x < a.world) st_release_sys(a.peer_flags[threadIdx.x] + slot * P2P_MAX_WORLD + a.rank, epoch);
     // 3. wait until every rank's vector of this epoch has landed here
     if (threadIdx.x < a.world) {
         const unsigned long long *f = a.peer_flags[a.rank] + slot * P2P_MAX_WORLD + threadIdx.x;
         const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(f) < a.epoch) {
+        while (ld_acquire_sys(f) < epoch) {
             if (global_timer_ns() - t0 > 30ull * 1000000000ull) __trap();      // a peer died: fail loudly instead of hanging
         }
     }
@@ -167,6 +172,7 @@ p2p_allreduce_kernel(const P2pArgs a, double *__restrict__ buf, int count) {
         for (int r = 1; r < a.world; ++r) s += __ldcg(mine + (size_t)r * kSlotDoubles + i);
         buf[i] = s;
     }
+    if (threadIdx.x == 0) *a.epoch_dev = epoch;      // read again only by the next launch on this stream
 }
 
 // Map every rank's mailbox.  Collective: the IPC handles travel through an ncclAllGather, the go / no-go decision
@@ -243,16 +249,25 @@ void finish_create(oemb200_comm *c) {
 }
 }  // namespace
 
-void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream) {
+bool comm_can_skip(const oemb200_comm *c, int64_t count) {
+    return !c || c->world <= 1 || (c->p2p && count <= OEMB200_P2P_MAX_DOUBLES);
+}
+
+void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream, const int *skip) {
     if (!c || c->world <= 1 || count <= 0) return;
-    if (c->p2p && count <= OEMB200_P2P_MAX_DOUBLES && (count == 1 || (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0)) {
+    const bool aligned = count == 1 || (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0;
+    if (skip && !(c->p2p && count <= OEMB200_P2P_MAX_DOUBLES && aligned))
+        fail(OEMB200_ECOMM, "a predicated all-reduce needs the peer-memory transport and a 16-byte aligned buffer");
+    if (c->p2p && count <= OEMB200_P2P_MAX_DOUBLES && aligned) {
         P2pArgs a;
         memset(&a, 0, sizeof a);
         for (int r = 0; r < c->world; ++r) {
             a.peer_data[r] = static_cast<double *>(c->peer_base[r]);
             a.peer_flags[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(c->peer_base[r]) + mailbox_data_bytes(c->world));
         }
-        a.rank = c->rank; a.world = c->world; a.epoch = ++c->epoch;
+        a.rank = c->rank; a.world = c->world; a.skip = skip;
+        a.epoch_dev = reinterpret_cast<unsigned long long *>(static_cast<char *>(c->mailbox_base) + mailbox_data_bytes(c->world) +
+                                                             2 * (size_t)P2P_MAX_WORLD * 8);
         p2p_allreduce_kernel<<<1, P2P_THREADS, 0, stream>>>(a, dev_buf, (int)count);
         OEM_CUDA(cudaGetLastError());
         c->calls_p2p += 1;

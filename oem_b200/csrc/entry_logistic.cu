@@ -23,7 +23,8 @@
 
 namespace oemb200 {
 
-__global__ void clamp_one_kernel(double *w, long long idx, double lo) {
+__global__ void clamp_one_kernel(double *w, long long idx, double lo, const int *skip) {
+    if (skip && *skip) return;
     if (w[idx] < lo) w[idx] = lo;
 }
 
@@ -50,7 +51,8 @@ __global__ void logistic_loss_kernel(const double *__restrict__ y, const double 
 
 // b = beta[icpt:] o colsq_inv, b0 = beta[0]: the coefficients the data pass multiplies raw X with (:875-890)
 __global__ void irls_coef_kernel(const double *__restrict__ beta, const double *__restrict__ cinv, int p, int icpt,
-                                 double *__restrict__ b, double *__restrict__ b0) {
+                                 double *__restrict__ b, double *__restrict__ b0, const int *__restrict__ skip) {
+    if (skip && *skip) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < p) b[j] = cinv ? beta[icpt + j] * cinv[j] : beta[icpt + j];
     if (j == 0) *b0 = icpt ? beta[0] : 0.0;
@@ -66,7 +68,8 @@ __global__ void irls_pack_grad_kernel(const double *__restrict__ xr, const doubl
 // XY = XX beta + grad with grad = [g0 / n, (g_j / n) o colsq_inv] (oem_logistic_dense.h:970-999).  One warp per row.
 __global__ void irls_xy_kernel(int q, int icpt, const double *__restrict__ XX, const double *__restrict__ beta,
                                const double *__restrict__ g, const double *__restrict__ cinv, double n_tot,
-                               double *__restrict__ XY) {
+                               double *__restrict__ XY, const int *__restrict__ skip) {
+    if (skip && *skip) return;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= q) return;
     const int lane = threadIdx.x & 31;
@@ -88,9 +91,13 @@ __global__ void irls_xy_kernel(int q, int icpt, const double *__restrict__ XX, c
 
 // stopRule(beta_new, beta_prev, irls_tol) (src/utils.cpp:537-549) on the device; the verdict goes to pinned host
 // memory, the inner loop's iteration count is accumulated for the statistics.  One CTA.
+// `conv` (device) is the predicate of speculatively enqueued work: once an IRLS loop has converged, every later kernel
+// of that lambda -- this one included -- returns at once, so the host may enqueue iteration it + 1 before it has read
+// iteration it's verdict.
 __global__ void irls_stop_kernel(const double *__restrict__ cur, const double *__restrict__ prev, int q, double tol,
                                  const int *__restrict__ niter, long long *__restrict__ iters_total,
-                                 volatile int *__restrict__ host_flag) {
+                                 volatile int *__restrict__ host_flag, int *__restrict__ conv) {
+    if (conv && *conv) return;
     __shared__ int bad;
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
@@ -104,15 +111,16 @@ __global__ void irls_stop_kernel(const double *__restrict__ cur, const double *_
     __syncthreads();
     if (threadIdx.x == 0) {
         *iters_total += niter[0];
+        if (conv && !bad) *conv = 1;
         *host_flag = bad ? 0 : 1;
         __threadfence_system();
     }
 }
 
 namespace {
-struct PinnedFlag {
+struct PinnedFlag {          // four verdict slots: the host reads slot (iteration & 3) after that iteration's event
     int *p = nullptr;
-    PinnedFlag() { OEM_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&p), 64, cudaHostAllocMapped)); *p = 0; }
+    PinnedFlag() { OEM_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&p), 64, cudaHostAllocMapped)); memset(p, 0, 64); }
     ~PinnedFlag() { if (p) cudaFreeHost(p); }
 };
 struct ScratchHolder {
@@ -255,23 +263,38 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     double dval = 0.0;
     const double *cinv_dev = stdz ? d_cinv.p : nullptr;
 
+    // One IRLS iteration as a chain of kernels on the stream (k = IRLS counter of this lambda).  Every kernel of the chain
+    // takes `d_conv` as its predicate, so an iteration enqueued AFTER the loop has converged costs a few empty launches.
+    DBuf<int> d_conv(1);
+    // Speculation: enqueue iteration k + 1 before reading iteration k's verdict, so the GPU never waits for the host round
+    // trip (the gap was ~100 us per iteration: 5 % of the fit on one GPU, 25 % row-sharded over eight).  Possible when every
+    // kernel of the chain can be predicated: slab route, upper-bound Hessian (the Gram launch cannot), and a cross-rank sum
+    // that runs on the peer-memory transport (an NCCL collective cannot be predicated from the device).
+    const bool speculate = slab && !o->hessian_full && cx.all_reduce_can_skip((int64_t)p + 1) &&
+                           getenv("OEMB200_IRLS_NO_SPECULATION") == nullptr;
+    cudaEvent_t ev_done[2] = {event_acquire(), event_acquire()};
+    struct EvGuard { cudaEvent_t *e; ~EvGuard() { event_release(e[0]); event_release(e[1]); } } ev_guard{ev_done};
+    long long gi = 0;                            // global IRLS iteration counter (verdict slot = gi & 3, event = gi & 1)
+
     for (int pp = 0; pp < su.P; ++pp) {
-        double *cur = d_iter.p, *nxt = d_iter.p + q;
-        OEM_CUDA(cudaMemsetAsync(cur, 0, sizeof(double) * q, cx.stream));      // init(): beta = 0, on_lam_1 = true
+        int par0 = 0;                            // d_iter.p + par0 * q holds the iterate the next iteration starts from
+        OEM_CUDA(cudaMemsetAsync(d_iter.p, 0, sizeof(double) * q, cx.stream));      // init(): beta = 0, on_lam_1 = true
         for (int i = 0; i < su.nlam_run[pp]; ++i) {
             const bool on_lam_1 = (i == 0);
-            int it = 0;
-            bool broke = false;
-            for (it = 0; it < o->irls_maxit; ++it) {
+            OEM_CUDA(cudaMemsetAsync(d_conv.p, 0, sizeof(int), cx.stream));
+            const int *skip = d_conv.p;
+
+            auto enqueue_iteration = [&](int k) {
+                double *cur = d_iter.p + (size_t)((par0 + k) & 1) * q, *nxt = d_iter.p + (size_t)((par0 + k + 1) & 1) * q;
                 bool rebuilt = false;
-                if (!(it == 0 && !on_lam_1)) {
-                    const bool need_w = (it == 0 && on_lam_1) || o->hessian_full;
-                    irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p);
+                if (!(k == 0 && !on_lam_1)) {
+                    const bool need_w = (k == 0 && on_lam_1) || o->hessian_full;
+                    irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p, skip);
                     cx.st.kernel_launches += 1;
                     if (slab) {
                         // one kernel, one HBM sweep: prob, W and the gradient sums [sum r, X'r]
                         const size_t t1 = tm.start(&cx.st.ms_irls_xb);
-                        logit_slab_launch(cx, slabs_p, n, p, d_b.p, d_b0.p, yv.p, d_prob.p, d_W.p, d_g.p);
+                        logit_slab_launch(cx, slabs_p, n, p, d_b.p, d_b0.p, yv.p, d_prob.p, d_W.p, d_g.p, skip);
                         tm.stop(t1);
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (3.0 * n + 2.0 * p);
                     } else {
@@ -281,8 +304,8 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
                         cx.st.data_passes += 1;
                     }
-                    if (cx.rank == 0 && it < n) {            // W(i) clamp, sic (oem_logistic_dense.h:953-959)
-                        clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, it, 1e-5);
+                    if (cx.rank == 0 && k < n) {            // W(i) clamp, sic (oem_logistic_dense.h:953-959)
+                        clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, k, 1e-5, skip);
                         cx.st.kernel_launches += 1;
                     }
                     if (need_w) {
@@ -315,11 +338,11 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                     }
                     if (cx.distributed()) {
                         const size_t t_ar = tm.start(&cx.st.ms_allreduce);
-                        cx.all_reduce(d_g.p, (int64_t)p + 1);
+                        cx.all_reduce(d_g.p, (int64_t)p + 1, speculate ? skip : nullptr);
                         tm.stop(t_ar);
                     }
                     // XY = XX beta + grad (:999)
-                    irls_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p);
+                    irls_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p, skip);
                     cx.st.kernel_launches += 1;
                 }
                 // inner OEM loop: one chain, one lambda, warm start (oem_logistic_dense.h:1010-1022)
@@ -339,17 +362,45 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                 pr.maxit = o->maxit; pr.tol = o->tol;
                 pr.beta_out = nxt; pr.niter_out = d_niter.p; pr.lanczos_steps = d_lz.p;
                 pr.scratch = scratch.s;
+                pr.skip = skip;
                 const size_t t3 = tm.start(&cx.st.ms_path);
                 path_launch(cx, pr);
                 tm.stop(t3);
-                irls_stop_kernel<<<1, 256, 0, cx.stream>>>(nxt, cur, q, o->irls_tol, d_niter.p, d_iters_total.p, flag.p);
+                irls_stop_kernel<<<1, 256, 0, cx.stream>>>(nxt, cur, q, o->irls_tol, d_niter.p, d_iters_total.p,
+                                                           flag.p + (gi & 3), d_conv.p);
                 cx.st.kernel_launches += 1;
-                cx.sync();                                   // the one host round trip of the IRLS iteration
-                std::swap(cur, nxt);                         // cur = the new iterate
-                if (*flag.p) { broke = true; break; }
+                OEM_CUDA(cudaEventRecord(ev_done[gi & 1], cx.stream));
+                ++gi;
+            };
+
+            int it = 0;
+            bool broke = false;
+            enqueue_iteration(0);
+            for (;;) {
+                // iteration `it` is in the stream (event (gi - 1) & 1 if nothing was enqueued after it)
+                const bool ahead = speculate && it + 1 < o->irls_maxit;
+                const oemb200_stats before = cx.st;
+                if (ahead) enqueue_iteration(it + 1);
+                const long long gi_it = gi - 1 - (ahead ? 1 : 0);
+                cx.st.host_syncs += 1;
+                OEM_CUDA(cudaEventSynchronize(ev_done[gi_it & 1]));          // the one host round trip of the IRLS iteration
+                if (flag.p[gi_it & 3]) {
+                    broke = true;
+                    if (ahead) {           // the speculative iteration found d_conv set: nothing of it ran
+                        cx.st.data_passes = before.data_passes; cx.st.xb_launches = before.xb_launches;
+                        cx.st.gemv_bytes = before.gemv_bytes; cx.st.allreduce_calls = before.allreduce_calls;
+                        cx.st.allreduce_doubles = before.allreduce_doubles;
+                    }
+                    break;
+                }
+                ++it;
+                if (it >= o->irls_maxit) { it = o->irls_maxit - 1; break; }
+                if (!ahead) enqueue_iteration(it);
             }
             res->niter[(size_t)pp * L + i] = (broke ? it : o->irls_maxit) + 1;
-            OEM_CUDA(cudaMemcpyAsync(d_path.p + ((size_t)pp * L + i) * q, cur, sizeof(double) * q, cudaMemcpyDeviceToDevice,
+            par0 = (par0 + it + 1) & 1;                      // the iterate the last EXECUTED iteration produced
+            double *fin = d_iter.p + (size_t)par0 * q;
+            OEM_CUDA(cudaMemcpyAsync(d_path.p + ((size_t)pp * L + i) * q, fin, sizeof(double) * q, cudaMemcpyDeviceToDevice,
                                      cx.stream));
             if (s->compute_loss && res->loss) {
                 logistic_loss_kernel<<<1024, 256, 0, cx.stream>>>(yv.p, d_prob.p, n, d_losspart.p);
@@ -538,14 +589,14 @@ void fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *v
             for (it = 0; it < o->irls_maxit; ++it) {
                 bool rebuilt = false;
                 if (!(it == 0 && !on_lam_1)) {
-                    irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p);
+                    irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p, nullptr);
                     cx.st.kernel_launches += 1;
                     const size_t t1 = tm.start(&cx.st.ms_irls_xb);
                     sparse_xb_logistic_launch(cx, sd.get(), d_b.p, d_b0.p, yv.p, d_prob.p, d_res.p, d_W.p);
                     tm.stop(t1);
                     cx.st.data_passes += 1;
                     if (cx.rank == 0 && it < n) {            // W(i) clamp, sic (:948-954)
-                        clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, it, 1e-5);
+                        clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, it, 1e-5, nullptr);
                         cx.st.kernel_launches += 1;
                     }
                     sparse_gram_launch(cx, sd.get(), d_W.p, G);                                   // X'WX
@@ -577,7 +628,7 @@ void fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *v
                     logit_sparse_assemble_kernel<<<(unsigned)(((size_t)q * q + 255) / 256), 256, 0, cx.stream>>>(
                         p, icpt, G, statsW + (size_t)p, cinv_dev, intval, xxdiag, n_tot, d_XX.p);
                     irls_pack_grad_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(statsR + (size_t)p, rs, p, d_g.p);
-                    irls_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p);
+                    irls_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p, nullptr);
                     cx.st.kernel_launches += 3;
                     rebuilt = true;
                 }
@@ -600,7 +651,7 @@ void fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *v
                 const size_t t3 = tm.start(&cx.st.ms_path);
                 path_launch(cx, pr);
                 tm.stop(t3);
-                irls_stop_kernel<<<1, 256, 0, cx.stream>>>(nxt, cur, q, o->irls_tol, d_niter.p, d_iters_total.p, flag.p);
+                irls_stop_kernel<<<1, 256, 0, cx.stream>>>(nxt, cur, q, o->irls_tol, d_niter.p, d_iters_total.p, flag.p, nullptr);
                 cx.st.kernel_launches += 1;
                 cx.sync();
                 std::swap(cur, nxt);

@@ -42,8 +42,10 @@ template <int RT, int NC, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 logit_slab_kernel(const double *__restrict__ slabs, long long n, int p, size_t stage_stride /* doubles */,
                   const double *__restrict__ b, const double *__restrict__ b0_ptr, const double *__restrict__ y,
-                  double *__restrict__ prob, double *__restrict__ wout, double *__restrict__ partial) {
+                  double *__restrict__ prob, double *__restrict__ wout, double *__restrict__ partial,
+                  const int *__restrict__ skip) {
     static_assert(RT == 4 || RT == 8 || RT == 16, "rows per slab");
+    if (skip && *skip) return;               // speculatively enqueued pass of an IRLS loop that has already converged
     constexpr int LOG_RT = RT == 4 ? 2 : (RT == 8 ? 3 : 4);
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -192,8 +194,9 @@ logit_slab_kernel(const double *__restrict__ slabs, long long n, int p, size_t s
 // 8th row, then a fixed-order sum of the 8 lanes: same result for a given grid on every run, ~5 us instead of the 32 us a
 // one-thread-per-column loop over ~300 rows took.
 __global__ void __launch_bounds__(256) ls_sum_partials_kernel(const double *__restrict__ partial, int nparts, int width,
-                                                              double *__restrict__ out) {
+                                                              double *__restrict__ out, const int *__restrict__ skip) {
     __shared__ double sm[8][33];
+    if (skip && *skip) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int k = blockIdx.x * 32 + tx;
     double s = 0.0;
@@ -277,7 +280,7 @@ void logit_slab_relayout(Ctx &cx, const double *X, int64_t n, int p, int64_t ld,
 
 // grad_out[0] = sum r, grad_out[1 + j] = sum_i x_ij r_i (device, p + 1 doubles); b0 is read from device memory
 void logit_slab_launch(Ctx &cx, const double *slabs, int64_t n, int p, const double *b, const double *b0_dev,
-                       const double *y, double *prob, double *w, double *grad_out) {
+                       const double *y, double *prob, double *w, double *grad_out, const int *skip) {
     const SlabShape sh = slab_shape(p);
     if (!sh.rt) fail(OEMB200_EINVAL, "slab route does not apply to p = %d", p);
     const int rt = sh.rt;
@@ -296,9 +299,10 @@ void logit_slab_launch(Ctx &cx, const double *slabs, int64_t n, int p, const dou
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)cx.num_sms * sh.ctas);
     DBuf<double> partial((size_t)grid * (p + 1));       // every CTA writes its whole row
     long long nn = n;
-    void *args[] = {(void *)&slabs, &nn, &p, (void *)&stage_stride, (void *)&b, (void *)&b0_dev, (void *)&y, &prob, &w, &partial.p};
+    void *args[] = {(void *)&slabs, &nn, &p, (void *)&stage_stride, (void *)&b, (void *)&b0_dev, (void *)&y, &prob, &w, &partial.p,
+                    (void *)&skip};
     OEM_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(sh.threads), args, smem, cx.stream));
-    ls_sum_partials_kernel<<<(p + 1 + 31) / 32, 256, 0, cx.stream>>>(partial.p, grid, p + 1, grad_out);
+    ls_sum_partials_kernel<<<(p + 1 + 31) / 32, 256, 0, cx.stream>>>(partial.p, grid, p + 1, grad_out, skip);
     OEM_CUDA(cudaGetLastError());
     cx.st.kernel_launches += 2;
     cx.st.xb_launches += 1;

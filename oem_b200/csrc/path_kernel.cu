@@ -86,6 +86,7 @@ struct PathArgs {
     unsigned *barriers;      // ngram counters, zero-initialised
     int *gflags;             // ngram x 2 x team_size violation masks (global mode)
     long long *prof;         // optional (debug): cycle counters of CTA 0 / thread 0
+    const int *skip;         // optional: the whole launch is a no-op when *skip != 0 (speculatively enqueued IRLS iterations)
 };
 
 __device__ __forceinline__ double pk_warp_sum(double v) {
@@ -522,6 +523,7 @@ __device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, doub
 template <int MODE>
 __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs a) {
     extern __shared__ __align__(16) double sm[];
+    if (a.skip && *a.skip) return;           // uniform over the grid: nobody reaches a barrier
     const int q = a.q, qs = a.qs;            // qs = padded vector / slice stride, = 4 (mod 16), >= roundup(q, 4)
     const int team = blockIdx.x / a.team_size, rank = blockIdx.x - team * a.team_size;
     const int c0 = min(q, rank * a.cpc), c1 = min(q, c0 + a.cpc);
@@ -1229,7 +1231,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     // ---- small coordinate-wise problems: register-resident variant (d comes from a Lanczos-only generic launch) ----
     {
         bool reg_ok = getenv("OEMB200_PATH_GENERIC") == nullptr && q <= 256 && !pp.accelerate && !pp.post_scale &&
-                      !pp.beta_init && !pp.beta_final && max_ct <= PR_MAXCT && !pp.chains.empty();
+                      !pp.beta_init && !pp.beta_final && !pp.skip && max_ct <= PR_MAXCT && !pp.chains.empty();
         for (auto &c : pp.chains) reg_ok = reg_ok && c.penalty < OEMB200_PEN_GRP_LASSO;
         const int NC = q <= 128 ? 1 : (q + 31) / 32;
         const int QP = q <= 128 ? 128 : 256;
@@ -1409,6 +1411,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     a.group_weights = pp.group_weights; a.post_scale = pp.post_scale; a.beta_init = pp.beta_init;
     a.beta_final = pp.beta_final; a.beta_out = pp.beta_out; a.niter_out = pp.niter_out;
     a.lanczos_steps = pp.lanczos_steps; a.ubuf = d_ubuf.p; a.barriers = d_bar.p; a.gflags = d_gflags_p;
+    a.skip = pp.skip;
 
     DBuf<long long> d_prof;
     const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;

@@ -150,10 +150,16 @@ void pool_release_all() {
     }
 }
 
-void Ctx::all_reduce(double *dev_buf, int64_t count) {
+bool Ctx::all_reduce_can_skip(int64_t count) const {
+    if (comm) return comm_can_skip(comm, count);
+    return allreduce == nullptr;
+}
+
+void Ctx::all_reduce(double *dev_buf, int64_t count, const int *skip) {
     if (comm) {
-        comm_all_reduce(comm, dev_buf, count, stream);
+        comm_all_reduce(comm, dev_buf, count, stream, skip);
     } else if (allreduce) {
+        if (skip) fail(OEMB200_ECOMM, "a predicated all-reduce needs the in-library peer-memory transport");
         const int rc = allreduce(dev_buf, count, stream, allreduce_ctx);
         if (rc != 0) fail(OEMB200_ECOMM, "all-reduce callback failed with code %d", rc);
     } else {

@@ -62,7 +62,8 @@ struct Ctx {
     void sync() { st.host_syncs += 1; OEM_CUDA(cudaStreamSynchronize(stream)); }
     bool distributed() const { return comm != nullptr || allreduce != nullptr; }
     // in-place sum over ranks, ordered on `stream`; no-op in single-process runs
-    void all_reduce(double *dev_buf, int64_t count);
+    void all_reduce(double *dev_buf, int64_t count, const int *skip = nullptr);
+    bool all_reduce_can_skip(int64_t count) const;   // true in single-process runs and on the peer-memory transport
     void finish();                 // sync the stream, fold the event timings into st
 };
 
@@ -145,7 +146,10 @@ void h2d_block(Ctx &cx, const double *src, int64_t ldx, int64_t nr, int p, doubl
 void release_host_stager();
 
 // ---------------- comm.cu ----------------
-void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream);
+// skip (optional device flag, identical on every rank): the collective is a no-op when *skip != 0; only the peer-memory
+// transport can honour it (comm_can_skip), NCCL collectives cannot be predicated from the device
+void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream, const int *skip = nullptr);
+bool comm_can_skip(const oemb200_comm *c, int64_t count);
 
 // ---------------- gram_syrk.cu ----------------
 struct RowSegment { int64_t row0, row1; int out; };   // rows [row0,row1) accumulate into Gram #out
@@ -218,6 +222,7 @@ struct PathProblem {
     int *niter_out = nullptr;      // device, nchains x Lmax
     int *lanczos_steps = nullptr;  // device, ngram (may be NULL)
     PathScratch *scratch = nullptr;   // optional, see above
+    const int *skip = nullptr;        // optional device flag: the launch does nothing when it is non-zero
 };
 void path_launch(Ctx &cx, const PathProblem &pp);
 // throws OEMB200_EUNSUPPORTED if a beta of dimension q (chains_per_gram penalties, Lmax lambdas) cannot be held by the path kernel
@@ -246,8 +251,9 @@ int logit_slab_rows(int p);                       // rows per slab (0: the slab 
 size_t logit_slab_doubles(int64_t n, int p);      // size of the re-laid-out copy
 void logit_slab_relayout(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, double *slabs);
 // one pass over the slabs: prob, w (may be NULL), grad_out[0] = sum (y - prob), grad_out[1 + j] = sum_i x_ij (y_i - prob_i)
+// skip (optional device flag): the pass does nothing and leaves every output untouched when *skip != 0
 void logit_slab_launch(Ctx &cx, const double *slabs, int64_t n, int p, const double *b, const double *b0_dev,
-                       const double *y, double *prob, double *w, double *grad_out);
+                       const double *y, double *prob, double *w, double *grad_out, const int *skip = nullptr);
 
 // ---------------- cvscore.cu ----------------
 // order[i]: for every tile of fold_gather_tile_rows() source rows, the tile-local row indices grouped by fold

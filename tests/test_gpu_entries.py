@@ -179,6 +179,24 @@ def test_logit_slab_pass_matches_fp64_reference(lib, n, p):
     assert torch.equal(grad, grad2)
 
 
+def test_logistic_speculative_iterations_change_nothing(lib, monkeypatch):
+    # the dense logistic driver enqueues IRLS iteration k + 1 before it has read iteration k's stop-rule verdict; every kernel
+    # of the chain is predicated on the device-side "converged" flag, so the speculation must be invisible in the results:
+    # same beta to the bit, same IRLS counts, same number of executed data passes as with OEMB200_IRLS_NO_SPECULATION=1
+    X, y = binomial_problem(404, 6000, 260)
+    a = args_xy(X, y, "binomial", ["lasso", "mcp"], nlambda=12, lmin_ratio=2e-2, compute_loss=True)
+    spec = lib.oem_fit_logistic_dense(*a)
+    monkeypatch.setenv("OEMB200_IRLS_NO_SPECULATION", "1")
+    plain = lib.oem_fit_logistic_dense(*a)
+    for k in range(2):
+        assert np.array_equal(spec["beta"][k], plain["beta"][k])
+        assert np.array_equal(spec["niter"][k], plain["niter"][k])
+        assert np.array_equal(spec["loss"][k], plain["loss"][k])
+    assert spec["stats"]["data_passes"] == plain["stats"]["data_passes"] > 0
+    assert spec["stats"]["total_oem_iters"] == plain["stats"]["total_oem_iters"]
+    assert spec["stats"]["kernel_launches"] > plain["stats"]["kernel_launches"]       # the predicated extra iterations were enqueued
+
+
 def test_logistic_cuda_path_matches_independent_coordinate_descent(lib):
     # the CUDA path itself (slab route, p = 130) against the independent coordinate-descent binomial lasso of
     # tests/independent_cd.py at tight tolerances: agreement at 1e-7, like oem vs glmnet in the reference's README
