@@ -238,3 +238,29 @@ def test_cv_helpers_known_answers():
     l, r, f = fe.lambda_interp(lam, [0.5, 0.75, 2.0, 0.1])
     assert l.tolist() == [1, 0, 0, 2] and r.tolist() == [1, 1, 0, 2]
     assert np.allclose(f, [1.0, 0.5, 1.0, 1.0])
+
+
+def test_bench_reference_arm_smoke(tmp_path):
+    """bench.py --impl reference (the CPU arm the driver runs next to the GPU arm) on a toy size: one JSON line with the
+    contract's keys, a MEASURED full-size fit (the toy 'full size' fits in RAM), and the BLAS thread count it actually used."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")          # what torchrun exports at nproc > 1: the arm must override it
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2",
+                          "--warmup", "1", "--rows", "40000", "--cpu-sample-rows", "8000"], capture_output=True, text=True,
+                         timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    cb = line["cpu_baseline"]
+    assert line["impl"] == "reference" and line["steps"] == 2 and cb["kind"] == "port"
+    assert cb["measured"] is True and cb["measured_full_size_steps"] == 2 and len(cb["step_seconds"]) == 2
+    assert abs(line["value"] - sum(cb["step_seconds"]) / 2) < 0.02 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert cb["cores"] == len(os.sched_getaffinity(0)) or cb["cores"] >= 1          # the pool size that was set, not the env's 1
+    if len(os.sched_getaffinity(0)) > 1:
+        assert cb["cores"] > 1
