@@ -376,7 +376,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
         # default: the library's own communicator (ncclAllReduce + one-shot NVLink peer kernel issued by the library on
         # its stream); --comm callback routes the all-reduces through torch.distributed instead
-        comm = Comm() if args.comm == "callback" else LibComm(device=local)
+        if args.comm == "callback":
+            comm = Comm()
+        else:
+            # every rank must end up with the same transport: agree on whether the in-library communicator came up
+            try:
+                comm = LibComm(device=local)
+                ok = 1.0
+            except Exception as e:                      # e.g. no libnccl.so.2 to dlopen
+                print(f"[bench] rank {rank}: in-library communicator unavailable ({e!r})", file=sys.stderr, flush=True)
+                comm, ok = None, 0.0
+            flag = torch.tensor([ok], dtype=torch.float64, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if flag.item() < 0.5:
+                if comm is not None:
+                    comm.close()
+                comm = Comm()
+                args.comm = "callback"
     api.load()
     rows = args.rows
     fp64_peak = measure_fp64_peak(torch, device)

@@ -97,10 +97,23 @@ class LibComm:
         if self.world <= 1:
             return
         uid = np.zeros(128, dtype=np.uint8)
-        if self.rank == 0:
+        on_gpu = dist.get_backend(group) == "nccl"
+        # every rank asks for an id (rank 0's is the one that is used): this proves libnccl can be loaded HERE before any
+        # rank enters a collective it could hang in; the ranks then agree on the outcome
+        err = None
+        try:
             api._check(L.oemb200_comm_unique_id(uid.ctypes.data))
+        except api.OemB200Error as e:
+            err = e
+        ok = torch.tensor([0.0 if err else 1.0], dtype=torch.float64)
+        if on_gpu:
+            ok = ok.cuda(self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if float(ok.item()) < 0.5:
+            raise RuntimeError(f"in-library communicator unavailable on at least one rank ({err or 'another rank failed'}); "
+                               "use oem_b200.dist.Comm (host-callback all-reduce) instead")
         t = torch.from_numpy(uid)
-        if dist.get_backend(group) == "nccl":
+        if on_gpu:
             t = t.cuda(self.device)
         dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         uid = t.cpu().numpy().copy()
