@@ -584,7 +584,7 @@ static void predict_entry(const double *x, int64_t n, int p, int64_t ldx, const 
 extern "C" {
 
 const char *oemb200_last_error(void) { return g_last_error.c_str(); }
-const char *oemb200_version(void) { return "oem_b200 0.1 (sm_100a)"; }
+const char *oemb200_version(void) { return "oem_b200 0.2 (sm_100a)"; }
 int oemb200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

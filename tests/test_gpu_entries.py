@@ -197,6 +197,17 @@ def test_logistic_speculative_iterations_change_nothing(lib, monkeypatch):
     assert spec["stats"]["kernel_launches"] > plain["stats"]["kernel_launches"]       # the predicated extra iterations were enqueued
 
 
+@pytest.mark.parametrize("irls_maxit", [1, 2, 3])
+def test_logistic_irls_maxit_exhausted(lib, oracle, irls_maxit):
+    # the IRLS cap cuts the (speculatively pipelined) loop short: niter reports irls_maxit + 1 where the loop did not converge,
+    # and the iterate handed to the next lambda is the one the last EXECUTED iteration produced
+    X, y = binomial_problem(405, 5000, 140)
+    a = args_xy(X, y, "binomial", ["lasso"], nlambda=8, lmin_ratio=2e-2, opts=dict(irls_maxit=irls_maxit, irls_tol=1e-9))
+    got, ref = lib.oem_fit_logistic_dense(*a), oracle.oem_fit_logistic_dense(*a)
+    assert_same_fit(got, ref, tol=1e-8)
+    assert np.array_equal(got["niter"][0], ref["niter"][0]) and got["niter"][0].max() == irls_maxit + 1
+
+
 def test_logistic_cuda_path_matches_independent_coordinate_descent(lib):
     # the CUDA path itself (slab route, p = 130) against the independent coordinate-descent binomial lasso of
     # tests/independent_cd.py at tight tolerances: agreement at 1e-7, like oem vs glmnet in the reference's README
