@@ -231,6 +231,25 @@ void cv_build_coef_launch(Ctx &cx, const double *beta_raw, const double *cinv, i
 // predict.oemfit_binomial, R/methods.R:355-358).  The store modes write pred[c * ldo + row] for c < nc.
 constexpr int EPI_MSE = 0, EPI_MAE = 1, EPI_LINK = 2, EPI_RESPONSE = 3;
 
+// one k-tile (CV_KC rows of the contraction) of a warp's 32 x (8 NAT) tile: NAT column atoms, compile-time
+template <int NAT>
+__device__ __forceinline__ void cv_ktile(double (&acc)[4][10][2], const double *__restrict__ xs, const double *__restrict__ bs,
+                                         int xbox, int offA, int offB, int t) {
+#pragma unroll
+    for (int ks = 0; ks < CV_KSTEPS; ++ks) {
+        double a[4], b[NAT];
+        const int k = ks * 4 + t;
+#pragma unroll
+        for (int ma = 0; ma < 4; ++ma) a[ma] = xs[k * xbox + offA + ma * 8];
+#pragma unroll
+        for (int na = 0; na < NAT; ++na) b[na] = bs[k * CV_BBOX + offB + na * 8];
+#pragma unroll
+        for (int ma = 0; ma < 4; ++ma)
+#pragma unroll
+            for (int na = 0; na < NAT; ++na) dmma884(acc[ma][na][0], acc[ma][na][1], a[ma], b[na]);
+    }
+}
+
 template <int EPI, int NH>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, int p, int ncld,
@@ -254,7 +273,10 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const CvItem it = items[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = NH == 2 ? warp >> 2 : warp >> 1, wn = NH == 2 ? warp & 3 : warp & 1;
+    // Warp columns.  Warps w and w + 4 share an SM sub-partition (and its FP64 tensor pipe); rotating the column index of the
+    // upper warp rows pairs a wide warp column with a narrow one on every sub-partition (see `nat` below).
+    const int wm = NH == 2 ? warp >> 2 : warp >> 1;
+    const int wn = NH == 2 ? ((warp & 3) + 2 * wm) & 3 : ((warp & 1) ^ (wm >> 1));
     const int nkt = (p + CV_KC - 1) / CV_KC;
     const int ntiles = (int)((it.row_end - it.row0 + ROWS - 1) / ROWS);
     const long long total = (long long)ntiles * nkt;
@@ -281,9 +303,20 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (threadIdx.x == 0)
         for (long long i = 0; i < CV_STAGES && i < total; ++i) issue(i);
 
+    // Column atoms (8 columns each) this warp owns.  A column block holds `a` live atoms (<= 20 per 160-column box); each box
+    // splits its atoms over its two warp columns (first gets the odd one), so the 300 columns of three penalties x 100 lambdas
+    // cost 10 / 10 / 9 / 9 atoms = 19 per sub-partition instead of the 20 of a padded 320-column tile, and a narrow last block
+    // costs what it holds.  Atoms beyond `nat` are skipped in the main loop and in every epilogue.
+    const int a_live = max(0, min(COLS / 8, (nc - col0 + 7) / 8));
+    const int box = wn >> 1;
+    const int a_box = max(0, min(20, a_live - 20 * box));
+    const int nat = (wn & 1) ? a_box / 2 : (a_box + 1) / 2;
+    const int colw = (wn & 1) ? ((a_box + 1) / 2) * 8 : 0;          // first column of this warp inside its box
     const int offA = wm * 32 + g;                         // + ma*8 + (k)*XBOX
-    const int offB = (wn & 1) * 80 + g;                   // + na*8 + (k)*CV_BBOX, box = wn >> 1
+    const int offB = colw + g;                            // + na*8 + (k)*CV_BBOX, box = wn >> 1
     double run_cnt = 0.0;
+    for (int c = threadIdx.x; c < 2 * NWM * COLS; c += CV_THREADS) red[c] = 0.0;     // columns no warp owns stay finite
+    __syncthreads();
 
     long long idx = 0;
     for (int tile = 0; tile < ntiles; ++tile) {
@@ -304,18 +337,20 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             mbar_wait(&full[s], ph);
             const double *xs = reinterpret_cast<const double *>(smem_raw + (size_t)s * STAGE_BYTES);
             const double *bs = xs + CV_KC * XBOX + (wn >> 1) * (CV_KC * CV_BBOX);
-#pragma unroll
-            for (int ks = 0; ks < CV_KSTEPS; ++ks) {
-                double a[4], b[10];
-                const int k = ks * 4 + t;
-#pragma unroll
-                for (int ma = 0; ma < 4; ++ma) a[ma] = xs[k * XBOX + offA + ma * 8];
-#pragma unroll
-                for (int na = 0; na < 10; ++na) b[na] = bs[k * CV_BBOX + offB + na * 8];
-#pragma unroll
-                for (int ma = 0; ma < 4; ++ma)
-#pragma unroll
-                    for (int na = 0; na < 10; ++na) dmma884(acc[ma][na][0], acc[ma][na][1], a[ma], b[na]);
+            // the atom count is warp-uniform: dispatch ONCE per k-tile to a straight-line loop with a compile-time count (a
+            // per-atom runtime test inside the unrolled loop cost more issue slots than the trimmed atoms saved)
+            switch (nat) {
+                case 10: cv_ktile<10>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 9:  cv_ktile<9>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 8:  cv_ktile<8>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 7:  cv_ktile<7>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 6:  cv_ktile<6>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 5:  cv_ktile<5>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 4:  cv_ktile<4>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 3:  cv_ktile<3>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 2:  cv_ktile<2>(acc, xs, bs, XBOX, offA, offB, t); break;
+                case 1:  cv_ktile<1>(acc, xs, bs, XBOX, offA, offB, t); break;
+                default: break;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
@@ -324,7 +359,7 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 issue(idx + CV_STAGES);
             }
         }
-        const int cbase = (wn >> 1) * CV_BHALF + (wn & 1) * 80 + 2 * t;      // + na*8 + {0,1}
+        const int cbase = box * CV_BHALF + colw + 2 * t;                     // + na*8 + {0,1}
         if (EPI >= EPI_LINK) {
             // ---------------- epilogue (predict): store link / response, rows of one atom are 64 contiguous bytes ----------------
 #pragma unroll
@@ -336,7 +371,7 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int c = col0 + cbase + na * 8 + h;
-                        if (c >= nc) continue;
+                        if (na >= nat || c >= nc) continue;
                         double v = acc[ma][na][h] + __ldg(b0 + (size_t)it.fold * ncld + c);
                         if (EPI == EPI_RESPONSE) v = 1.0 / (1.0 + exp(-v));
                         pred[(size_t)c * ldo + row] = v;
@@ -358,6 +393,7 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int na = 0; na < 10; ++na)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    if (na >= nat) continue;
                     const int c = cbase + na * 8 + h;
                     const double r = yv - (acc[ma][na][h] + __ldg(b0 + (size_t)it.fold * ncld + col0 + c));
                     const double tv = valid ? (MAE ? fabs(r) : r * r) * wv : 0.0;   // oem_xval_dense.cpp:389-401
@@ -377,7 +413,8 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int na = 0; na < 10; ++na)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) red[(0 * NWM + wm) * COLS + cbase + na * 8 + h] = s1[na * 2 + h];
+                for (int h = 0; h < 2; ++h)
+                    if (na < nat) red[(0 * NWM + wm) * COLS + cbase + na * 8 + h] = s1[na * 2 + h];
         }
         __syncthreads();
         const double cnt = (double)max(0ll, min((long long)ROWS, it.valid_end - trow0));
@@ -389,6 +426,7 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int na = 0; na < 10; ++na)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    if (na >= nat) continue;
                     const int c = cbase + na * 8 + h;
                     double ssum = red[c];
 #pragma unroll
@@ -414,7 +452,8 @@ cvscore_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int na = 0; na < 10; ++na)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) red[(1 * NWM + wm) * COLS + cbase + na * 8 + h] = m2[na * 2 + h];
+                for (int h = 0; h < 2; ++h)
+                    if (na < nat) red[(1 * NWM + wm) * COLS + cbase + na * 8 + h] = m2[na * 2 + h];
         }
         __syncthreads();
         // Chan merge of the tile into the running state, one thread per column
