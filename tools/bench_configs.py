@@ -65,6 +65,7 @@ def main():
     ap.add_argument("--configs", default="1,2,3,4")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="scale n (debug)")
+    ap.add_argument("--nlambda", type=int, default=100, help="lambdas per penalty for the xval config (experiments on the CV GEMM's column count)")
     a = ap.parse_args()
     cfgs = [int(c) for c in a.configs.split(",")]
     opts = dict(maxit=500, tol=1e-7)
@@ -92,11 +93,11 @@ def main():
         rng = np.random.default_rng(103)
         foldid = (1 + rng.permutation(n) % F).astype(np.int32)
         groups = np.concatenate([[0], np.repeat(np.arange(1, 51), 10)])
-        args = [X, y, "gaussian", ["lasso", "grp.lasso", "mcp"], [], groups, np.unique(groups), [], [], 100, 1e-4, 1.0, 3.0, 0.5,
+        args = [X, y, "gaussian", ["lasso", "grp.lasso", "mcp"], [], groups, np.unique(groups), [], [], a.nlambda, 1e-4, 1.0, 3.0, 0.5,
                 np.ones(p), True, True, F, foldid, False, "mse", dict(opts)]
         w, out = timed(lambda: oem_b200.oem_xval_dense(*args), a.reps)
         line("configs[2] xval.oem 10-fold lasso+grp.lasso+mcp n=1e7 p=500", w, out,
-             lambda st: {"cvscore_tflops": 2.0 * n * p * 300 / (st["ms_cvscore"] / 1e3) / 1e12,
+             lambda st: {"cvscore_tflops": 2.0 * n * p * 3 * a.nlambda / (st["ms_cvscore"] / 1e3) / 1e12,
                          "cvm_min_lasso": float(np.min(out["cvm"][0]))})
         del X, y
     if 4 in cfgs:
