@@ -146,6 +146,12 @@ typedef struct oemb200_result {
  *   every rank: oemb200_comm_create(id, rank, world, device, &comm);   opts.comm = comm;   ...fits...
  *               oemb200_comm_destroy(comm)
  * An R / C++ host that already owns an ncclComm_t wraps it with oemb200_comm_from_nccl (not owned, not destroyed).
+ *
+ * Rules: creation and destruction are collective (every rank, same order).  A communicator serves ONE stream of calls at a
+ * time -- collectives are matched across ranks by their order on that stream, and the peer-memory transport keeps its epoch
+ * counter in device memory in stream order -- so do not issue fits that share a communicator from two host threads at once.
+ * If a peer dies, the peer-memory kernel traps after 30 s instead of spinning forever (the CUDA context is then lost, like
+ * after any device-side fault).
  */
 #define OEMB200_COMM_ID_BYTES 128
 #define OEMB200_P2P_MAX_DOUBLES 8192
@@ -236,6 +242,8 @@ int oemb200_predict_sparse(const int *row_idx, const int *col_ptr, const double 
  * host -> device traffic for x.  The handle also keeps the row-slab copy the logistic entry builds on first use, so
  * repeated binomial fits skip the re-layout too.  An Rcpp shim wraps the handle in an XPtr with
  * oemb200_matrix_destroy as its finalizer, exactly like the reference passes `x@address`.
+ * A handle is immutable after creation except for that lazily built slab copy: fits on one handle may run one after the
+ * other from any thread, but not concurrently.
  * ------------------------------------------------------------------------------------------ */
 typedef struct oemb200_matrix oemb200_matrix;
 int oemb200_matrix_create(const double *x, int64_t n, int p, int64_t ldx, const oemb200_opts *opts,
