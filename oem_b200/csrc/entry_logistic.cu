@@ -100,8 +100,18 @@ __global__ void irls_xy_kernel(int q, int icpt, const double *__restrict__ XX, c
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= q) return;
     const int lane = threadIdx.x & 31;
-    double s = 0.0;
-    for (int c = lane; c < q; c += 32) s = fma(XX[(size_t)r * q + c], beta[c], s);
+    // four independent partial sums per lane: the 8 MB of XX come from L2, one dependent FMA chain per lane left the loads
+    // of a row serialised (12 us per call at q = 1001, once per IRLS data pass)
+    const double *row = XX + (size_t)r * q;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = lane;
+    for (; c + 96 < q; c += 128) {
+        const double x0 = __ldg(row + c), x1 = __ldg(row + c + 32), x2 = __ldg(row + c + 64), x3 = __ldg(row + c + 96);
+        s0 = fma(x0, beta[c], s0); s1 = fma(x1, beta[c + 32], s1);
+        s2 = fma(x2, beta[c + 64], s2); s3 = fma(x3, beta[c + 96], s3);
+    }
+    for (; c < q; c += 32) s0 = fma(__ldg(row + c), beta[c], s0);
+    double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
