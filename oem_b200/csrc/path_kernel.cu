@@ -107,23 +107,6 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     return s;
 }
 
-// One arrival counter per team.  bar.sync orders the CTA's writes before thread 0's gpu-scope
-// release; the acquire poll + bar.sync makes the other members' writes visible to the whole CTA.
-__device__ __forceinline__ void team_barrier(unsigned *ctr, unsigned &target, int team_size) {
-    __syncthreads();
-    if (team_size > 1) {
-        if (threadIdx.x == 0) {
-            target += (unsigned)team_size;
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-            unsigned v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-            } while ((int)(v - target) < 0);
-        }
-        __syncthreads();
-    }
-}
-
 // |x| > thr for thr >= 0, on the integer pipe (IEEE-754 ordering of non-negative doubles)
 __device__ __forceinline__ bool abs_gt(double x, double thr) {
     return (__double_as_longlong(x) & 0x7fffffffffffffffLL) > __double_as_longlong(thr);
@@ -295,8 +278,10 @@ __device__ __noinline__ void prox_inplace(int q, const SmemTabs &tb, int pen, do
 // per thread of the CTA) on the Sturm sign pattern (division-free scaled determinant recurrence), then the
 // backward eigenvector recurrence for the residual bound be[k-1] * |s_k| / ||s||.
 // out[0] = theta, out[1] = |s_k| / ||s||, out[2] = lower bracket;  ibe[i] = 1 / be[i].  Called by all threads.
+// `rounds` multisection rounds (each narrows the bracket 257-fold): 9 reach the last bit from any Gershgorin bracket, 3 are
+// enough for the convergence checks on the way.
 __device__ __noinline__ void tridiag_top(const double *al, const double *be, const double *ibe, int k, double lo_hint, double *out,
-                            double *red, int *ibuf) {
+                            double *red, int *ibuf, int rounds) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double lo = -1e300, hi = -1e300;
     for (int i = threadIdx.x; i < k; i += PK_THREADS) {
@@ -315,7 +300,7 @@ __device__ __noinline__ void tridiag_top(const double *al, const double *be, con
     for (int w = 0; w < PK_WARPS; ++w) { lo = fmax(lo, red[w]); hi = fmax(hi, red[8 + w]); }
     lo = fmax(lo, lo_hint);           // Ritz values grow with k (interlacing)
     hi += 1e-14 * fabs(hi) + 1e-300;
-    for (int round = 0; round < 9; ++round) {
+    for (int round = 0; round < rounds; ++round) {
         const double w = hi - lo;
         if (!(w > 2e-16 * fmax(fabs(hi), fabs(lo)))) break;      // uniform: lo / hi are identical in all threads
         const double x = lo + w * (double)(threadIdx.x + 1) / (double)(PK_THREADS + 1);
@@ -408,6 +393,30 @@ __device__ __noinline__ double prox_coord_nonzero(int kind, double u, double tp,
     return st_lasso_r(u, tp, dp, rdp);
 }
 
+// sums acc[c][*] over the 32 lanes for NCT chains at once (stage-major so the chains' shuffles overlap):
+// on return tot[c] in lane l is the total of column l / (32 / CPW)
+template <int NCT, int CPW>
+__device__ __forceinline__ void reduce_cols(double (&acc)[NCT][CPW], double (&tot)[NCT], int lane) {
+#pragma unroll
+    for (int n = CPW, off = 16; n > 1; n >>= 1, off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int c = 0; c < NCT; ++c)
+#pragma unroll
+            for (int v = 0; v < n / 2; ++v) {
+                const double keep = hi ? acc[c][v + n / 2] : acc[c][v];
+                const double send = hi ? acc[c][v] : acc[c][v + n / 2];
+                acc[c][v] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < NCT; ++c) tot[c] = acc[c][0];
+#pragma unroll
+    for (int off = 16 / CPW; off >= 1; off >>= 1)
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) tot[c] += __shfl_xor_sync(0xffffffffu, tot[c], off);
+}
+
 // ---- mat-vec on the FP64 tensor pipe with the prox / stop rule fused into its epilogue ----
 struct MvCtx {
     const double *Amine, *xy, *pf, *cpar, *gam;
@@ -416,6 +425,7 @@ struct MvCtx {
     int *violw;               // shared word: bit c set when chain c's stop rule is violated somewhere in my slice
     int q, qs, c0, c1, natm, max_ct, team_size;
     double tol;
+    long long *prof;          // debug: cycle counters (CTA 0 only)
 };
 
 template <int MODE>
@@ -429,7 +439,7 @@ __device__ __forceinline__ void mv_publish(const MvCtx &m, double *dst_local, in
 
 // Chains in `fastmask` get their coordinate-wise prox (src/oem_dense.h:527-629) and stop rule (src/utils.cpp:537-549)
 // right here, on the one member that owns column j: the published value is then the NEXT BETA, not u.
-__device__ __forceinline__ double mv_finish(const MvCtx &m, unsigned fastmask, const double *prev, int c, int j, double u) {
+__device__ __forceinline__ double mv_finish(const MvCtx &m, unsigned fastmask, const double *prev, int c, int j, double u, bool &viol) {
     if (!((fastmask >> c) & 1u)) return u;
     const double *cp = m.cpar + c * 8;
     const int kind = m.kind[c];
@@ -440,7 +450,7 @@ __device__ __forceinline__ double mv_finish(const MvCtx &m, unsigned fastmask, c
     const double pv = prev[(size_t)c * m.qs + j];
     if (__double_as_longlong(r) != __double_as_longlong(pv)) {      // identical bit patterns (0 -> 0) need no arithmetic
         const bool bc = abs_gt(r, 1e-13), bp = abs_gt(pv, 1e-13);
-        if (bc != bp || (bc && abs_gt(r - pv, m.tol * fabs(pv)))) atomicOr(m.violw, 1 << c);   // |(cur-prev)/prev| > tol
+        if (bc != bp || (bc && abs_gt(r - pv, m.tol * fabs(pv)))) viol = true;                 // |(cur-prev)/prev| > tol
     }
     return r;
 }
@@ -461,6 +471,7 @@ __device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, doub
     const int ktot = qs >> 2;                                   // k4 steps (zero padded)
     const int kper = (ktot + ksplit - 1) / ksplit;
     const int tasks = units * ksplit;
+    const long long tm0 = m.prof ? clock64() : 0;
     for (int task = warp; task < tasks; task += PK_WARPS) {
         const int unit = task / ksplit, kp = task - unit * ksplit;
         const int am = unit % m.natm, an = unit / m.natm;
@@ -494,10 +505,16 @@ __device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, doub
             const int cv = an * 8 + 2 * t;
             if (j < m.c1) {
                 const double add = add_xy ? m.xy[j] : 0.0;
-                if (cv < nv && !(inactive && inactive[cv]))
-                    mv_publish<MODE>(m, dst_local, par, cv, j, mv_finish(m, fastmask, vec, cv, j, r0 + add));
-                if (cv + 1 < nv && !(inactive && inactive[cv + 1]))
-                    mv_publish<MODE>(m, dst_local, par, cv + 1, j, mv_finish(m, fastmask, vec, cv + 1, j, r1 + add));
+                if (cv < nv && !(inactive && inactive[cv])) {
+                    bool viol = false;
+                    mv_publish<MODE>(m, dst_local, par, cv, j, mv_finish(m, fastmask, vec, cv, j, r0 + add, viol));
+                    if (viol) atomicOr(m.violw, 1 << cv);
+                }
+                if (cv + 1 < nv && !(inactive && inactive[cv + 1])) {
+                    bool viol = false;
+                    mv_publish<MODE>(m, dst_local, par, cv + 1, j, mv_finish(m, fastmask, vec, cv + 1, j, r1 + add, viol));
+                    if (viol) atomicOr(m.violw, 1 << (cv + 1));
+                }
             }
         } else {
             m.part[task * 64 + lane * 2] = r0;
@@ -505,7 +522,9 @@ __device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, doub
         }
     }
     if (ksplit > 1) {
+        const long long tm1 = m.prof ? clock64() : 0;
         __syncthreads();
+        const long long tm2 = m.prof ? clock64() : 0;
         for (int e = threadIdx.x; e < units * 64; e += PK_THREADS) {
             const int unit = e >> 6, w = e & 63;
             const int ln = w >> 1, h = w & 1;
@@ -514,14 +533,140 @@ __device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, doub
             const int am = unit % m.natm, an = unit / m.natm;
             const int j = m.c0 + am * 8 + (ln >> 2);
             const int cv = an * 8 + 2 * (ln & 3) + h;
-            if (j < m.c1 && cv < nv && !(inactive && inactive[cv]))
-                mv_publish<MODE>(m, dst_local, par, cv, j, mv_finish(m, fastmask, vec, cv, j, sacc + (add_xy ? m.xy[j] : 0.0)));
+            if (j < m.c1 && cv < nv && !(inactive && inactive[cv])) {
+                bool viol = false;
+                mv_publish<MODE>(m, dst_local, par, cv, j, mv_finish(m, fastmask, vec, cv, j, sacc + (add_xy ? m.xy[j] : 0.0), viol));
+                if (viol) atomicOr(m.violw, 1 << cv);
+            }
+        }
+        if (m.prof && threadIdx.x == 0 && add_xy) {
+            const long long tm3 = clock64();
+            m.prof[13] += tm1 - tm0; m.prof[14] += tm2 - tm1; m.prof[15] += tm3 - tm2;
         }
     }
 }
 
-template <int MODE>
+// ---- register-resident mat-vec of the global mode (8-column members, <= 4 chains, q <= 256 * RPT) ----
+// At q ~ 1000 a member owns ONE 8-column atom and the team runs 1..3 chains: a DMMA would spend 5/8..7/8 of every
+// instruction on padding vectors, its split-K partial tiles go through shared memory, and the measured mat-vec was
+// 4.2 k cycles of an 11 k-cycle iteration (K loop 2.0 k: two warps per sub-partition queueing on the DMMA pipe with a
+// dependent accumulator chain; reduce + prox + publish 2.2 k).  Here thread t keeps rows t, t + 256, ... of the 8 columns
+// in registers for the whole launch (8 * RPT doubles), an iteration reads only the iterate from shared memory
+// (conflict-free, NV * RPT loads), runs 8 * NV independent DFMA chains, reduces the 8 * NV sums with the multi-value
+// butterfly (fixed order), and ONE warp finishes: fixed-order sum over the 8 warps, + XY, coordinate-wise prox, stop
+// rule, publication of the next beta and of the member's violation mask.
+// Coordinate-wise prox without divergent branches (the lanes of the finishing warp serve different penalties).  Everything
+// that does not depend on u -- the thresholds of the region tests -- is computed BEFORE the sums arrive; afterwards the
+// region tests run on the integer pipe (abs_gt), select ONE numerator / denominator pair, and a single Markstein division
+// follows.  Same operations on the same operands as st_lasso_r / st_mcp_r / st_scad_r (v - copysign(pen, v) is v - pen
+// for v > 0 and v + pen for v < 0; |x| > t for t >= 0 is the integer comparison of the bit patterns).
+struct ProxPre {
+    double tp, thr_big, thr_mid, gpen, gm1, dp, rdp, den2, rden2, tolpv, pv;
+    int kind;
+};
+__device__ __forceinline__ double prox_select(const ProxPre &k, double u) {
+    double num = u - copysign(k.tp, u), den = k.dp, rden = k.rdp;
+    bool nz = abs_gt(u, k.tp);
+    if (k.kind == 1) { den = k.den2; rden = k.rden2; }
+    if (k.kind == 2 && abs_gt(u, k.thr_mid)) {
+        const double gp = k.gm1 * u;
+        num = gp - copysign(k.gpen, gp); den = k.den2; rden = k.rden2;
+        nz = abs_gt(gp, k.gpen);
+    }
+    if (k.kind == 3 || ((k.kind == 1 || k.kind == 2) && abs_gt(u, k.thr_big))) { num = u; den = k.dp; rden = k.rdp; nz = true; }
+    return nz ? div_r(num, den, rden) : 0.0;
+}
+
+template <int RPT, int NV>
+__device__ __forceinline__ void matvec_reg(const double (&areg)[8][RPT], const MvCtx &m, const double *vec, int *inactive,
+                                           int add_xy, unsigned fastmask, int par, int *gflag_slot) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tm0 = m.prof ? clock64() : 0;
+    double acc[NV][8];
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c][j] = 0.0;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = threadIdx.x + r * PK_THREADS;
+        if (i < m.qs) {
+            double b[NV];
+#pragma unroll
+            for (int c = 0; c < NV; ++c) b[c] = vec[(size_t)c * m.qs + i];
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[c][j] = fma(areg[j][r], b[c], acc[c][j]);
+        }
+    }
+    double tot[NV];
+    const long long tm1 = m.prof ? clock64() : 0;
+    reduce_cols<NV, 8>(acc, tot, lane);          // tot[c] = this warp's sum for column lane / 4, in all 4 lanes of the group
+    {
+        const int c = lane & 3;
+        double v = tot[0];
+#pragma unroll
+        for (int cc = 1; cc < NV; ++cc) v = (c == cc) ? tot[cc] : v;
+        if (c < NV) m.part[warp * 32 + lane] = v;
+    }
+    const long long tm2 = m.prof ? clock64() : 0;
+    // the finishing warp fetches everything its epilogue needs besides the sums BEFORE the barrier
+    const int fc = lane & 3, fj = m.c0 + (lane >> 2);
+    const bool fin_lane = warp == 0 && fc < NV && fj < m.c1 && !(inactive && inactive[fc]);
+    const bool fast = (fastmask >> fc) & 1u;
+    ProxPre pk;
+    double xyj = 0.0;
+    double *pub = nullptr;                 // where this lane publishes (address arithmetic off the critical path)
+    if (fin_lane) {
+        pub = m.ub + ((size_t)par * m.max_ct + fc) * m.q + fj;
+        if (fast) {
+            const double *cp = m.cpar + fc * 8;
+            const double gamma = m.gam[fc];
+            pk.kind = m.kind[fc];
+            pk.tp = m.pf[fj] * cp[0]; pk.dp = cp[1]; pk.rdp = cp[4]; pk.den2 = cp[6]; pk.rden2 = cp[7];
+            pk.thr_big = cp[5] * pk.tp;               // gamma d t
+            pk.thr_mid = (pk.dp + 1.0) * pk.tp;
+            pk.gpen = gamma * pk.tp; pk.gm1 = gamma - 1.0;
+            pk.pv = vec[(size_t)fc * m.qs + fj];
+            pk.tolpv = m.tol * fabs(pk.pv);
+        }
+        if (add_xy) xyj = m.xy[fj];
+    }
+    __syncthreads();
+    const long long tm3 = m.prof ? clock64() : 0;
+    if (warp == 0) {
+        const int c = fc;
+        bool viol = false;
+        if (fin_lane) {
+            double pw[PK_WARPS];
+#pragma unroll
+            for (int w = 0; w < PK_WARPS; ++w) pw[w] = m.part[w * 32 + lane];
+            double r = (((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7]))) + xyj;   // fixed order
+            if (fast) {
+                r = prox_select(pk, r);
+                if (__double_as_longlong(r) != __double_as_longlong(pk.pv)) {      // stop rule, src/utils.cpp:537-549
+                    const bool bc = abs_gt(r, 1e-13), bp = abs_gt(pk.pv, 1e-13);
+                    viol = bc != bp || (bc && abs_gt(r - pk.pv, pk.tolpv));
+                }
+            }
+            *pub = r;
+        }
+        if (gflag_slot) {
+            const unsigned vm = __reduce_or_sync(0xffffffffu, viol ? (1u << c) : 0u);
+            if (lane == 0) *gflag_slot = (int)vm;
+        }
+        if (m.prof && threadIdx.x == 0 && add_xy) {
+            const long long tm4 = clock64();
+            m.prof[13] += tm1 - tm0; m.prof[14] += tm2 - tm1; m.prof[15] += tm4 - tm3; m.prof[7] += tm3 - tm2;
+        }
+    }
+}
+
+template <int MODE, int RPT>
 __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs a) {
+    static_assert(PK_WARPS == 8, "matvec_reg sums eight warp partials");
+    static_assert(RPT == 0 || MODE == MODE_GLOBAL, "the register mat-vec belongs to the global mode");
     extern __shared__ __align__(16) double sm[];
     if (a.skip && *a.skip) return;           // uniform over the grid: nobody reaches a barrier
     const int q = a.q, qs = a.qs;            // qs = padded vector / slice stride, = 4 (mod 16), >= roundup(q, 4)
@@ -548,7 +693,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     double *chd = ak + PK_MAXCT;                           // 3 * PK_MAXCT: alpha, gamma, tau
     double *misc = chd + 3 * PK_MAXCT;                     // 8
     double *cpar = misc + 8;                               // 8 * PK_MAXCT: per-lambda derived constants
-    int *lam_idx = reinterpret_cast<int *>(cpar + 8 * PK_MAXCT);   // PK_MAXCT each
+    double *psm = cpar + 8 * PK_MAXCT;                     // q, only with post_scale (oem.xtx scale.factor / sparse intercept)
+    int *lam_idx = reinterpret_cast<int *>(psm + (a.post_scale ? q : 0));   // PK_MAXCT each
     int *iter = lam_idx + PK_MAXCT;
     int *done = iter + PK_MAXCT;
     int *chi = done + PK_MAXCT;                            // 3 * PK_MAXCT: penalty, nlam, out_off
@@ -565,10 +711,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     double *ub = a.ubuf ? a.ubuf + (size_t)team * 2 * a.max_ct * q : nullptr;
     int *gflag = a.gflags ? a.gflags + (size_t)team * 2 * a.team_size : nullptr;
     const double *XXg = a.XX + (size_t)team * q * q;
-    double *Amine = a.a_in_smem ? Asl : a.Abuf + ((size_t)team * a.team_size + rank) * a.cpc_pad * qs;
+    double *Amine = RPT > 0 ? nullptr : a.a_in_smem ? Asl : a.Abuf + ((size_t)team * a.team_size + rank) * a.cpc_pad * qs;
 
     // ---- one-time loads: my column slice of XX (zero padded to cpc_pad x qs) and every table ----
-    for (int jl = warp; jl < a.cpc_pad; jl += PK_WARPS) {
+    // register variant: rows t, t + 256, ... of my 8 columns, straight from L2 (8 * RPT independent loads per thread)
+    double areg[8][RPT > 0 ? RPT : 1];
+    if (RPT > 0) {
+#pragma unroll
+        for (int jl = 0; jl < 8; ++jl)
+#pragma unroll
+            for (int r = 0; r < (RPT > 0 ? RPT : 1); ++r) {
+                const int j = c0 + jl, i = threadIdx.x + r * PK_THREADS;
+                areg[jl][r] = (j < c1 && i < q) ? __ldg(XXg + (size_t)j * q + i) : 0.0;
+            }
+    }
+    for (int jl = warp; jl < (RPT > 0 ? 0 : a.cpc_pad); jl += PK_WARPS) {
         const int j = c0 + jl;
         double *dst = Amine + (size_t)jl * qs;
         const double *src = XXg + (size_t)j * q;
@@ -593,6 +750,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         xy[j] = a.XY[(size_t)team * q + j];
         pf[j] = a.pen_fact ? a.pen_fact[j] : 1.0;
         if (a.ngroups) cover[j] = a.grp_cover[j];
+        if (a.post_scale) psm[j] = a.post_scale[j];
     }
     for (int gi = threadIdx.x; gi < a.ngroups; gi += PK_THREADS) {
         gw[gi] = a.group_weights[gi];
@@ -624,25 +782,61 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     SmemTabs tb{pf, gw, grp_ptr, grp_unique, grp_idx, cover, a.ngroups};
 
     // ---- exchange: barrier (+ in global mode the copy of the published vectors into my shared memory) ----
-    auto exchange = [&](int par, double *dst, int nv, const int *inactive) {
+    // Global mode: one arrival counter per team (bar.sync orders the CTA's publications before thread 0's gpu-scope
+    // release; the acquire poll + bar.sync makes the other members' publications visible to the whole CTA).  After the
+    // barrier everything a member needs -- the published vectors AND the members' violation masks -- is requested in
+    // ONE batch of loads (up to 12 doubles + 1 word in flight per thread) before the first use: one L2 round trip per
+    // exchange (the chain-by-chain copy of round 1 paid one per chain, the masks one more).  A bulk-copy (cp.async.bulk
+    // + mbarrier) version of this fetch was measured and is slower: 2.5 k cycles against 1.8 k for 24 KB.
+    auto exchange = [&](int par, double *dst, int nv, const int *inactive, unsigned *flags_out) {
         if (MODE == MODE_SINGLE) __syncthreads();
         else if (MODE == MODE_CLUSTER) cluster_sync_all();
         else {
-            team_barrier(bar, bar_target, a.team_size);
+            const long long te0 = (a.prof && blockIdx.x == 0) ? clock64() : 0;
+            __syncthreads();
+            if (a.team_size > 1) {
+                if (threadIdx.x == 0) {
+                    bar_target += (unsigned)a.team_size;
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+                    unsigned v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+                    } while ((int)(v - bar_target) < 0);
+                }
+                __syncthreads();
+            }
+            if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[17] += clock64() - te0;
             const double *src = ub + (size_t)par * a.max_ct * q;
-            // per chain, 4 loads in flight per thread before the first use (one L2 round trip per batch)
-            for (int c = 0; c < nv; ++c) {
-                if (inactive && inactive[c]) continue;
-                const double *sc = src + (size_t)c * q;
-                double *dc = dst + (size_t)c * qs;
+            unsigned fl = 0u;
+            if (flags_out)
+                for (int r = threadIdx.x; r < a.team_size; r += PK_THREADS) fl |= (unsigned)__ldcg(gflag + (size_t)par * a.team_size + r);
+            constexpr int XB = 3;
+            for (int cb = 0; cb < nv; cb += XB) {
                 for (int j0 = threadIdx.x; j0 < q; j0 += 4 * PK_THREADS) {
-                    double tmp[4];
+                    double tmp[XB][4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int j = j0 + u * PK_THREADS; tmp[u] = j < q ? ld_cg(sc + j) : 0.0; }
+                    for (int cc = 0; cc < XB; ++cc) {
+                        const int c = cb + cc;
+                        const bool live = c < nv && !(inactive && inactive[c]);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int j = j0 + u * PK_THREADS; if (j < q) dc[j] = tmp[u]; }
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j0 + u * PK_THREADS;
+                            tmp[cc][u] = (live && j < q) ? ld_cg(src + (size_t)c * q + j) : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < XB; ++cc) {
+                        const int c = cb + cc;
+                        const bool live = c < nv && !(inactive && inactive[c]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j0 + u * PK_THREADS;
+                            if (live && j < q) dst[(size_t)c * qs + j] = tmp[cc][u];
+                        }
+                    }
                 }
             }
+            if (flags_out) *flags_out = fl;
             __syncthreads();
         }
     };
@@ -651,7 +845,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     mv.Amine = Amine; mv.xy = xy; mv.pf = pf; mv.cpar = cpar; mv.gam = chd + PK_MAXCT; mv.kind = kind;
     mv.part = part; mv.ub = ub; mv.violw = violw;
     mv.q = q; mv.qs = qs; mv.c0 = c0; mv.c1 = c1; mv.natm = a.cpc_pad >> 3; mv.max_ct = a.max_ct;
-    mv.team_size = a.team_size; mv.tol = a.tol;
+    mv.team_size = a.team_size; mv.tol = a.tol; mv.prof = (a.prof && blockIdx.x == 0) ? a.prof : nullptr;
 
     // =========================== phase 0: top eigenvalue ===========================
     double dval;
@@ -680,8 +874,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         bool conv = false;
         while (!conv) {
             double *w = B1 + (size_t)par * qs;
-            matvec_dmma<MODE>(mv, v, w, 1, nullptr, 0, 0u, par);
-            exchange(par, w, 1, nullptr);
+            if constexpr (RPT > 0) matvec_reg<RPT, 1>(areg, mv, v, nullptr, 0, 0u, par, nullptr);
+            else matvec_dmma<MODE>(mv, v, w, 1, nullptr, 0, 0u, par);
+            exchange(par, w, 1, nullptr, nullptr);
             par ^= 1;
             double dot = 0.0;
             for (int i = threadIdx.x; i < q; i += PK_THREADS) dot = fma(v[i], w[i], dot);
@@ -700,12 +895,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
             const bool breakdown = !(beta_k > 1e-14 * fabs(alpha_k));
             if (k <= 4 || (k & 7) == 0 || breakdown || k >= kmax) {
                 const long long tq = clock64();
-                tridiag_top(lz_al, lz_be, lz_ib, k, lo_hint, misc, red, reinterpret_cast<int *>(cpar));
+                // a coarse Ritz value (bracket / 1.7e7) decides whether to look closer; the value that is used is exact
+                tridiag_top(lz_al, lz_be, lz_ib, k, lo_hint, misc, red, reinterpret_cast<int *>(cpar), 3);
                 __syncthreads();
-                ttri += clock64() - tq;
                 theta = misc[0];
                 lo_hint = misc[2];
-                const double res = beta_k * misc[1];
+                double res = beta_k * misc[1];
+                if (breakdown || k >= kmax || (res <= 4.0 * a.eig_tol * fabs(theta))) {
+                    __syncthreads();
+                    tridiag_top(lz_al, lz_be, lz_ib, k, lo_hint, misc, red, reinterpret_cast<int *>(cpar), 9);
+                    __syncthreads();
+                    theta = misc[0];
+                    lo_hint = misc[2];
+                    res = beta_k * misc[1];
+                }
+                ttri += clock64() - tq;
                 res_last = res;
                 conv = breakdown || k >= kmax || (res <= a.eig_tol * fabs(theta));
                 // step cap reached before the Ritz value converged (q > LZ_MAX with a clustered top spectrum): an
@@ -750,11 +954,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
             const double den2 = is_mcp ? dp - 1.0 / gamma : (gamma - 1.0) * dp - 1.0;   // second denominator
             double *cp = cpar + c * 8;
             cp[0] = lp; cp[1] = dp; cp[2] = (is_scad || is_mcp) ? fmin(1.0, gammad) : 1.0; cp[3] = lambda;
-            cp[4] = 1.0 / dp; cp[5] = gammad; cp[6] = den2; cp[7] = 1.0 / den2;
+            cp[4] = __drcp_rn(dp); cp[5] = gammad; cp[6] = den2; cp[7] = __drcp_rn(den2);   // correctly rounded, like 1.0 / x
         };
         __syncthreads();      // the Lanczos scratch aliases cpar
         // ---- A = d I - XX on my slice; iterate buffers; first-lambda constants ----
-        for (int jl = warp; jl < a.cpc_pad; jl += PK_WARPS) {
+        if (RPT > 0) {
+#pragma unroll
+            for (int jl = 0; jl < 8; ++jl)
+#pragma unroll
+                for (int r = 0; r < (RPT > 0 ? RPT : 1); ++r) {
+                    const int i = threadIdx.x + r * PK_THREADS;
+                    const double x = -areg[jl][r];
+                    areg[jl][r] = (i == c0 + jl && i < c1) ? x + dval : x;
+                }
+        }
+        for (int jl = warp; jl < (RPT > 0 ? 0 : a.cpc_pad); jl += PK_WARPS) {
             const int j = c0 + jl;
             double *col = Amine + (size_t)jl * qs;
             if (j < c1)
@@ -790,10 +1004,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
             if (nactive == 0) break;
             long long t0 = clock64();
             double *Bc = cur ? B1 : B0, *Bn = cur ? B0 : B1;
+            if constexpr (RPT > 0) {
+                // the finishing warp publishes my violation mask itself (the exchange's bar.sync orders it)
+                int *slot = gflag + (size_t)cur * a.team_size + rank;
+                switch (nct) {
+                    case 1: matvec_reg<RPT, 1>(areg, mv, Bc, done, 1, fastmask, cur, slot); break;
+                    case 2: matvec_reg<RPT, 2>(areg, mv, Bc, done, 1, fastmask, cur, slot); break;
+                    case 3: matvec_reg<RPT, 3>(areg, mv, Bc, done, 1, fastmask, cur, slot); break;
+                    default: matvec_reg<RPT, 4>(areg, mv, Bc, done, 1, fastmask, cur, slot); break;
+                }
+            } else {
             matvec_dmma<MODE>(mv, Bc, Bn, nct, done, 1, fastmask, cur);
             __syncthreads();
+            }
             // my violation mask -> every member (same parity slot scheme as the vectors)
-            if (threadIdx.x == 0) {
+            if (RPT == 0 && threadIdx.x == 0) {
                 const int vm = violw[0];
                 violw[0] = 0;
                 if (MODE == MODE_SINGLE) cflag[cur * 8] = vm;
@@ -806,13 +1031,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                 } else gflag[(size_t)cur * a.team_size + rank] = vm;
             }
             long long t1 = clock64();
-            exchange(cur, Bn, nct, done);
-            long long t2 = clock64();
             unsigned bad = 0u;
-            if (MODE == MODE_GLOBAL) {
-                for (int r = threadIdx.x; r < a.team_size; r += PK_THREADS)
-                    bad |= (unsigned)__ldcg(gflag + (size_t)cur * a.team_size + r);
-            } else if (threadIdx.x < a.team_size) bad = (unsigned)cflag[cur * 8 + threadIdx.x];
+            exchange(cur, Bn, nct, done, &bad);
+            long long t2 = clock64();
+            if (MODE != MODE_GLOBAL && threadIdx.x < a.team_size) bad = (unsigned)cflag[cur * 8 + threadIdx.x];
             const long long tA = clock64();
             if (any_slow) {
                 for (int c = 0; c < nct; ++c) {
@@ -853,6 +1075,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
 #pragma unroll
             for (int w = 0; w < PK_WARPS; ++w) bad |= (unsigned)flagw[w];
             const long long tC = clock64();
+            // nothing finished (the common iteration): only the iteration counters move.  In the global mode the
+            // iterate buffers are written by the exchange alone, so no further CTA barrier is needed either.
+            bool anyfin = false;
+            for (int c = 0; c < nct; ++c)
+                if (!done[c] && (!((bad >> c) & 1u) || iter[c] + 1 >= a.maxit)) anyfin = true;
+            if (MODE == MODE_GLOBAL && !anyfin) {
+                if (threadIdx.x < nct && !done[threadIdx.x]) iter[threadIdx.x] += 1;
+                cur ^= 1;
+                if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+                    const long long t3 = clock64();
+                    a.prof[0] += t1 - t0; a.prof[1] += t2 - t1; a.prof[2] += t3 - t2; a.prof[3] += 1;
+                    a.prof[8] += tA - t2; a.prof[9] += tB - tA; a.prof[10] += tC - tB; a.prof[16] += 1;
+                }
+                continue;
+            }
             // ---- finished chains (rare): scale.factor quirk of oem_xtx, then their column of the path ----
             for (int c = 0; c < nct; ++c) {
                 if (done[c]) continue;
@@ -862,11 +1099,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                 double *bo = Bc + (size_t)c * qs;
                 const bool last = lam_idx[c] + 1 >= chi[PK_MAXCT + c];
                 double *gout = a.beta_out + ((size_t)chi[2 * PK_MAXCT + c] * a.Lmax + lam_idx[c]) * q;
+                // every member holds the whole iterate and writes its own slice of the path column
                 for (int j = threadIdx.x; j < q; j += PK_THREADS) {
                     double x = bn[j];
-                    if (a.post_scale) { x *= a.post_scale[j]; bn[j] = x; }   // get_beta() mutates the iterate: src/oem_xtx.h:576-581
+                    if (a.post_scale) { x *= psm[j]; bn[j] = x; }            // get_beta() mutates the iterate: src/oem_xtx.h:576-581
                     if (last) bo[j] = x;                                       // a finished chain keeps its beta in both buffers
-                    if (rank == 0) gout[j] = x;
+                    if (j >= c0 && j < c1) gout[j] = x;
                 }
             }
             __syncthreads();
@@ -925,30 +1163,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
 // then ONE cluster barrier per iteration (a __syncthreads for one CTA).  The per-warp violation masks travel with
 // the same barrier; all threads keep the per-chain state (iteration count, lambda index) redundantly in registers,
 // so nothing else is synchronised until a chain moves to its next lambda.
-// sums acc[c][*] over the 32 lanes for NCT chains at once (stage-major so the chains' shuffles overlap):
-// on return tot[c] in lane l is the total of column l / (32 / CPW)
-template <int NCT, int CPW>
-__device__ __forceinline__ void reduce_cols(double (&acc)[NCT][CPW], double (&tot)[NCT], int lane) {
-#pragma unroll
-    for (int n = CPW, off = 16; n > 1; n >>= 1, off >>= 1) {
-        const bool hi = (lane & off) != 0;
-#pragma unroll
-        for (int c = 0; c < NCT; ++c)
-#pragma unroll
-            for (int v = 0; v < n / 2; ++v) {
-                const double keep = hi ? acc[c][v + n / 2] : acc[c][v];
-                const double send = hi ? acc[c][v] : acc[c][v + n / 2];
-                acc[c][v] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-    }
-#pragma unroll
-    for (int c = 0; c < NCT; ++c) tot[c] = acc[c][0];
-#pragma unroll
-    for (int off = 16 / CPW; off >= 1; off >>= 1)
-#pragma unroll
-        for (int c = 0; c < NCT; ++c) tot[c] += __shfl_xor_sync(0xffffffffu, tot[c], off);
-}
-
 constexpr int PR_MAXCT = 4;       // chains per Gram handled by the register variant
 
 // coordinate-wise prox with the per-lambda constants cp[0..7] (see set_cpar) -- same arithmetic as mv_finish
@@ -1182,12 +1396,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathA
 
 // Shared memory every member of a generic path launch needs besides its slice of A: the ping-pong iterates of all the
 // team's chains, XY, per-lambda tables, the Lanczos tridiagonal, group tables.
-static size_t path_fixed_smem_bytes(int q, int max_ct, int Lmax, int ng, int ngidx) {
+static size_t path_fixed_smem_bytes(int q, int max_ct, int Lmax, int ng, int ngidx, bool post = false) {
     const int nvec = std::max(max_ct, 2);
     const int q4 = (q + 3) / 4 * 4;
     const int qs = q4 + (((4 - q4) % 16) + 16) % 16;
     return ((size_t)2 * nvec * qs + 2 * (size_t)q + (size_t)max_ct * std::max(Lmax, 1) + ng + PK_PART * 64 + 16 +
-            3 * LZ_MAX + PK_MAXCT + 3 * PK_MAXCT + 8 + 8 * PK_MAXCT) * 8 +
+            3 * LZ_MAX + PK_MAXCT + 3 * PK_MAXCT + 8 + 8 * PK_MAXCT + (post ? (size_t)q : 0)) * 8 +
            ((size_t)7 * PK_MAXCT + 20 + (ng ? 2 * (size_t)ng + 1 + ngidx + q : 0)) * 4 + 16;
 }
 
@@ -1279,7 +1493,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
             a.lambdas = pp.lambdas; a.pen_fact = pp.pen_fact; a.beta_out = pp.beta_out; a.niter_out = pp.niter_out;
             DBuf<long long> d_prof;
             const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;
-            if (prof) { d_prof.alloc(16); d_prof.zero(cx.stream); a.prof = d_prof.p; }
+            if (prof) { d_prof.alloc(32); d_prof.zero(cx.stream); a.prof = d_prof.p; }
             void *kargs[] = {&a};
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
@@ -1291,8 +1505,8 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
             OEM_CUDA(cudaLaunchKernelExC(&cfg, kern, kargs));
             cx.st.kernel_launches += 1;
             if (prof) {
-                long long h[16];
-                d_prof.download(h, 16, cx.stream);
+                long long h[32];
+                d_prof.download(h, 32, cx.stream);
                 OEM_CUDA(cudaStreamSynchronize(cx.stream));
                 fprintf(stderr, "[path prof] register variant: team=%d q=%d nct=%d | iters=%lld cyc/iter=%.0f (matvec+prox %.0f, barrier %.0f)\n",
                         NC, q, max_ct, h[3], h[3] ? (double)h[0] / h[3] : 0.0, h[3] ? (double)h[1] / h[3] : 0.0,
@@ -1309,7 +1523,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     const int ng = pp.ngroups, ngidx = ng ? pp.ngidx : 0;
     auto fixed_for = [&](int nbuf) {
         (void)nbuf;     // two ping-pong buffers in every mode
-        return path_fixed_smem_bytes(q, max_ct, pp.Lmax, ng, ngidx);
+        return path_fixed_smem_bytes(q, max_ct, pp.Lmax, ng, ngidx, pp.post_scale != nullptr);
     };
     size_t fixed_bytes = fixed_for(1);
     const size_t smem_cap = cx.smem_optin;
@@ -1328,19 +1542,21 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         if (cs && G * cs <= cx.num_sms) { mode = MODE_CLUSTER; team = cs; fixed_bytes = fixed_for(2); }
         else { mode = MODE_GLOBAL; team = 0; }
     }
-    void *kern = mode == MODE_SINGLE ? (void *)oem_path_kernel<MODE_SINGLE>
-               : mode == MODE_CLUSTER ? (void *)oem_path_kernel<MODE_CLUSTER> : (void *)oem_path_kernel<MODE_GLOBAL>;
+    void *kern = mode == MODE_SINGLE ? (void *)oem_path_kernel<MODE_SINGLE, 0>
+               : mode == MODE_CLUSTER ? (void *)oem_path_kernel<MODE_CLUSTER, 0> : (void *)oem_path_kernel<MODE_GLOBAL, 0>;
     // the attribute and the occupancy answer are per (kernel, device): asked once, not on every launch of an IRLS loop
-    static int per_sm_cache[3][64];
-    static bool attr_set[3][64];
+    static int per_sm_cache[3 + 4][64];
+    static bool attr_set[3 + 4][64];
     const int dslot = cx.device & 63;
-    if (!attr_set[mode][dslot]) {
-        OEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    auto prepare_kernel = [&](void *k, int slot) {
+        if (attr_set[slot][dslot]) return;
+        OEM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         int ps = 0;
-        OEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, kern, PK_THREADS, smem_cap));
-        per_sm_cache[mode][dslot] = ps;
-        attr_set[mode][dslot] = true;
-    }
+        OEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, k, PK_THREADS, smem_cap));
+        per_sm_cache[slot][dslot] = ps;
+        attr_set[slot][dslot] = true;
+    };
+    prepare_kernel(kern, mode);
     if (mode == MODE_GLOBAL) {
         const int per_sm = per_sm_cache[mode][dslot];
         const int max_ctas = std::max(1, per_sm) * cx.num_sms;
@@ -1357,7 +1573,17 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         team = (q + cpc - 1) / cpc;                                    // drop members that would own nothing
     }
     const int cpc_pad = (cpc + 7) / 8 * 8;
-    const bool a_in_smem = (size_t)cpc_pad * qs * 8 + fixed_bytes <= smem_cap;
+    // one 8-column atom per member and <= 4 chains: the register-resident mat-vec (matvec_reg)
+    int rpt = 0;
+    if (mode == MODE_GLOBAL && cpc_pad == 8 && max_ct <= 4 && qs <= 5 * PK_THREADS && getenv("OEMB200_PATH_DMMA") == nullptr) {
+        rpt = std::max(2, (qs + PK_THREADS - 1) / PK_THREADS);
+        void *kr = rpt == 2 ? (void *)oem_path_kernel<MODE_GLOBAL, 2> : rpt == 3 ? (void *)oem_path_kernel<MODE_GLOBAL, 3>
+                 : rpt == 4 ? (void *)oem_path_kernel<MODE_GLOBAL, 4> : (void *)oem_path_kernel<MODE_GLOBAL, 5>;
+        prepare_kernel(kr, 3 + rpt - 2);
+        if (per_sm_cache[3 + rpt - 2][dslot] >= 1 && G * team <= per_sm_cache[3 + rpt - 2][dslot] * cx.num_sms) kern = kr;
+        else rpt = 0;
+    }
+    const bool a_in_smem = rpt == 0 && (size_t)cpc_pad * qs * 8 + fixed_bytes <= smem_cap;
     const size_t smem_bytes = fixed_bytes + (a_in_smem ? (size_t)cpc_pad * qs * 8 : 0);
 
     // device tables: rebuilt unless the caller's scratch already holds exactly this layout
@@ -1369,7 +1595,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
             const unsigned char *b = static_cast<const unsigned char *>(ptr);
             key.insert(key.end(), b, b + bytes);
         };
-        const int geo[10] = {q, qs, G, team, cpc_pad, max_ct, mode, a_in_smem ? 1 : 0, (int)cd.size(), cx.device};
+        const int geo[11] = {q, qs, G, team, cpc_pad, max_ct, mode, a_in_smem ? 1 : 0, (int)cd.size(), cx.device, rpt};
         put(geo, sizeof geo);
         if (!cd.empty()) put(cd.data(), cd.size() * sizeof(ChainDev));
         put(tptr.data(), tptr.size() * sizeof(int));
@@ -1384,7 +1610,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
         S.nflags = mode == MODE_GLOBAL ? (size_t)G * 2 * team : 0;
         S.bar.alloc((size_t)G + S.nflags);
         if (mode == MODE_GLOBAL) S.ubuf.alloc((size_t)G * 2 * max_ct * q);
-        if (!a_in_smem) S.A.alloc((size_t)G * team * cpc_pad * qs);
+        if (!a_in_smem && rpt == 0) S.A.alloc((size_t)G * team * cpc_pad * qs);
         if (!cd.empty()) S.chains.upload(cd.data(), cd.size(), cx.stream);
         S.tptr.upload(tptr.data(), tptr.size(), cx.stream);
         if (!tidx.empty()) S.tidx.upload(tidx.data(), tidx.size(), cx.stream);
@@ -1415,7 +1641,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
 
     DBuf<long long> d_prof;
     const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;
-    if (prof) { d_prof.alloc(16); d_prof.zero(cx.stream); a.prof = d_prof.p; }
+    if (prof) { d_prof.alloc(32); d_prof.zero(cx.stream); a.prof = d_prof.p; }
     void *kargs[] = {&a};
     if (mode == MODE_GLOBAL) {
         OEM_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G * team), dim3(PK_THREADS), kargs, smem_bytes, cx.stream));
@@ -1431,14 +1657,16 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     }
     cx.st.kernel_launches += 1;
     if (prof) {
-        long long h[16];
-        d_prof.download(h, 16, cx.stream);
+        long long h[32];
+        d_prof.download(h, 32, cx.stream);
         OEM_CUDA(cudaStreamSynchronize(cx.stream));
-        fprintf(stderr, "[path prof] mode=%d team=%d cpc=%d q=%d nct=%d | iters=%lld cyc/iter: matvec=%.0f exchange=%.0f prox+update=%.0f | "
-                "lanczos: steps=%lld total=%lld cyc (tridiag %lld)\n", mode, team, cpc, q, max_ct, h[3],
+        fprintf(stderr, "[path prof] mode=%d rpt=%d team=%d cpc=%d q=%d nct=%d | iters=%lld cyc/iter: matvec=%.0f exchange=%.0f prox+update=%.0f | "
+                "lanczos: steps=%lld total=%lld cyc (tridiag %lld)\n", mode, rpt, team, cpc, q, max_ct, h[3],
                 h[3] ? (double)h[0] / h[3] : 0.0, h[3] ? (double)h[1] / h[3] : 0.0, h[3] ? (double)h[2] / h[3] : 0.0, h[6], h[4], h[5]);
-        if (h[3]) fprintf(stderr, "[path prof]   flags=%.0f replicated=%.0f reduce=%.0f finished=%.0f state=%.0f\n", (double)h[8] / h[3],
-                          (double)h[9] / h[3], (double)h[10] / h[3], (double)h[11] / h[3], (double)h[12] / h[3]);
+        if (h[3]) fprintf(stderr, "[path prof]   flags=%.0f replicated=%.0f reduce=%.0f finished=%.0f state=%.0f | matvec: kloop=%.0f butterfly|sync=%.0f "
+                          "reduce+prox+publish=%.0f (reg: sync %.0f) | team barrier=%.0f of the exchange, %lld iterations without a finished chain\n", (double)h[8] / h[3],
+                          (double)h[9] / h[3], (double)h[10] / h[3], (double)h[11] / h[3], (double)h[12] / h[3],
+                          (double)h[13] / h[3], (double)h[14] / h[3], (double)h[15] / h[3], (double)h[7] / h[3], (double)h[17] / h[3], h[16]);
     }
 }
 
