@@ -218,7 +218,9 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     b0.download(h0.data(), nb0, cx.stream);
     cx.sync();
     const double n_tot = h0[nb0 - 1];
-    if (!(n_tot > q)) fail(OEMB200_EUNSUPPORTED, "n <= p logistic branch is outside the hot path");
+    if (!(n_tot > q)) fail(OEMB200_EUNSUPPORTED, "oem_fit_logistic_dense with n <= p + intercept: the reference takes least-squares steps on the 0/1 "
+                                          "response there, with a step matrix its d does not bound (src/oem_logistic_dense.h:478-483, 530-568; "
+                                          "restated in oracle/oracle.py:_logistic_wide, which diverges) -- not built");
     std::vector<double> cinv(p, 1.0);
     if (stdz)
         for (int j = 0; j < p; ++j) {
@@ -597,7 +599,9 @@ void fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *v
     b0.download(h0.data(), nb0, cx.stream);
     cx.sync();
     const double n_tot = h0[nb0 - 1];
-    if (!(n_tot > q)) fail(OEMB200_EUNSUPPORTED, "n <= p sparse logistic branch (XWX' form, src/oem_logistic_sparse.h:504-509) is outside the hot path");
+    if (!(n_tot > q)) fail(OEMB200_EUNSUPPORTED, "oem_fit_logistic_sparse with n <= p + intercept: the reference takes least-squares steps on the 0/1 "
+                                          "response there, with a step matrix its d does not bound (src/oem_logistic_sparse.h:503-509, 534-580; "
+                                          "restated in oracle/oracle.py:_logistic_wide, which diverges) -- not built");
     std::vector<double> cinv(p, 1.0);
     if (stdz)
         for (int j = 0; j < p; ++j) {

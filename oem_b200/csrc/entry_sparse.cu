@@ -641,13 +641,27 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
     double n_tot = 0.0;
     OEM_CUDA(cudaMemcpyAsync(&n_tot, nobs, 8, cudaMemcpyDeviceToHost, cx.stream));
     cx.sync();
-    if (!(n_tot > p)) fail(OEMB200_EUNSUPPORTED, "n <= p sparse branch (XX' form, src/oem_sparse.h:609-616) is outside the hot path");
+    // n <= p (src/oem_sparse.h:609-616, 630-640): d = 1.005 lambda_max(XX'/n) and u = X'(Y - X beta)/n + d beta on the RAW X --
+    // term by term (dI - X'X/n) beta + X'y/n with the same non-zero spectrum, so the p x p route serves it.  `standardize`
+    // only reaches lambda_max (XY is scaled in init_oem, :829-846, but next_u never uses XY) and get_beta() (:901-911).
+    // With an intercept the reference indexes XY(n) and beta(p + 1) past their ends (XXdim = min(n, p), :782-784): rejected.
+    const bool wide = !(n_tot > p);
+    if (wide && icpt)
+        fail(OEMB200_EUNSUPPORTED, "oem_fit_sparse with n <= p and intercept = TRUE is dimensionally inconsistent in the reference "
+             "(src/oem_sparse.h:782-784, 829-841)");
 
     // ---- assembly: the oem_big layout, then row / column 0 times intval (src/oem_sparse.h:566-594, 829-846) ----
     const size_t t_as = tm.start(&cx.st.ms_assemble);
     DBuf<double> XX0((size_t)q * q), XY0(q), XX((size_t)q * q), XY(q), cinv(p), dscale;
     assemble_aug_launch(cx, p, icpt, s->standardize ? 1 : 0, 1, 1, G, stats, ysum, 1, nobs, nobs, XX0.p, XY0.p, cinv.p, nullptr);
-    std::vector<double> hcinv(p), hsq(p), hXY(q);
+    std::vector<double> hcinv(p), hsq(p), hXY(q), hXYlam;
+    if (wide && s->standardize) {
+        // lambda_max from the scaled XY (kept from the call above), the iteration from the raw statistics
+        hXYlam.resize(q);
+        XY0.download(hXYlam.data(), q, cx.stream);
+        cx.sync();
+        assemble_aug_launch(cx, p, 0, 0, 1, 1, G, stats, ysum, 1, nobs, nobs, XX0.p, XY0.p, nullptr, nullptr);
+    }
     cinv.download(hcinv.data(), p, cx.stream);
     OEM_CUDA(cudaMemcpyAsync(hsq.data(), stats + 2 * (size_t)p, sizeof(double) * p, cudaMemcpyDeviceToHost, cx.stream));
     cx.sync();
@@ -670,7 +684,7 @@ void fit_sparse(const int *row_idx, const int *col_ptr, const double *values, in
     cx.sync();
 
     double lmax = 0.0;   // compute_lambda_zero: the X entries only (src/oem_sparse.h:851-862)
-    for (int j = icpt; j < q; ++j) lmax = std::max(lmax, std::fabs(hXY[j]));
+    for (int j = icpt; j < q; ++j) lmax = std::max(lmax, std::fabs(hXYlam.empty() ? hXY[j] : hXYlam[j]));
     su.build_lambdas(s, lmax, false);
 
     std::vector<double> pf(q, 0.0);

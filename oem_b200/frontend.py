@@ -194,9 +194,9 @@ def big_oem(x, y, family="gaussian", penalty=None, weights=(), lambda_=(), nlamb
             hessian_type="full", varnames=None, comm=None):
     """R/big_oem.R:121-543.  `x` plays the role of the big.matrix: an ndarray / np.memmap (see
     oem_b200.bigmatrix.attach for .bk/.desc files) or a column-major CUDA tensor.  Only the gaussian family is
-    on the hot path (the reference's big.oem binomial branch is not)."""
+    exists: the reference's own big.oem stops on binomial (R/big_oem.R:159)."""
     if family != "gaussian":
-        raise NotImplementedError("big.oem family = 'binomial' is outside the hot path (SURVEY.md 8a)")
+        raise NotImplementedError("binomial case not implemented yet")          # R/big_oem.R:159, same words
     penalty = _match_penalty(penalty)
     n, p = _shape(x)
     if len(weights) > 0:
@@ -248,7 +248,7 @@ def xval_oem(x, y, nfolds=10, foldid=None, type_measure="mse", ncores=-1, family
              irls_maxit=100, irls_tol=1e-3, compute_loss=False, varnames=None, seed=None, comm=None):
     """R/oem_xval.R:107-460: fit + fast cross-validation in one call; adds lambda.min / lambda.1se / cvup / cvlo."""
     if family != "gaussian":
-        raise NotImplementedError("xval.oem family = 'binomial' is outside the hot path (SURVEY.md 8a)")
+        raise NotImplementedError("binomial models not yet supported for xval, use cv.oem() instead")   # R/oem_xval.R:160-163
     if type_measure not in ("mse", "deviance", "mae"):
         raise ValueError("type.measure must be 'mse', 'deviance' or 'mae' for the gaussian family")
     penalty = _match_penalty(penalty)

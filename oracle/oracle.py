@@ -626,7 +626,7 @@ def oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_
                    nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor, standardize_, intercept,
                    compute_loss, opts):
     """src/oem_sparse.cpp:30-264, src/oem_sparse.h:490-636,791-943: dgCMatrix X,
-    n > p branch, unweighted.  Like oem_fit_big it scales by the uncentred colsq/(n-1) and carries an
+    unweighted; n > p, and n <= p without an intercept.  Like oem_fit_big it scales by the uncentred colsq/(n-1) and carries an
     explicit intercept column -- but that column is the CONSTANT intval = sqrt(mean(diag(X-block))/n)
     (:577-594), lambda_max skips the intercept entry (:851-862), and get_beta() multiplies the member
     beta(0) by intval IN PLACE (:895-900), so the next lambda warm-starts from the rescaled intercept and
@@ -640,8 +640,10 @@ def oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_
     X = sp.csc_matrix(x, dtype=np.float64)
     Y = np.asarray(y, dtype=np.float64).ravel()
     n, p = X.shape
-    if not n > p:
-        raise NotImplementedError("n <= p sparse branch (XX' form) is out of scope")
+    wide = not n > p
+    if wide and intercept:
+        raise NotImplementedError("n <= p with an intercept: XY has min(n, p) entries and beta p + 1 in the reference "
+                                  "(src/oem_sparse.h:782-784, 829-841), dimensionally inconsistent")
     q = p + int(intercept)
     pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
     if intercept:
@@ -674,10 +676,18 @@ def oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_
     if standardize_:
         XY[q - p:] *= colsq_inv
     XY /= n
-    d = top_eig(XX) * 1.005
+    lmax = float(np.abs(XY[q - p:]).max())          # compute_lambda_zero: tail only
+    if wide:
+        # n <= p, no intercept (:609-616, 630-640): d from the n x n matrix XX'/n of the RAW X, and
+        # next_u = X'(Y - X beta)/n + d beta never looks at XY or colsq_inv -- (dI - X'X/n) beta + X'y/n term by term.
+        # `standardize` survives only in lambda_max (above, from the scaled XY) and in get_beta().
+        d = top_eig(np.asarray((X @ X.T).todense()) / n) * 1.005
+        XX = np.asarray((X.T @ X).todense()) / n
+        XY = np.asarray(X.T @ Y).ravel() / n
+    else:
+        d = top_eig(XX) * 1.005
     A = -XX
     A[np.diag_indices(q)] += d
-    lmax = float(np.abs(XY[q - p:]).max())          # compute_lambda_zero: tail only
     lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha)
     grp = _Groups(groups, unique_groups, group_weights, scan=q)      # scans groups.size() (:466)
     s = _Solver(q, pf, grp, o["maxit"], o["tol"])
@@ -708,6 +718,131 @@ def oem_fit_sparse(x, y, family, penalty, weights, groups, unique_groups, group_
     return out
 
 
+
+# ------------------------------------------------------------------------------------------
+# n <= p + intercept branches of the two logistic solvers (shared: they differ in three quirks only)
+# ------------------------------------------------------------------------------------------
+def logistic_wide_next_u(X, Y, W, beta_prev, d, colsq_inv, standardize_, intercept):
+    """next_u of the n <= p + intercept branch, LITERALLY as the reference writes it
+    (src/oem_logistic_dense.h:530-568, src/oem_logistic_sparse.h:534-580): the intercept variants use the unweighted
+    residual Y - X beta, the no-intercept variants weight it by W.  Used by the tests to tie the Gram form iterated
+    below -- (dI - G) beta + b -- to the reference's own expression."""
+    n, p = X.shape
+    cinv = colsq_inv if standardize_ else np.ones(p)
+    if intercept:
+        resid = Y - X @ (beta_prev[1:] * cinv)
+        resid = resid - beta_prev[0]
+        resid = resid / float(n)
+        u = np.empty(p + 1)
+        u[1:] = cinv * (X.T @ resid) + d * beta_prev[1:]
+        u[0] = resid.sum() + d * beta_prev[0]
+        return u
+    return cinv * (X.T @ ((W * (Y - X @ (beta_prev * cinv))) / float(n))) + d * beta_prev
+
+
+def logistic_wide_gram_form(X, Y, W, colsq_inv, standardize_, intercept):
+    """The same iteration as (G, b) with u = (dI - G) beta + b: intercept variants G = [1, X D]'[1, X D] / n (unweighted,
+    fixed for the whole fit), b = [sum y, D X'y] / n; no-intercept variants G = D X'WX D / n, b = D X'(W o y) / n."""
+    n, p = X.shape
+    cinv = colsq_inv if standardize_ else np.ones(p)
+    Xs = X * cinv[None, :]
+    if intercept:
+        Xa = np.hstack([np.ones((n, 1)), Xs])
+        return Xa.T @ Xa / float(n), Xa.T @ Y / float(n)
+    return (Xs * W[:, None]).T @ Xs / float(n), Xs.T @ (W * Y) / float(n)
+
+
+def _logistic_wide(X, Y, penalty, groups, unique_groups, group_weights, lambda_, nlambda, lmin_ratio, alpha, gamma, tau,
+                   penalty_factor, standardize_, intercept, compute_loss, o, sparse_quirks):
+    """n <= p + intercept (`nobs > nvars + int(intercept)` false): src/oem_logistic_dense.h:478-483, 530-568, 848-1036 and
+    the sparse twin src/oem_logistic_sparse.h:503-509, 534-580, 851-1030.  What the reference does there is NOT a
+    logistic fit: d = 1.0005 lambda_max((sqrt(W) X X' sqrt(W) + 1 [intercept]) / n) on the RAW X (the standardised
+    variant is commented out), no gradient / XY update (the `nobs > nvars + intercept` guard at :965), and next_u
+    (logistic_wide_next_u) is a least-squares step on the 0/1 response -- unweighted with an intercept, W-weighted
+    without one.  Restated because the arithmetic is deterministic; iterated in Gram form (logistic_wide_gram_form).
+    Quirks of the sparse solver: compute_XtX_d_update_A() on every data pass (no hessian.type test, :958-961);
+    get_beta() multiplies beta(0) by `intval`, which this branch never sets (0), whenever nobs > nvars, i.e. for
+    n = p + 1 with an intercept (:1040-1043)."""
+    n, p = X.shape
+    q = p + int(intercept)
+    pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
+    if intercept:
+        pf = np.concatenate([[0.0], pf])
+    colsq_inv = np.ones(p)
+    if standardize_:
+        colsq = (X ** 2).sum(axis=0) / (float(n) - 1.0)
+        colsq = np.where(colsq == 0.0, 1.0, colsq)
+        colsq_inv = 1.0 / np.sqrt(colsq)
+    XY0 = np.zeros(q)
+    XY0[q - p:] = X.T @ Y
+    if intercept:
+        XY0[0] = Y.sum()
+    if standardize_:
+        XY0[q - p:] *= colsq_inv
+    XY0 /= n
+    lmax = float(np.abs(XY0[q - p:]).max())
+    lams = _lambda_lists(lambda_, penalty, nlambda, lmin_ratio, lmax, alpha,
+                         logistic_fudge=True, gamma=_gamma_for(gamma, 0))
+    grp = _Groups(groups, unique_groups, group_weights, scan=q, zero_weight_for_group0=True)
+    s = _Solver(q, pf, grp, o["maxit"], o["tol"])
+    every_pass = sparse_quirks or o["hessian_type"] == "full"
+    G, b, d = None, None, None
+    W = np.zeros(n)
+    prob = np.zeros(n)
+    out = dict(beta=[], lambda_=[], niter=[], loss=[], d=None)
+    for pp, pen in enumerate(penalty):
+        lam = lams[pp]
+        L = 1 if pen == "ols" else lam.size
+        beta = np.zeros((p + 1, L), order="F")
+        niter = np.zeros(L, dtype=np.int32)
+        loss = np.full(L, 1e99)
+        s.init(pen, alpha, _gamma_for(gamma, pp), tau)
+        for i in range(L):
+            on_lam_1 = (i == 0)
+            it = 0
+            for it in range(o["irls_maxit"]):
+                beta_prev_irls = s.beta.copy()
+                if not (it == 0 and not on_lam_1):
+                    bx = s.beta[q - p:] * colsq_inv if standardize_ else s.beta[q - p:]
+                    eta = X @ bx + (s.beta[0] if intercept else 0.0)
+                    prob = 1.0 / (1.0 + np.exp(-eta))
+                    W = prob * (1.0 - prob)
+                    if it < n and W[it] < 1e-5:         # sic: indexed by the IRLS counter
+                        W[it] = 1e-5
+                    if (it == 0 and on_lam_1) or every_pass:
+                        sw = np.sqrt(W)
+                        M = (X * sw[:, None]) @ (X * sw[:, None]).T          # XWXt(): n x n, raw X
+                        if intercept:
+                            M = M + 1.0
+                        d = top_eig(M / float(n)) * 1.0005
+                    if not intercept or G is None:
+                        G, b = logistic_wide_gram_form(X, Y, W, colsq_inv, standardize_, intercept)
+                A = -G
+                A[np.diag_indices(q)] += d
+                s.solve(A, b, d, lam[i])
+                if stop_rule(s.beta, beta_prev_irls, o["irls_tol"]):
+                    break
+            else:
+                it = o["irls_maxit"]
+            niter[i] = it + 1
+            if sparse_quirks and intercept and n > p:
+                s.beta[0] *= 0.0                        # get_beta(): beta(0) *= intval with intval never set
+            res = s.beta.copy()
+            if standardize_:
+                res[q - p:] *= colsq_inv
+            beta[1 - int(intercept):, i] = res
+            if compute_loss:
+                ok = np.where(Y == 1, prob > 1e-5, prob <= 1.0 - 1e-5)
+                pr = np.where(Y == 1, prob, 1.0 - prob)
+                loss[i] = float(np.where(ok, np.log(1.0 / np.where(ok, pr, 1.0)), np.log(1.0 / 1e-5)).sum())
+        out["beta"].append(beta)
+        out["lambda_"].append(lam)
+        out["niter"].append(niter)
+        out["loss"].append(loss)
+    out["d"] = d
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # oem_fit_logistic_dense
 # ------------------------------------------------------------------------------------------
@@ -715,7 +850,7 @@ def oem_fit_logistic_dense(x, y, family, penalty, weights, groups, unique_groups
                            lambda_, nlambda, lmin_ratio, alpha, gamma, tau, penalty_factor,
                            standardize_, intercept, compute_loss, opts):
     """src/oem_logistic_dense.cpp:29-313, src/oem_logistic_dense.h:721-1036,
-    n > p branch, unweighted, ncores=1, including the quirks of Appendix B item 5."""
+    unweighted, ncores=1, including the quirks of Appendix B item 5 (n <= p + intercept: _logistic_wide)."""
     o = _as_opts(opts)
     if np.asarray(weights).size:
         raise ValueError("weights not implemented yet.")
@@ -724,7 +859,8 @@ def oem_fit_logistic_dense(x, y, family, penalty, weights, groups, unique_groups
     n, p = X.shape
     q = p + int(intercept)
     if not n > q:
-        raise NotImplementedError("n <= p logistic branch is out of scope (SURVEY.md 8f row 4)")
+        return _logistic_wide(X, Y, penalty, groups, unique_groups, group_weights, lambda_, nlambda, lmin_ratio, alpha,
+                              gamma, tau, penalty_factor, standardize_, intercept, compute_loss, o, sparse_quirks=False)
     pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
     if intercept:
         pf = np.concatenate([[0.0], pf])
@@ -848,7 +984,9 @@ def oem_fit_logistic_sparse(x, y, family, penalty, weights, groups, unique_group
     n, p = X.shape
     q = p + int(intercept)
     if not n > q:
-        raise NotImplementedError("n <= p sparse logistic branch (XWX' form) is out of scope")
+        return _logistic_wide(np.asarray(X.todense()), Y, penalty, groups, unique_groups, group_weights, lambda_, nlambda,
+                              lmin_ratio, alpha, gamma, tau, penalty_factor, standardize_, intercept, compute_loss, o,
+                              sparse_quirks=True)
     pf = np.asarray(penalty_factor, dtype=np.float64).ravel()
     if intercept:
         pf = np.concatenate([[0.0], pf])

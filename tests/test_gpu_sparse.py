@@ -59,6 +59,25 @@ def test_sparse_routes_agree(lib, oracle, monkeypatch, route):
     assert got["stats"]["gram_flops"] == (0.0 if route == "sparse" else 3001.0 * 80 * 81)      # which kernel built X'X
 
 
+@pytest.mark.parametrize("standardize", [True, False])
+@pytest.mark.parametrize("n,p", [(120, 180), (150, 150)])
+def test_sparse_wide_no_intercept(lib, oracle, standardize, n, p):
+    # n <= p without an intercept (src/oem_sparse.h:609-616, 630-640): raw-X iteration, `standardize` only in lambda_max
+    # and get_beta(); with an intercept the reference is dimensionally inconsistent and the call is refused
+    X, y = sparse_problem(300 + n + standardize, n, p, density=0.2, nnz=8, noise=0.3)
+    g = np.arange(p) // 6 + 1
+    a = args_xy(X, y, "gaussian", ["lasso", "mcp", "grp.lasso", "elastic.net"], groups=g, unique_groups=np.unique(g), alpha=0.7,
+                nlambda=12, lmin_ratio=0.05, standardize=standardize, intercept=False, compute_loss=True,
+                opts=dict(tol=1e-10, maxit=5000))
+    got, ref = lib.oem_fit_sparse(*a), oracle.oem_fit_sparse(*a)
+    assert_same_fit(got, ref)
+    for lg, lr in zip(got["loss"], ref["loss"]):
+        assert np.allclose(lg[:len(lr)], lr, rtol=1e-9, atol=0)
+    a[16] = True
+    with pytest.raises(Exception, match="dimensionally inconsistent"):
+        lib.oem_fit_sparse(*a)
+
+
 def test_sparse_equals_dense_identity(lib):
     # man/oem.Rd:104-125 -> docs/reference/oem.html prints max|dense - sparse| = 1.58e-15 / 1.61e-15 for
     # standardize = FALSE, intercept = FALSE (inputs from rsparsematrix, not reproducible): same order here
