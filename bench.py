@@ -523,6 +523,10 @@ def run_e2e(torch, api, oem_b200, X, y, rows, opts, timed, args, st_dev):
     avail = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) * 1024
     budget = int(avail * 0.8 / world)
     rows_h = min(rows, budget // (P * 8) // 72 * 72)
+    if world > 1:       # MemAvailable is read at slightly different moments on every rank: agree on one answer
+        t = torch.tensor([float(rows_h)], dtype=torch.float64, device=X.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+        rows_h = int(t.item())
     if rows_h < rows and not args.allow_partial_e2e:
         return {"value": None, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": f"host RAM cannot hold the {rows * P * 8 / 1e9:.0f} GB shard per rank ({avail / 1e9:.0f} GB available "
@@ -596,6 +600,7 @@ def run_e2e(torch, api, oem_b200, X, y, rows, opts, timed, args, st_dev):
         out["h2d_probe_error"] = repr(e)
     if pinned:
         cudart.cudaHostUnregister(Xh.data_ptr())
+    if all_pinned:      # a decision every rank takes alike: the fit below contains collectives
         # the same call once more from PAGEABLE memory (what an R matrix or a numpy array is): the library stages it through
         # its pinned bounce ring + reader threads (csrc/ingest.cu).  Reported next to the pinned figure, not instead of it.
         try:

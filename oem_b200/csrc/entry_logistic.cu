@@ -92,49 +92,23 @@ __global__ void irls_pack_grad_kernel(const double *__restrict__ xr, const doubl
     if (j == 0) g[0] = sr[0];
 }
 
-// XY = XX beta + grad with grad = [g0 / n, (g_j / n) o colsq_inv] (oem_logistic_dense.h:970-999).  One warp per row.
-__global__ void irls_xy_kernel(int q, int icpt, const double *__restrict__ XX, const double *__restrict__ beta,
-                               const double *__restrict__ g, const double *__restrict__ cinv, double n_tot,
-                               double *__restrict__ XY, const int *__restrict__ skip) {
-    if (skip && *skip) return;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= q) return;
-    const int lane = threadIdx.x & 31;
-    // four independent partial sums per lane: the 8 MB of XX come from L2, one dependent FMA chain per lane left the loads
-    // of a row serialised (12 us per call at q = 1001, once per IRLS data pass)
-    const double *row = XX + (size_t)r * q;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int c = lane;
-    for (; c + 96 < q; c += 128) {
-        const double x0 = __ldg(row + c), x1 = __ldg(row + c + 32), x2 = __ldg(row + c + 64), x3 = __ldg(row + c + 96);
-        s0 = fma(x0, beta[c], s0); s1 = fma(x1, beta[c + 32], s1);
-        s2 = fma(x2, beta[c + 64], s2); s3 = fma(x3, beta[c + 96], s3);
-    }
-    for (; c < q; c += 32) s0 = fma(__ldg(row + c), beta[c], s0);
-    double s = (s0 + s1) + (s2 + s3);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-        double gr;
-        if (icpt && r == 0) gr = g[0] / n_tot;
-        else {
-            const int j = r - icpt;
-            gr = g[1 + j] / n_tot;
-            if (cinv) gr *= cinv[j];
-        }
-        XY[r] = s + gr;
-    }
-}
-
 // stopRule(beta_new, beta_prev, irls_tol) (src/utils.cpp:537-549) on the device; the verdict goes to pinned host
 // memory, the inner loop's iteration count is accumulated for the statistics.  One CTA.
 // `conv` (device) is the predicate of speculatively enqueued work: once an IRLS loop has converged, every later kernel
 // of that lambda -- this one included -- returns at once, so the host may enqueue iteration it + 1 before it has read
 // iteration it's verdict.
+// With `b` given it also prepares the NEXT data pass: b = beta_new[icpt:] o colsq_inv, b0 = beta_new[0] (what
+// irls_coef_kernel computes) -- one launch less per IRLS iteration.
 __global__ void irls_stop_kernel(const double *__restrict__ cur, const double *__restrict__ prev, int q, double tol,
                                  const int *__restrict__ niter, long long *__restrict__ iters_total,
-                                 volatile int *__restrict__ host_flag, int *__restrict__ conv) {
+                                 volatile int *__restrict__ host_flag, int *__restrict__ conv,
+                                 const double *__restrict__ cinv = nullptr, int p = 0, int icpt = 0, double *__restrict__ b = nullptr,
+                                 double *__restrict__ b0 = nullptr) {
     if (conv && *conv) return;
+    if (b) {
+        for (int j = threadIdx.x; j < p; j += blockDim.x) b[j] = cinv ? cur[icpt + j] * cinv[j] : cur[icpt + j];
+        if (threadIdx.x == 0) *b0 = icpt ? cur[0] : 0.0;
+    }
     __shared__ int bad;
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
@@ -339,11 +313,13 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
 
             auto enqueue_iteration = [&](int k) {
                 double *cur = d_iter.p + (size_t)((par0 + k) & 1) * q, *nxt = d_iter.p + (size_t)((par0 + k + 1) & 1) * q;
-                bool rebuilt = false;
+                bool rebuilt = false, form_xy = false;
                 if (!(k == 0 && !on_lam_1)) {
                     const bool need_w = (k == 0 && on_lam_1) || o->hessian_full;
-                    irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p, skip);
-                    cx.st.kernel_launches += 1;
+                    if (k == 0) {      // later passes of this lambda get b from the previous iteration's irls_stop_kernel
+                        irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p, skip);
+                        cx.st.kernel_launches += 1;
+                    }
                     if (slab) {
                         // one kernel, one HBM sweep: prob, W and the gradient sums [sum r, X'r]
                         const size_t t1 = tm.start(&cx.st.ms_irls_xb);
@@ -357,7 +333,9 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
                         cx.st.data_passes += 1;
                     }
-                    if (cx.rank == 0 && k < n) {            // W(i) clamp, sic (oem_logistic_dense.h:953-959)
+                    // W(i) clamp, sic (oem_logistic_dense.h:953-959).  W is consumed by the Hessian build alone (the next data pass
+                    // recomputes it from scratch), so the clamp only has to happen in front of one
+                    if (need_w && cx.rank == 0 && k < n) {
                         clamp_one_kernel<<<1, 1, 0, cx.stream>>>(d_W.p, k, 1e-5, skip);
                         cx.st.kernel_launches += 1;
                     }
@@ -417,9 +395,7 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                         cx.all_reduce(d_g.p, (int64_t)p + 1, speculate ? skip : nullptr);
                         tm.stop(t_ar);
                     }
-                    // XY = XX beta + grad (:999)
-                    irls_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p, skip);
-                    cx.st.kernel_launches += 1;
+                    form_xy = true;           // XY = XX beta + grad (:999): formed by the path launch below
                 }
                 // inner OEM loop: one chain, one lambda, warm start (oem_logistic_dense.h:1010-1022)
                 PathProblem pr;
@@ -439,11 +415,12 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                 pr.beta_out = nxt; pr.niter_out = d_niter.p; pr.lanczos_steps = d_lz.p;
                 pr.scratch = scratch.s;
                 pr.skip = skip;
+                if (form_xy) { pr.xy_grad = d_g.p; pr.xy_cinv = cinv_dev; pr.xy_n = n_tot; pr.xy_icpt = icpt; pr.xy_out = d_XY.p; }
                 const size_t t3 = tm.start(&cx.st.ms_path);
                 path_launch(cx, pr);
                 tm.stop(t3);
                 irls_stop_kernel<<<1, 256, 0, cx.stream>>>(nxt, cur, q, o->irls_tol, d_niter.p, d_iters_total.p,
-                                                           flag.p + (gi & 3), d_conv.p);
+                                                           flag.p + (gi & 3), d_conv.p, cinv_dev, p, icpt, d_b.p, d_b0.p);
                 cx.st.kernel_launches += 1;
                 OEM_CUDA(cudaEventRecord(ev_done[gi & 1], cx.stream));
                 ++gi;
@@ -709,8 +686,8 @@ void fit_logistic_sparse(const int *row_idx, const int *col_ptr, const double *v
                     logit_sparse_assemble_kernel<<<(unsigned)(((size_t)q * q + 255) / 256), 256, 0, cx.stream>>>(
                         p, icpt, G, statsW + (size_t)p, cinv_dev, intval, xxdiag, n_tot, d_XX.p);
                     irls_pack_grad_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(statsR + (size_t)p, rs, p, d_g.p);
-                    irls_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p, nullptr);
-                    cx.st.kernel_launches += 3;
+                    cx.st.kernel_launches += 2;
+                    path_xy_launch(cx, q, icpt, d_XX.p, cur, d_g.p, cinv_dev, n_tot, d_XY.p, nullptr);
                     rebuilt = true;
                 }
                 PathProblem pr;

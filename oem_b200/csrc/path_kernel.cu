@@ -87,6 +87,11 @@ struct PathArgs {
     int *gflags;             // ngram x 2 x team_size violation masks (global mode)
     long long *prof;         // optional (debug): cycle counters of CTA 0 / thread 0
     const int *skip;         // optional: the whole launch is a no-op when *skip != 0 (speculatively enqueued IRLS iterations)
+    // register mode only: form XY = XX beta_init + grad in the prologue (PathProblem::xy_grad)
+    const double *xy_grad, *xy_cinv;
+    double xy_n;
+    int xy_icpt, pad2;
+    double *xy_out;
 };
 
 __device__ __forceinline__ double pk_warp_sum(double v) {
@@ -747,7 +752,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     }
     for (int e = threadIdx.x; e < 2 * nvec * qs; e += PK_THREADS) B0[e] = 0.0;
     for (int j = threadIdx.x; j < q; j += PK_THREADS) {
-        xy[j] = a.XY[(size_t)team * q + j];
+        xy[j] = (RPT > 0 && a.xy_grad) ? 0.0 : a.XY[(size_t)team * q + j];
         pf[j] = a.pen_fact ? a.pen_fact[j] : 1.0;
         if (a.ngroups) cover[j] = a.grp_cover[j];
         if (a.post_scale) psm[j] = a.post_scale[j];
@@ -936,6 +941,48 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
         }
     } else {
         dval = a.d[team];
+    }
+
+    // ---- logistic inner loop: XY = XX beta_init + grad for MY columns, from the XX slice in registers (the only entries of
+    //      XY this member ever reads are its own; they also go to xy_out, which a later launch without a data pass reuses) ----
+    if constexpr (RPT > 0) {
+        if (a.xy_grad && nct > 0) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < qs; e += PK_THREADS)
+                B0[e] = (e < q && a.beta_init) ? a.beta_init[(size_t)a.chains[a.team_idx[ct0]].out_off * q + e] : 0.0;
+            __syncthreads();
+            double acc1[1][8], tot1[1];
+#pragma unroll
+            for (int jl = 0; jl < 8; ++jl) acc1[0][jl] = 0.0;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int i = threadIdx.x + r * PK_THREADS;
+                if (i < qs) {
+                    const double b = B0[i];
+#pragma unroll
+                    for (int jl = 0; jl < 8; ++jl) acc1[0][jl] = fma(areg[jl][r], b, acc1[0][jl]);
+                }
+            }
+            reduce_cols<1, 8>(acc1, tot1, lane);
+            if ((lane & 3) == 0) part[warp * 8 + (lane >> 2)] = tot1[0];
+            __syncthreads();
+            if (threadIdx.x < 8 && c0 + (int)threadIdx.x < c1) {
+                const int jr = c0 + threadIdx.x;
+                double sxy = part[threadIdx.x];
+#pragma unroll
+                for (int w = 1; w < PK_WARPS; ++w) sxy += part[w * 8 + threadIdx.x];
+                double gr;
+                if (a.xy_icpt && jr == 0) gr = a.xy_grad[0] / a.xy_n;
+                else {
+                    const int jx = jr - a.xy_icpt;
+                    gr = a.xy_grad[1 + jx] / a.xy_n;
+                    if (a.xy_cinv) gr *= a.xy_cinv[jx];
+                }
+                xy[jr] = sxy + gr;
+                a.xy_out[(size_t)team * q + jr] = sxy + gr;
+            }
+            __syncthreads();
+        }
     }
 
     if (nct > 0) {
@@ -1396,6 +1443,47 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathA
 
 // Shared memory every member of a generic path launch needs besides its slice of A: the ping-pong iterates of all the
 // team's chains, XY, per-lambda tables, the Lanczos tridiagonal, group tables.
+// XY = XX beta + grad with grad = [g0 / n, (g_j / n) o colsq_inv] (oem_logistic_dense.h:970-999).  One warp per row.
+__global__ void path_xy_kernel(int q, int icpt, const double *__restrict__ XX, const double *__restrict__ beta,
+                               const double *__restrict__ g, const double *__restrict__ cinv, double n_tot,
+                               double *__restrict__ XY, const int *__restrict__ skip) {
+    if (skip && *skip) return;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= q) return;
+    const int lane = threadIdx.x & 31;
+    // four independent partial sums per lane: the 8 MB of XX come from L2, one dependent FMA chain per lane left the loads
+    // of a row serialised (12 us per call at q = 1001, once per IRLS data pass)
+    const double *row = XX + (size_t)r * q;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = lane;
+    for (; c + 96 < q; c += 128) {
+        const double x0 = __ldg(row + c), x1 = __ldg(row + c + 32), x2 = __ldg(row + c + 64), x3 = __ldg(row + c + 96);
+        s0 = fma(x0, beta[c], s0); s1 = fma(x1, beta[c + 32], s1);
+        s2 = fma(x2, beta[c + 64], s2); s3 = fma(x3, beta[c + 96], s3);
+    }
+    for (; c < q; c += 32) s0 = fma(__ldg(row + c), beta[c], s0);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        double gr;
+        if (icpt && r == 0) gr = g[0] / n_tot;
+        else {
+            const int j = r - icpt;
+            gr = g[1 + j] / n_tot;
+            if (cinv) gr *= cinv[j];
+        }
+        XY[r] = s + gr;
+    }
+}
+
+void path_xy_launch(Ctx &cx, int q, int icpt, const double *XX, const double *beta, const double *g, const double *cinv, double n_tot,
+                    double *XY, const int *skip) {
+    path_xy_kernel<<<(q + 7) / 8, 256, 0, cx.stream>>>(q, icpt, XX, beta, g, cinv, n_tot, XY, skip);
+    OEM_CUDA(cudaGetLastError());
+    cx.st.kernel_launches += 1;
+}
+
 static size_t path_fixed_smem_bytes(int q, int max_ct, int Lmax, int ng, int ngidx, bool post = false) {
     const int nvec = std::max(max_ct, 2);
     const int q4 = (q + 3) / 4 * 4;
@@ -1638,6 +1726,17 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     a.beta_final = pp.beta_final; a.beta_out = pp.beta_out; a.niter_out = pp.niter_out;
     a.lanczos_steps = pp.lanczos_steps; a.ubuf = d_ubuf.p; a.barriers = d_bar.p; a.gflags = d_gflags_p;
     a.skip = pp.skip;
+
+    if (pp.xy_grad) {
+        if (G != 1 || pp.chains.size() != 1 || !pp.xy_out || pp.xy_out != pp.XY || !pp.beta_init)
+            fail(OEMB200_EINVAL, "path: xy_grad needs one Gram, one chain, a warm start and xy_out == XY");
+        if (rpt > 0) {
+            a.xy_grad = pp.xy_grad; a.xy_cinv = pp.xy_cinv; a.xy_n = pp.xy_n; a.xy_icpt = pp.xy_icpt; a.xy_out = pp.xy_out;
+        } else {
+            path_xy_launch(cx, q, pp.xy_icpt, pp.XX, pp.beta_init + (size_t)pp.chains[0].out_off * q, pp.xy_grad, pp.xy_cinv, pp.xy_n,
+                           pp.xy_out, pp.skip);
+        }
+    }
 
     DBuf<long long> d_prof;
     const bool prof = getenv("OEMB200_PATH_PROF") != nullptr;

@@ -24,17 +24,19 @@ struct PhaseTimers {
     struct Rec { cudaEvent_t a, b; double *acc; };
     std::vector<Rec> recs;
     cudaStream_t s;
+    bool off = getenv("OEMB200_NO_PHASE_TIMERS") != nullptr;   // experiment: what do the event records themselves cost?
     explicit PhaseTimers(cudaStream_t s_) : s(s_) {}
     PhaseTimers(const PhaseTimers &) = delete;
     ~PhaseTimers() { for (auto &r : recs) { event_release(r.a); event_release(r.b); } }
     size_t start(double *acc) {
+        if (off) return 0;
         Rec r; r.acc = acc;
         r.a = event_acquire(); r.b = event_acquire();
         OEM_CUDA(cudaEventRecord(r.a, s));
         recs.push_back(r);
         return recs.size() - 1;
     }
-    void stop(size_t i) { OEM_CUDA(cudaEventRecord(recs[i].b, s)); }
+    void stop(size_t i) { if (!off) OEM_CUDA(cudaEventRecord(recs[i].b, s)); }
     void collect() {   // call after the stream is synchronized
         for (auto &r : recs) {
             float ms = 0.f;
@@ -223,8 +225,18 @@ struct PathProblem {
     int *lanczos_steps = nullptr;  // device, ngram (may be NULL)
     PathScratch *scratch = nullptr;   // optional, see above
     const int *skip = nullptr;        // optional device flag: the launch does nothing when it is non-zero
+    // Logistic inner loop (src/oem_logistic_dense.h:970-999): with xy_grad set the launch first forms
+    //   XY = XX beta_init + [g[0] / n, (g[1 + j] / n) o cinv[j]]
+    // into xy_out (which must be the buffer XY points at; one Gram, one chain).  The register-mode kernel does it with the
+    // XX slice it has just loaded; the other modes run path_xy_launch in front.
+    const double *xy_grad = nullptr, *xy_cinv = nullptr;
+    double xy_n = 0.0;
+    int xy_icpt = 0;
+    double *xy_out = nullptr;
 };
 void path_launch(Ctx &cx, const PathProblem &pp);
+void path_xy_launch(Ctx &cx, int q, int icpt, const double *XX, const double *beta, const double *g, const double *cinv, double n_tot,
+                    double *XY, const int *skip);
 // throws OEMB200_EUNSUPPORTED if a beta of dimension q (chains_per_gram penalties, Lmax lambdas) cannot be held by the path kernel
 void path_check_fits(Ctx &cx, int q, int chains_per_gram, int Lmax, int ngroups, int ngidx);
 

@@ -55,7 +55,7 @@ def line(name, wall, out, extra):
     d = {"config": name, "wall_s": wall, "phases_ms": {k: round(v, 3) for k, v in st.items() if k.startswith("ms_")},
          "oem_iterations": st["total_oem_iters"], "kernel_launches": st["kernel_launches"]}
     if st["gram_launches"]:
-        d["gram_tflops"] = st["gram_flops"] / (st["ms_gram"] / 1e3) / 1e12
+        d["gram_tflops"] = st["gram_flops"] / (max(st["ms_gram"], 1e-9) / 1e3) / 1e12
     d.update(extra(st) if extra else {})
     print(json.dumps(d), flush=True)
 
@@ -106,7 +106,7 @@ def main():
         args = [X, y, "binomial", ["lasso"], [], [], [], [], [], 100, 1e-4, 1.0, 3.0, 0.5, np.ones(p), True, True, False, dict(opts)]
         w, out = timed(lambda: oem_b200.oem_fit_logistic_dense(*args), max(1, a.reps - 1))
         line("configs[3] logistic lasso n=2e6 p=1000", w, out,
-             lambda st: {"data_pass_gbs": st["gemv_bytes"] / ((st["ms_irls_xb"] + st["ms_irls_xtr"]) / 1e3) / 1e9,
+             lambda st: {"data_pass_gbs": st["gemv_bytes"] / (max(st["ms_irls_xb"] + st["ms_irls_xtr"], 1e-9) / 1e3) / 1e9,
                          "ms_per_irls_data_pass": (st["ms_irls_xb"] + st["ms_irls_xtr"]) / max(1, st["xb_launches"]),
                          "irls_iterations": int(np.sum(out["niter"][0])), "xb_launches": st["xb_launches"]})
         del X, y
