@@ -82,10 +82,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        raise OemB200Error(-1, f"{_LIB_PATH} is missing: run `python -m oem_b200.build` "
+    path = os.environ.get("OEMB200_LIB_PATH", _LIB_PATH)      # A/B runs of two builds of the same ABI (tools/ab_build.sh)
+    if not os.path.exists(path):
+        raise OemB200Error(-1, f"{path} is missing: run `python -m oem_b200.build` "
                                "(the CUDA extension is the only implementation; there is no CPU fallback)")
-    L = ctypes.CDLL(_LIB_PATH)
+    L = ctypes.CDLL(path)
     L.oemb200_last_error.restype = ctypes.c_char_p
     L.oemb200_version.restype = ctypes.c_char_p
     L.oemb200_device_count.restype = ctypes.c_int
