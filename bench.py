@@ -600,7 +600,7 @@ def run_e2e(torch, api, oem_b200, X, y, rows, opts, timed, args, st_dev):
         out["h2d_probe_error"] = repr(e)
     if pinned:
         cudart.cudaHostUnregister(Xh.data_ptr())
-    if all_pinned:      # a decision every rank takes alike: the fit below contains collectives
+    if all_pinned and world == 1:      # single-process only: at N > 1 the pinned figure above is the e2e number
         # the same call once more from PAGEABLE memory (what an R matrix or a numpy array is): the library stages it through
         # its pinned bounce ring + reader threads (csrc/ingest.cu).  Reported next to the pinned figure, not instead of it.
         try:
