@@ -119,6 +119,7 @@ struct P2pArgs {
     int rank, world;
     unsigned long long *epoch_dev;     // this rank's count of EXECUTED collectives (skipped launches do not advance it)
     const int *skip;                   // optional: no-op when *skip != 0 (the flag is identical on every rank)
+    unsigned long long *t_acc;         // optional: += this launch's duration in ns (device-side phase clock)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -129,16 +130,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 // buf (count doubles, 16-byte aligned when count > 1) <- sum over ranks, in rank order.  One CTA.
 __global__ void __launch_bounds__(P2P_THREADS, 1)
 p2p_allreduce_kernel(const P2pArgs a, double *__restrict__ buf, int count) {
     if (a.skip && *a.skip) return;
+    const unsigned long long t_in = (a.t_acc && threadIdx.x == 0) ? global_timer_ns() : 0ull;
     // the epoch lives on the device: ranks skip the same launches, so their counters agree, and two consecutive EXECUTED
     // collectives always use different mailbox slots even when predicated launches were enqueued between them
     const unsigned long long epoch = *a.epoch_dev + 1ull;
@@ -172,7 +169,10 @@ p2p_allreduce_kernel(const P2pArgs a, double *__restrict__ buf, int count) {
         for (int r = 1; r < a.world; ++r) s += __ldcg(mine + (size_t)r * kSlotDoubles + i);
         buf[i] = s;
     }
-    if (threadIdx.x == 0) *a.epoch_dev = epoch;      // read again only by the next launch on this stream
+    if (threadIdx.x == 0) {
+        *a.epoch_dev = epoch;      // read again only by the next launch on this stream
+        if (a.t_acc) *a.t_acc += global_timer_ns() - t_in;
+    }
 }
 
 // Map every rank's mailbox.  Collective: the IPC handles travel through an ncclAllGather, the go / no-go decision
@@ -253,7 +253,7 @@ bool comm_can_skip(const oemb200_comm *c, int64_t count) {
     return !c || c->world <= 1 || (c->p2p && count <= OEMB200_P2P_MAX_DOUBLES);
 }
 
-void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream, const int *skip) {
+void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream, const int *skip, unsigned long long *t_acc) {
     if (!c || c->world <= 1 || count <= 0) return;
     const bool aligned = count == 1 || (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0;
     if (skip && !(c->p2p && count <= OEMB200_P2P_MAX_DOUBLES && aligned))
@@ -265,7 +265,7 @@ void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream
             a.peer_data[r] = static_cast<double *>(c->peer_base[r]);
             a.peer_flags[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(c->peer_base[r]) + mailbox_data_bytes(c->world));
         }
-        a.rank = c->rank; a.world = c->world; a.skip = skip;
+        a.rank = c->rank; a.world = c->world; a.skip = skip; a.t_acc = t_acc;
         a.epoch_dev = reinterpret_cast<unsigned long long *>(static_cast<char *>(c->mailbox_base) + mailbox_data_bytes(c->world) +
                                                              2 * (size_t)P2P_MAX_WORLD * 8);
         p2p_allreduce_kernel<<<1, P2P_THREADS, 0, stream>>>(a, dev_buf, (int)count);

@@ -293,6 +293,12 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     // One IRLS iteration as a chain of kernels on the stream (k = IRLS counter of this lambda).  Every kernel of the chain
     // takes `d_conv` as its predicate, so an iteration enqueued AFTER the loop has converged costs a few empty launches.
     DBuf<int> d_conv(1);
+    // Phase clocks of the per-iteration kernels live on the device (%globaltimer, accumulated by the kernels themselves): a
+    // pair of event records around each of them cost ~21 us of stream time per IRLS iteration, 6 % of a sharded fit.
+    //   [0] data passes (slab kernel start -> end of its partial-sum kernel), [1] scratch, [2] path launches, [3] all-reduces
+    DBuf<unsigned long long> d_clk(4);
+    d_clk.zero(cx.stream);
+    const bool clk_allreduce = cx.comm != nullptr && cx.all_reduce_can_skip((int64_t)p + 1);     // the peer-memory kernel
     // Speculation: enqueue iteration k + 1 before reading iteration k's verdict, so the GPU never waits for the host round
     // trip (the gap was ~100 us per iteration: 5 % of the fit on one GPU, 25 % row-sharded over eight).  Possible when every
     // kernel of the chain can be predicated: slab route, upper-bound Hessian (the Gram launch cannot), and a cross-rank sum
@@ -321,10 +327,8 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                         cx.st.kernel_launches += 1;
                     }
                     if (slab) {
-                        // one kernel, one HBM sweep: prob, W and the gradient sums [sum r, X'r]
-                        const size_t t1 = tm.start(&cx.st.ms_irls_xb);
-                        logit_slab_launch(cx, slabs_p, n, p, d_b.p, d_b0.p, yv.p, d_prob.p, d_W.p, d_g.p, skip);
-                        tm.stop(t1);
+                        // one kernel, one HBM sweep: prob, W and the gradient sums [sum r, X'r] (timed on the device: d_clk)
+                        logit_slab_launch(cx, slabs_p, n, p, d_b.p, d_b0.p, yv.p, d_prob.p, d_W.p, d_g.p, skip, d_clk.p + 0);
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (3.0 * n + 2.0 * p);
                     } else {
                         const size_t t1 = tm.start(&cx.st.ms_irls_xb);
@@ -391,9 +395,13 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                         cx.st.gemv_bytes += 8.0 * n * p + 8.0 * (n + p);
                     }
                     if (cx.distributed()) {
-                        const size_t t_ar = tm.start(&cx.st.ms_allreduce);
-                        cx.all_reduce(d_g.p, (int64_t)p + 1, speculate ? skip : nullptr);
-                        tm.stop(t_ar);
+                        if (clk_allreduce) {
+                            cx.all_reduce(d_g.p, (int64_t)p + 1, speculate ? skip : nullptr, d_clk.p + 3);
+                        } else {
+                            const size_t t_ar = tm.start(&cx.st.ms_allreduce);
+                            cx.all_reduce(d_g.p, (int64_t)p + 1, speculate ? skip : nullptr);
+                            tm.stop(t_ar);
+                        }
                     }
                     form_xy = true;           // XY = XX beta + grad (:999): formed by the path launch below
                 }
@@ -416,12 +424,12 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                 pr.scratch = scratch.s;
                 pr.skip = skip;
                 if (form_xy) { pr.xy_grad = d_g.p; pr.xy_cinv = cinv_dev; pr.xy_n = n_tot; pr.xy_icpt = icpt; pr.xy_out = d_XY.p; }
-                const size_t t3 = tm.start(&cx.st.ms_path);
+                pr.t_acc = d_clk.p + 2;
+                // the outer loop's stop rule, its verdicts and the next pass's coefficients are the launch's last step
+                pr.irls_conv = d_conv.p; pr.irls_host_flag = flag.p + (gi & 3); pr.irls_iters_total = d_iters_total.p;
+                pr.irls_tol = o->irls_tol; pr.irls_cinv = cinv_dev; pr.irls_p = p; pr.irls_icpt = icpt;
+                pr.irls_b = d_b.p; pr.irls_b0 = d_b0.p;
                 path_launch(cx, pr);
-                tm.stop(t3);
-                irls_stop_kernel<<<1, 256, 0, cx.stream>>>(nxt, cur, q, o->irls_tol, d_niter.p, d_iters_total.p,
-                                                           flag.p + (gi & 3), d_conv.p, cinv_dev, p, icpt, d_b.p, d_b0.p);
-                cx.st.kernel_launches += 1;
                 OEM_CUDA(cudaEventRecord(ev_done[gi & 1], cx.stream));
                 ++gi;
             };
@@ -475,7 +483,12 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     d_path.download(hpath.data(), hpath.size(), cx.stream);
     d_iters_total.download(&iters_total, 1, cx.stream);
     d_d.download(&dval, 1, cx.stream);
+    unsigned long long hclk[4] = {0, 0, 0, 0};
+    d_clk.download(hclk, 4, cx.stream);
     cx.sync();
+    cx.st.ms_irls_xb += (double)hclk[0] * 1e-6;
+    cx.st.ms_path += (double)hclk[2] * 1e-6;
+    cx.st.ms_allreduce += (double)hclk[3] * 1e-6;
     cx.st.d2h_bytes += (int64_t)hpath.size() * 8;
     cx.st.total_oem_iters += iters_total;
     for (int pp = 0; pp < su.P; ++pp)

@@ -43,9 +43,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 logit_slab_kernel(const double *__restrict__ slabs, long long n, int p, size_t stage_stride /* doubles */,
                   const double *__restrict__ b, const double *__restrict__ b0_ptr, const double *__restrict__ y,
                   double *__restrict__ prob, double *__restrict__ wout, double *__restrict__ partial,
-                  const int *__restrict__ skip) {
+                  const int *__restrict__ skip, unsigned long long *__restrict__ t_clock) {
     static_assert(RT == 4 || RT == 8 || RT == 16, "rows per slab");
     if (skip && *skip) return;               // speculatively enqueued pass of an IRLS loop that has already converged
+    if (t_clock && blockIdx.x == 0 && threadIdx.x == 0) t_clock[1] = global_timer_ns();    // start mark of the pass
     constexpr int LOG_RT = RT == 4 ? 2 : (RT == 8 ? 3 : 4);
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -194,7 +195,8 @@ logit_slab_kernel(const double *__restrict__ slabs, long long n, int p, size_t s
 // 8th row, then a fixed-order sum of the 8 lanes: same result for a given grid on every run, ~5 us instead of the 32 us a
 // one-thread-per-column loop over ~300 rows took.
 __global__ void __launch_bounds__(256) ls_sum_partials_kernel(const double *__restrict__ partial, int nparts, int width,
-                                                              double *__restrict__ out, const int *__restrict__ skip) {
+                                                              double *__restrict__ out, const int *__restrict__ skip,
+                                                              unsigned long long *__restrict__ t_clock) {
     __shared__ double sm[8][33];
     if (skip && *skip) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -210,6 +212,8 @@ __global__ void __launch_bounds__(256) ls_sum_partials_kernel(const double *__re
         for (int r = 1; r < 8; ++r) t += sm[r][tx];
         out[k] = t;
     }
+    // device-side phase clock: slab kernel start -> (about) the end of this reduction
+    if (t_clock && blockIdx.x == 0 && threadIdx.x == 0) t_clock[0] += global_timer_ns() - t_clock[1];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -280,7 +284,7 @@ void logit_slab_relayout(Ctx &cx, const double *X, int64_t n, int p, int64_t ld,
 
 // grad_out[0] = sum r, grad_out[1 + j] = sum_i x_ij r_i (device, p + 1 doubles); b0 is read from device memory
 void logit_slab_launch(Ctx &cx, const double *slabs, int64_t n, int p, const double *b, const double *b0_dev,
-                       const double *y, double *prob, double *w, double *grad_out, const int *skip) {
+                       const double *y, double *prob, double *w, double *grad_out, const int *skip, unsigned long long *t_clock) {
     const SlabShape sh = slab_shape(p);
     if (!sh.rt) fail(OEMB200_EINVAL, "slab route does not apply to p = %d", p);
     const int rt = sh.rt;
@@ -300,9 +304,9 @@ void logit_slab_launch(Ctx &cx, const double *slabs, int64_t n, int p, const dou
     DBuf<double> partial((size_t)grid * (p + 1));       // every CTA writes its whole row
     long long nn = n;
     void *args[] = {(void *)&slabs, &nn, &p, (void *)&stage_stride, (void *)&b, (void *)&b0_dev, (void *)&y, &prob, &w, &partial.p,
-                    (void *)&skip};
+                    (void *)&skip, (void *)&t_clock};
     OEM_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(sh.threads), args, smem, cx.stream));
-    ls_sum_partials_kernel<<<(p + 1 + 31) / 32, 256, 0, cx.stream>>>(partial.p, grid, p + 1, grad_out, skip);
+    ls_sum_partials_kernel<<<(p + 1 + 31) / 32, 256, 0, cx.stream>>>(partial.p, grid, p + 1, grad_out, skip, t_clock);
     OEM_CUDA(cudaGetLastError());
     cx.st.kernel_launches += 2;
     cx.st.xb_launches += 1;

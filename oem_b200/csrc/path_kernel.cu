@@ -92,6 +92,15 @@ struct PathArgs {
     double xy_n;
     int xy_icpt, pad2;
     double *xy_out;
+    unsigned long long *t_acc;   // optional: += duration of the launch in ns (CTA 0, device-side phase clock)
+    // IRLS epilogue (PathProblem::irls_*)
+    int *irls_conv;
+    volatile int *irls_host_flag;
+    long long *irls_iters_total;
+    double irls_tol;
+    const double *irls_cinv;
+    int irls_p, irls_icpt;
+    double *irls_b, *irls_b0;
 };
 
 __device__ __forceinline__ double pk_warp_sum(double v) {
@@ -674,6 +683,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
     static_assert(RPT == 0 || MODE == MODE_GLOBAL, "the register mat-vec belongs to the global mode");
     extern __shared__ __align__(16) double sm[];
     if (a.skip && *a.skip) return;           // uniform over the grid: nobody reaches a barrier
+    const unsigned long long t_in = (a.t_acc && blockIdx.x == 0 && threadIdx.x == 0) ? global_timer_ns() : 0ull;
     const int q = a.q, qs = a.qs;            // qs = padded vector / slice stride, = 4 (mod 16), >= roundup(q, 4)
     const int team = blockIdx.x / a.team_size, rank = blockIdx.x - team * a.team_size;
     const int c0 = min(q, rank * a.cpc), c1 = min(q, c0 + a.cpc);
@@ -1188,8 +1198,31 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
                 a.beta_final[(size_t)chi[2 * PK_MAXCT + c] * q + j] = Bc[(size_t)c * qs + j];
             }
         }
+        // ---- IRLS epilogue: the outer loop's stop rule on (final iterate, warm start), verdicts, next pass's coefficients ----
+        if (a.irls_conv && blockIdx.x == 0) {
+            __syncthreads();
+            const double *Bc = cur ? B1 : B0;                                   // chain 0 (the only one)
+            const double *prev = a.beta_init + (size_t)chi[2 * PK_MAXCT] * q;
+            int v = 0;
+            for (int i = threadIdx.x; i < q; i += PK_THREADS) {
+                const double cv = Bc[i], pv = prev[i];
+                const double ac = fabs(cv), ap = fabs(pv);
+                if ((ac > 1e-13 && ap <= 1e-13) || (ac <= 1e-13 && ap > 1e-13)) v = 1;
+                else if (ac > 1e-13 && ap > 1e-13 && fabs((cv - pv) / pv) > a.irls_tol) v = 1;
+                const int j = i - a.irls_icpt;
+                if (a.irls_b && j >= 0 && j < a.irls_p) a.irls_b[j] = a.irls_cinv ? cv * a.irls_cinv[j] : cv;
+            }
+            v = __syncthreads_or(v);
+            if (threadIdx.x == 0) {
+                if (a.irls_b0) *a.irls_b0 = a.irls_icpt ? Bc[0] : 0.0;
+                if (a.irls_iters_total) *a.irls_iters_total += a.niter_out[(size_t)chi[2 * PK_MAXCT] * a.Lmax];
+                if (!v) *a.irls_conv = 1;
+                if (a.irls_host_flag) *a.irls_host_flag = v ? 0 : 1;      // read by the host after this launch's event
+            }
+        }
     }
     if (MODE == MODE_CLUSTER) cluster_sync_all();   // no member may exit while peers can still write its shared memory
+    if (a.t_acc && blockIdx.x == 0 && threadIdx.x == 0) *a.t_acc += global_timer_ns() - t_in;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1533,7 +1566,7 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     // ---- small coordinate-wise problems: register-resident variant (d comes from a Lanczos-only generic launch) ----
     {
         bool reg_ok = getenv("OEMB200_PATH_GENERIC") == nullptr && q <= 256 && !pp.accelerate && !pp.post_scale &&
-                      !pp.beta_init && !pp.beta_final && !pp.skip && max_ct <= PR_MAXCT && !pp.chains.empty();
+                      !pp.beta_init && !pp.beta_final && !pp.skip && !pp.irls_conv && max_ct <= PR_MAXCT && !pp.chains.empty();
         for (auto &c : pp.chains) reg_ok = reg_ok && c.penalty < OEMB200_PEN_GRP_LASSO;
         const int NC = q <= 128 ? 1 : (q + 31) / 32;
         const int QP = q <= 128 ? 128 : 256;
@@ -1725,7 +1758,14 @@ void path_launch(Ctx &cx, const PathProblem &pp) {
     a.group_weights = pp.group_weights; a.post_scale = pp.post_scale; a.beta_init = pp.beta_init;
     a.beta_final = pp.beta_final; a.beta_out = pp.beta_out; a.niter_out = pp.niter_out;
     a.lanczos_steps = pp.lanczos_steps; a.ubuf = d_ubuf.p; a.barriers = d_bar.p; a.gflags = d_gflags_p;
-    a.skip = pp.skip;
+    a.skip = pp.skip; a.t_acc = pp.t_acc;
+    if (pp.irls_conv) {
+        if (G != 1 || pp.chains.size() != 1 || pp.chains[0].nlam != 1 || !pp.beta_init)
+            fail(OEMB200_EINVAL, "path: the IRLS epilogue needs one Gram, one chain, one lambda and a warm start");
+        a.irls_conv = pp.irls_conv; a.irls_host_flag = pp.irls_host_flag; a.irls_iters_total = pp.irls_iters_total;
+        a.irls_tol = pp.irls_tol; a.irls_cinv = pp.irls_cinv; a.irls_p = pp.irls_p; a.irls_icpt = pp.irls_icpt;
+        a.irls_b = pp.irls_b; a.irls_b0 = pp.irls_b0;
+    }
 
     if (pp.xy_grad) {
         if (G != 1 || pp.chains.size() != 1 || !pp.xy_out || pp.xy_out != pp.XY || !pp.beta_init)

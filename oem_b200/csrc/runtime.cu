@@ -155,9 +155,9 @@ bool Ctx::all_reduce_can_skip(int64_t count) const {
     return allreduce == nullptr;
 }
 
-void Ctx::all_reduce(double *dev_buf, int64_t count, const int *skip) {
+void Ctx::all_reduce(double *dev_buf, int64_t count, const int *skip, unsigned long long *t_acc) {
     if (comm) {
-        comm_all_reduce(comm, dev_buf, count, stream, skip);
+        comm_all_reduce(comm, dev_buf, count, stream, skip, t_acc);
     } else if (allreduce) {
         if (skip) fail(OEMB200_ECOMM, "a predicated all-reduce needs the in-library peer-memory transport");
         const int rc = allreduce(dev_buf, count, stream, allreduce_ctx);

@@ -64,7 +64,7 @@ struct Ctx {
     void sync() { st.host_syncs += 1; OEM_CUDA(cudaStreamSynchronize(stream)); }
     bool distributed() const { return comm != nullptr || allreduce != nullptr; }
     // in-place sum over ranks, ordered on `stream`; no-op in single-process runs
-    void all_reduce(double *dev_buf, int64_t count, const int *skip = nullptr);
+    void all_reduce(double *dev_buf, int64_t count, const int *skip = nullptr, unsigned long long *t_acc = nullptr);
     bool all_reduce_can_skip(int64_t count) const;   // true in single-process runs and on the peer-memory transport
     void finish();                 // sync the stream, fold the event timings into st
 };
@@ -150,7 +150,8 @@ void release_host_stager();
 // ---------------- comm.cu ----------------
 // skip (optional device flag, identical on every rank): the collective is a no-op when *skip != 0; only the peer-memory
 // transport can honour it (comm_can_skip), NCCL collectives cannot be predicated from the device
-void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream, const int *skip = nullptr);
+void comm_all_reduce(oemb200_comm *c, double *dev_buf, int64_t count, cudaStream_t stream, const int *skip = nullptr,
+                     unsigned long long *t_acc = nullptr);      // t_acc: device ns accumulator of the peer-memory kernel
 bool comm_can_skip(const oemb200_comm *c, int64_t count);
 
 // ---------------- gram_syrk.cu ----------------
@@ -225,6 +226,19 @@ struct PathProblem {
     int *lanczos_steps = nullptr;  // device, ngram (may be NULL)
     PathScratch *scratch = nullptr;   // optional, see above
     const int *skip = nullptr;        // optional device flag: the launch does nothing when it is non-zero
+    // Outer (IRLS) loop of the logistic entries folded into the launch's last step (one Gram, one chain, one lambda): the
+    // stop rule stopRule(beta_new, beta_init, irls_tol) (src/utils.cpp:537-549, called at src/oem_logistic_dense.h:1028),
+    // its verdict for the device (*irls_conv = 1: every later launch predicated on it returns at once) and for the host
+    // (*irls_host_flag, mapped pinned memory), the running count of inner iterations, and the coefficients the NEXT data
+    // pass multiplies X with: b = beta_new[icpt:] o cinv, b0 = beta_new[0] (src/oem_logistic_dense.h:875-890).
+    int *irls_conv = nullptr;
+    volatile int *irls_host_flag = nullptr;
+    long long *irls_iters_total = nullptr;
+    double irls_tol = 0.0;
+    const double *irls_cinv = nullptr;
+    int irls_p = 0, irls_icpt = 0;
+    double *irls_b = nullptr, *irls_b0 = nullptr;
+    unsigned long long *t_acc = nullptr;   // optional device word: += the kernel's duration in ns (%globaltimer of team 0's first member)
     // Logistic inner loop (src/oem_logistic_dense.h:970-999): with xy_grad set the launch first forms
     //   XY = XX beta_init + [g[0] / n, (g[1 + j] / n) o cinv[j]]
     // into xy_out (which must be the buffer XY points at; one Gram, one chain).  The register-mode kernel does it with the
@@ -265,7 +279,8 @@ void logit_slab_relayout(Ctx &cx, const double *X, int64_t n, int p, int64_t ld,
 // one pass over the slabs: prob, w (may be NULL), grad_out[0] = sum (y - prob), grad_out[1 + j] = sum_i x_ij (y_i - prob_i)
 // skip (optional device flag): the pass does nothing and leaves every output untouched when *skip != 0
 void logit_slab_launch(Ctx &cx, const double *slabs, int64_t n, int p, const double *b, const double *b0_dev,
-                       const double *y, double *prob, double *w, double *grad_out, const int *skip = nullptr);
+                       const double *y, double *prob, double *w, double *grad_out, const int *skip = nullptr,
+                       unsigned long long *t_clock = nullptr);   // t_clock (device, 2 words): [0] += ns of the pass, [1] scratch
 
 // ---------------- cvscore.cu ----------------
 // order[i]: for every tile of fold_gather_tile_rows() source rows, the tile-local row indices grouped by fold
