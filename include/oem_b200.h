@@ -39,7 +39,7 @@ extern "C" {
 #define OEMB200_EINVAL      1   /* bad argument (message says which) */
 #define OEMB200_ENODEVICE   2   /* no CUDA device / driver */
 #define OEMB200_ECUDA       3   /* a CUDA call or kernel failed */
-#define OEMB200_EUNSUPPORTED 4  /* reference feature outside the hot path (n<=p, sparse, weights outside xval) */
+#define OEMB200_EUNSUPPORTED 4  /* a shape or flag combination the reference itself leaves undefined or incoherent (the message cites where) */
 #define OEMB200_ECOMM       5   /* the all-reduce callback failed */
 
 /* Penalty ids, in the order the oracle uses (oracle/oem_oracle.c). Names are the R strings. */
@@ -204,8 +204,9 @@ int oemb200_fit_big(const double *x, int64_t n, int p, int64_t ldx, const double
 
 /* src/oem_sparse.cpp:30 -- x is a Matrix::dgCMatrix (what R/oem.R:236-240 coerces every sparseMatrix to), passed as its
  * three slots: row_idx = x@i (nnz 0-based row indices), col_ptr = x@p (p + 1 column pointers, col_ptr[p] = nnz),
- * values = x@x; host or device pointers.  Gaussian family, n > p.  Same result layout as oemb200_fit_dense
- * (beta (p+1) x L per penalty, row 0 = intercept). */
+ * values = x@x; host or device pointers.  Gaussian family; n > p, and n <= p without an intercept (src/oem_sparse.h:609-616,
+ * 630-640: the raw-X iteration; with an intercept the reference runs past the end of XY and beta there: OEMB200_EUNSUPPORTED).
+ * Same result layout as oemb200_fit_dense (beta (p+1) x L per penalty, row 0 = intercept). */
 int oemb200_fit_sparse(const int *row_idx, const int *col_ptr, const double *values, int64_t n, int p,
                        const double *y, const oemb200_spec *spec, const oemb200_opts *opts,
                        oemb200_result *res);
