@@ -9,9 +9,12 @@
 // (re)built, X'WX runs on the FP64 tensor pipe with the row weight fused into the fragment load
 // (gram_syrk_kernel<WEIGHT>) and the Lanczos eigenvalue inside the path kernel.
 //
-// The IRLS state never leaves the device: the iterate, the gradient, XY = XX beta + grad and the inner OEM loop are
-// chained kernels on one stream; row-sharded runs sum the (p+1)-vector gradient in stream order (comm.cu); the only
-// host round trip per IRLS iteration is ONE stream synchronisation that reads the stop-rule flag from pinned memory.
+// The IRLS state never leaves the device.  An iteration of the dense driver is three launches on one stream: the data pass
+// (+ its partial-sum kernel), in row-sharded runs the sum of the (p+1)-vector gradient (comm.cu), and the path launch, which
+// forms XY = XX beta + grad from the XX slice its members load anyway, runs the inner OEM loop, applies the outer stop rule
+// and leaves the next pass's coefficients (PathProblem::xy_grad / irls_*); their phase clocks are kept on the device.  The
+// only host round trip per IRLS iteration is ONE event synchronisation that reads the stop-rule flag from pinned memory,
+// and it is hidden behind the next iteration, which is enqueued one ahead and predicated on the device-side verdict.
 // The reference's quirks are kept: the data pass is skipped on the first IRLS
 // iteration of a warm lambda, W is clamped at index = IRLS counter, eigen factor 1.0005.
 #include <algorithm>
@@ -98,7 +101,8 @@ __global__ void irls_pack_grad_kernel(const double *__restrict__ xr, const doubl
 // of that lambda -- this one included -- returns at once, so the host may enqueue iteration it + 1 before it has read
 // iteration it's verdict.
 // With `b` given it also prepares the NEXT data pass: b = beta_new[icpt:] o colsq_inv, b0 = beta_new[0] (what
-// irls_coef_kernel computes) -- one launch less per IRLS iteration.
+// irls_coef_kernel computes).  The dense driver no longer launches this kernel -- the same steps are the last thing its
+// path launch does (oem_path_kernel, "IRLS epilogue") -- the sparse driver does.
 __global__ void irls_stop_kernel(const double *__restrict__ cur, const double *__restrict__ prev, int q, double tol,
                                  const int *__restrict__ niter, long long *__restrict__ iters_total,
                                  volatile int *__restrict__ host_flag, int *__restrict__ conv,
@@ -322,7 +326,7 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
                 bool rebuilt = false, form_xy = false;
                 if (!(k == 0 && !on_lam_1)) {
                     const bool need_w = (k == 0 && on_lam_1) || o->hessian_full;
-                    if (k == 0) {      // later passes of this lambda get b from the previous iteration's irls_stop_kernel
+                    if (k == 0) {      // later passes of this lambda get b from the previous iteration's path launch (IRLS epilogue)
                         irls_coef_kernel<<<(p + 255) / 256, 256, 0, cx.stream>>>(cur, cinv_dev, p, icpt, d_b.p, d_b0.p, skip);
                         cx.st.kernel_launches += 1;
                     }
