@@ -26,13 +26,17 @@
 // convergence decisions without any further communication.  Reductions use fixed orders.
 // Small problems (q <= 256, coordinate-wise penalties) take the register-resident variant further down
 // (oem_path_reg_kernel): there a DMMA would waste 4/8..7/8 of its B operand on 1..4 chains, and the FP64
-// CUDA-core pipe (measured: same rate as DMMA on B200) runs the product from registers.
+// CUDA-core pipe (measured: same rate as DMMA on B200) runs the product from registers.  The same holds at the other
+// end: in the global mode with one 8-column atom per member and <= 4 chains (q ~ 450..1184: oem / big.oem / the sparse
+// entry / the logistic inner loop at p = 1000) the members keep their XX slice in registers and run matvec_reg
+// (oem_path_kernel<MODE_GLOBAL, RPT>); the DMMA mat-vec serves everything else.
 // Three exchange modes, chosen on the host from q:
 //     MODE_SINGLE   the whole A fits one CTA: u goes straight into shared memory, __syncthreads only
 //     MODE_CLUSTER  A fits the shared memory of a thread-block cluster (<= 8 CTAs): every member stores
 //                   its u slice into all members' shared memory (DSMEM, st.shared::cluster) and the
 //                   barrier is the hardware cluster barrier
-//     MODE_GLOBAL   larger q: u goes through an L2-resident buffer, barrier = one atomic counter per team
+//     MODE_GLOBAL   larger q: u goes through an L2-resident buffer, barrier = one atomic counter per team, then ONE batch of
+//                   loads fetches every chain's published vector and the members' violation masks
 // Everything an iteration needs besides u (chain descriptors, lambdas, penalty factors, XY, group
 // tables) is copied to shared memory once: the gpu-scope synchronisation of the barrier invalidates
 // L1, so any per-iteration global read would be an L2 round trip on the critical path.  The prox
