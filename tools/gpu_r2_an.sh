@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: the advance-on-convergence variant these runs measured was dropped (no gain); OEMB200_IRLS_NO_ADVANCE no longer exists.
 # 2 GPUs: multi-GPU tests, then the logistic leg with and without advance-on-convergence (same library, env switch)
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -x 2>&1 | tail -2

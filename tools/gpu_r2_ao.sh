@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: the OEMB200_FG_COLS switch this run used was an experiment (4 columns per CTA stayed); it no longer exists.
 # fold gather: 4 / 8 / 16 columns per CTA (index traffic 12.5 / 6 / 3 % of the matrix) on configs[2], then the xval tests
 for c in 4 8 16 4 8 16; do
   OEMB200_FG_COLS=$c timeout 120 python tools/bench_configs.py --configs 3 --reps 3 2>&1 | tail -1 | python -c "
