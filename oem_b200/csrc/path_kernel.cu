@@ -1249,17 +1249,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_kernel(const PathArgs 
 // so nothing else is synchronised until a chain moves to its next lambda.
 constexpr int PR_MAXCT = 4;       // chains per Gram handled by the register variant
 
-// coordinate-wise prox with the per-lambda constants cp[0..7] (see set_cpar) -- same arithmetic as mv_finish
-__device__ __forceinline__ double prox_coord(int kind, double u, double pfj, const double *cp, double gamma) {
-    const double tp = pfj * cp[0];
-    if (kind == 3) return div_r(u, cp[1], cp[4]);
-    if (!abs_gt(u, tp * cp[2])) return 0.0;            // every rule returns 0 below its first threshold
-    const double dp = cp[1], rdp = cp[4], gammad = cp[5], den2 = cp[6], rden2 = cp[7];
-    if (kind == 2) return st_scad_r(u, tp, dp, rdp, gamma, gammad, den2, rden2);
-    if (kind == 1) return st_mcp_r(u, tp, dp, rdp, gammad, den2, rden2);
-    return st_lasso_r(u, tp, dp, rdp);
-}
-
 template <int CPW, int KPL, int NCT>
 __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathArgs a) {
     constexpr int LPC = 32 / CPW;             // lanes that share one column after the butterfly
@@ -1353,11 +1342,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathA
     if (NC > 1) cluster_sync_all();      // peers may start storing into my buffers
     else __syncthreads();
     // per-lambda constants of every chain live in registers; refreshed when a chain moves to its next lambda
-    double cp[NCT][8];
+    // ... as the thresholds of the region tests of THIS lane's column (prox_select), so that an iteration's prox is a few
+    // integer comparisons, one select and one Markstein division after the column sum arrives
+    ProxPre pk[NCT];
+    auto load_pre = [&](int c) {
+        const double *cp = cpar + c * 8;
+        const double gamma = gam[c];
+        pk[c].kind = kind[c];
+        pk[c].tp = pfj * cp[0]; pk[c].dp = cp[1]; pk[c].rdp = cp[4]; pk[c].den2 = cp[6]; pk[c].rden2 = cp[7];
+        pk[c].thr_big = cp[5] * pk[c].tp;
+        pk[c].thr_mid = (pk[c].dp + 1.0) * pk[c].tp;
+        pk[c].gpen = gamma * pk[c].tp; pk[c].gm1 = gamma - 1.0;
+        pk[c].pv = 0.0; pk[c].tolpv = 0.0;
+    };
 #pragma unroll
-    for (int c = 0; c < NCT; ++c)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) cp[c][e] = cpar[c * 8 + e];
+    for (int c = 0; c < NCT; ++c) load_pre(c);
 
     const unsigned all = (1u << NCT) - 1u;
     int par = 0;
@@ -1392,7 +1391,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathA
         double rnew[NCT];
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
-            double r = prox_coord(kind[c], tot[c] + xyj, pfj, cp[c], gam[c]);
+            double r = prox_select(pk[c], tot[c] + xyj);
             if (!jvalid) r = 0.0;
             const double pv = prev[c];
             if (__double_as_longlong(r) != __double_as_longlong(pv)) {
@@ -1463,10 +1462,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) oem_path_reg_kernel(const PathA
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < NCT; ++c)
-                if ((advanced >> c) & 1u) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) cp[c][e] = cpar[c * 8 + e];
-                }
+                if ((advanced >> c) & 1u) load_pre(c);
         }
         par ^= 1;
         ++niters;
