@@ -139,32 +139,6 @@ __device__ __forceinline__ double div_r(double x, double d, double r) {
     const double e = fma(-d, q0, x);
     return fma(e, r, q0);
 }
-// same rules as st_lasso / st_mcp / st_scad below, with the reciprocals of the denominators precomputed
-__device__ __forceinline__ double st_lasso_r(double v, double pen, double d, double rd) {
-    if (v > pen) return div_r(v - pen, d, rd);
-    if (v < -pen) return div_r(v + pen, d, rd);
-    return 0.0;
-}
-__device__ __forceinline__ double st_mcp_r(double v, double pen, double d, double rd, double gammad, double dmg, double rdmg) {
-    if (fabs(v) > gammad * pen) return div_r(v, d, rd);
-    if (v > pen) return div_r(v - pen, dmg, rdmg);
-    if (v < -pen) return div_r(v + pen, dmg, rdmg);
-    return 0.0;
-}
-__device__ __forceinline__ double st_scad_r(double v, double pen, double d, double rd, double gamma, double gammad, double den2,
-                                            double rden2) {
-    if (fabs(v) > gammad * pen) return div_r(v, d, rd);
-    if (fabs(v) > (d + 1.0) * pen) {
-        const double gp = (gamma - 1.0) * v, gpen = gamma * pen;
-        if (gp > gpen) return div_r(gp - gpen, den2, rden2);
-        if (gp < -gpen) return div_r(gp + gpen, den2, rden2);
-        return 0.0;
-    }
-    if (v > pen) return div_r(v - pen, d, rd);
-    if (v < -pen) return div_r(v + pen, d, rd);
-    return 0.0;
-}
-
 // ---- thresholding family (coordinate-wise), operation order as in src/oem_dense.h:76-149 ----
 __device__ __forceinline__ double st_lasso(double v, double pen, double d) {
     if (v > pen) return (v - pen) / d;
@@ -403,14 +377,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
 }
 
 
-// slow path of the coordinate-wise prox (non-zero result), out of line: the persistent loop must stay small
-__device__ __noinline__ double prox_coord_nonzero(int kind, double u, double tp, const double *cp, double gamma) {
-    const double dp = cp[1], rdp = cp[4], gammad = cp[5], den2 = cp[6], rden2 = cp[7];
-    if (kind == 2) return st_scad_r(u, tp, dp, rdp, gamma, gammad, den2, rden2);
-    if (kind == 1) return st_mcp_r(u, tp, dp, rdp, gammad, den2, rden2);
-    return st_lasso_r(u, tp, dp, rdp);
-}
-
 // sums acc[c][*] over the 32 lanes for NCT chains at once (stage-major so the chains' shuffles overlap):
 // on return tot[c] in lane l is the total of column l / (32 / CPW)
 template <int NCT, int CPW>
@@ -433,6 +399,29 @@ __device__ __forceinline__ void reduce_cols(double (&acc)[NCT][CPW], double (&to
     for (int off = 16 / CPW; off >= 1; off >>= 1)
 #pragma unroll
         for (int c = 0; c < NCT; ++c) tot[c] += __shfl_xor_sync(0xffffffffu, tot[c], off);
+}
+
+// Coordinate-wise prox without divergent branches (the lanes of the finishing warp serve different penalties).  Everything
+// that does not depend on u -- the thresholds of the region tests -- is computed BEFORE the sums arrive; afterwards the
+// region tests run on the integer pipe (abs_gt), select ONE numerator / denominator pair, and a single Markstein division
+// follows.  Same operations on the same operands as st_lasso / st_mcp / st_scad above with x / d taken as div_r(x, d, 1 / d)
+// (v - copysign(pen, v) is v - pen
+// for v > 0 and v + pen for v < 0; |x| > t for t >= 0 is the integer comparison of the bit patterns).
+struct ProxPre {
+    double tp, thr_big, thr_mid, gpen, gm1, dp, rdp, den2, rden2, tolpv, pv;
+    int kind;
+};
+__device__ __forceinline__ double prox_select(const ProxPre &k, double u) {
+    double num = u - copysign(k.tp, u), den = k.dp, rden = k.rdp;
+    bool nz = abs_gt(u, k.tp);
+    if (k.kind == 1) { den = k.den2; rden = k.rden2; }
+    if (k.kind == 2 && abs_gt(u, k.thr_mid)) {
+        const double gp = k.gm1 * u;
+        num = gp - copysign(k.gpen, gp); den = k.den2; rden = k.rden2;
+        nz = abs_gt(gp, k.gpen);
+    }
+    if (k.kind == 3 || ((k.kind == 1 || k.kind == 2) && abs_gt(u, k.thr_big))) { num = u; den = k.dp; rden = k.rdp; nz = true; }
+    return nz ? div_r(num, den, rden) : 0.0;
 }
 
 // ---- mat-vec on the FP64 tensor pipe with the prox / stop rule fused into its epilogue ----
@@ -460,12 +449,13 @@ __device__ __forceinline__ void mv_publish(const MvCtx &m, double *dst_local, in
 __device__ __forceinline__ double mv_finish(const MvCtx &m, unsigned fastmask, const double *prev, int c, int j, double u, bool &viol) {
     if (!((fastmask >> c) & 1u)) return u;
     const double *cp = m.cpar + c * 8;
-    const int kind = m.kind[c];
-    const double tp = m.pf[j] * cp[0];
-    double r = 0.0;
-    if (kind == 3) r = div_r(u, cp[1], cp[4]);
-    else if (abs_gt(u, tp * cp[2])) r = prox_coord_nonzero(kind, u, tp, cp, m.gam[c]);   // else every rule returns 0
+    const double gamma = m.gam[c];
+    ProxPre k;                                   // everything but the last line is independent of u
+    k.kind = m.kind[c];
+    k.tp = m.pf[j] * cp[0]; k.dp = cp[1]; k.rdp = cp[4]; k.den2 = cp[6]; k.rden2 = cp[7];
+    k.thr_big = cp[5] * k.tp; k.thr_mid = (k.dp + 1.0) * k.tp; k.gpen = gamma * k.tp; k.gm1 = gamma - 1.0;
     const double pv = prev[(size_t)c * m.qs + j];
+    const double r = prox_select(k, u);
     if (__double_as_longlong(r) != __double_as_longlong(pv)) {      // identical bit patterns (0 -> 0) need no arithmetic
         const bool bc = abs_gt(r, 1e-13), bp = abs_gt(pv, 1e-13);
         if (bc != bp || (bc && abs_gt(r - pv, m.tol * fabs(pv)))) viol = true;                 // |(cur-prev)/prev| > tol
@@ -573,28 +563,6 @@ __device__ __noinline__ void matvec_dmma(const MvCtx &m, const double *vec, doub
 // (conflict-free, NV * RPT loads), runs 8 * NV independent DFMA chains, reduces the 8 * NV sums with the multi-value
 // butterfly (fixed order), and ONE warp finishes: fixed-order sum over the 8 warps, + XY, coordinate-wise prox, stop
 // rule, publication of the next beta and of the member's violation mask.
-// Coordinate-wise prox without divergent branches (the lanes of the finishing warp serve different penalties).  Everything
-// that does not depend on u -- the thresholds of the region tests -- is computed BEFORE the sums arrive; afterwards the
-// region tests run on the integer pipe (abs_gt), select ONE numerator / denominator pair, and a single Markstein division
-// follows.  Same operations on the same operands as st_lasso_r / st_mcp_r / st_scad_r (v - copysign(pen, v) is v - pen
-// for v > 0 and v + pen for v < 0; |x| > t for t >= 0 is the integer comparison of the bit patterns).
-struct ProxPre {
-    double tp, thr_big, thr_mid, gpen, gm1, dp, rdp, den2, rden2, tolpv, pv;
-    int kind;
-};
-__device__ __forceinline__ double prox_select(const ProxPre &k, double u) {
-    double num = u - copysign(k.tp, u), den = k.dp, rden = k.rdp;
-    bool nz = abs_gt(u, k.tp);
-    if (k.kind == 1) { den = k.den2; rden = k.rden2; }
-    if (k.kind == 2 && abs_gt(u, k.thr_mid)) {
-        const double gp = k.gm1 * u;
-        num = gp - copysign(k.gpen, gp); den = k.den2; rden = k.rden2;
-        nz = abs_gt(gp, k.gpen);
-    }
-    if (k.kind == 3 || ((k.kind == 1 || k.kind == 2) && abs_gt(u, k.thr_big))) { num = u; den = k.dp; rden = k.rdp; nz = true; }
-    return nz ? div_r(num, den, rden) : 0.0;
-}
-
 template <int RPT, int NV>
 __device__ __forceinline__ void matvec_reg(const double (&areg)[8][RPT], const MvCtx &m, const double *vec, int *inactive,
                                            int add_xy, unsigned fastmask, int par, int *gflag_slot) {
