@@ -294,7 +294,7 @@ int oemb200_xb_logistic(const double *x_dev, int64_t n, int p, int64_t ldx, cons
  * once, grad_dev[0] = sum_i (y_i - prob_i), grad_dev[1 + j] = sum_i x_ij (y_i - prob_i); prob_dev / w_dev as in
  * oemb200_xb_logistic (either may be NULL).  The slab copy is built inside the call (time reported separately in
  * *ms_relayout_out); the pass is run `reps` times and *ms_out is the CUDA-event average of one pass.  Returns
- * OEMB200_EUNSUPPORTED for p outside the slab kernel's range (128..2048).
+ * OEMB200_EUNSUPPORTED for p outside the slab kernel's range (8..2048).
  * src/oem_logistic_dense.h:864-949 + 970-992 in one sweep. */
 int oemb200_logit_slab_pass(const double *x_dev, int64_t n, int p, int64_t ldx, const double *b_dev, double b0,
                             const double *y_dev, double *prob_dev, double *w_dev, double *grad_dev, int reps,

@@ -885,7 +885,7 @@ int oemb200_logit_slab_pass(const double *x_dev, int64_t n, int p, int64_t ldx, 
                             double *ms_out, double *ms_relayout_out) {
     return guarded([&] {
         if (!x_dev || !b_dev || !y_dev || !grad_dev || n < 1 || p < 1 || ldx < n) fail(OEMB200_EINVAL, "logit_slab_pass: bad arguments");
-        if (!logit_slab_rows(p)) fail(OEMB200_EUNSUPPORTED, "the slab kernel covers 128 <= p <= 2048 (p = %d)", p);
+        if (!logit_slab_rows(p)) fail(OEMB200_EUNSUPPORTED, "the slab kernel covers 8 <= p <= 2048 (p = %d)", p);
         oemb200_opts o_; phase_ctx_opts(o_, stream);
         Ctx cx(&o_);
         cudaEvent_t e0, e1, e2;

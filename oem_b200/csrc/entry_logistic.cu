@@ -218,7 +218,8 @@ void fit_logistic(const double *x, int64_t n, int p, int64_t ldx, const double *
     //      slab (default where it applies): X re-laid out once, one HBM sweep per pass (logit_slab.cu)
     //      sweeps: xb_kernel + colstats_kernel, two HBM sweeps per pass (small / very wide p, or no room for the copy)
     const char *route_env = getenv("OEMB200_LOGIT_ROUTE");
-    bool slab = logit_slab_rows(p) != 0 && !(route_env && strcmp(route_env, "sweeps") == 0);
+    bool slab = logit_slab_rows(p) != 0 && !(route_env && strcmp(route_env, "sweeps") == 0) &&
+                (logit_slab_preferred(n, p) || (route_env && strcmp(route_env, "slab") == 0));
     DBuf<double> slabs_own;
     const double *slabs_p = nullptr;
     if (slab && cache && cache->slabs && cache->rt == logit_slab_rows(p)) {

@@ -257,7 +257,7 @@ slab_relayout_kernel(const double *__restrict__ X, long long n, int p, long long
 struct SlabShape { int rt, nc, threads, ctas; };
 static SlabShape slab_shape(int p) {
     SlabShape z{0, 0, 0, 0};
-    if (p < 128 || p > 2048) return z;
+    if (p < 8 || p > 2048) return z;
     static const bool two = [] { const char *e = getenv("OEMB200_SLAB_CTAS"); return !(e && e[0] == '1'); }();
     if (p <= 512) return two ? SlabShape{8, (p + 255) / 256, 256, 2} : SlabShape{16, 1, 512, 1};
     if (p <= 1024) return two ? SlabShape{4, (p + 255) / 256, 256, 2} : SlabShape{8, 2, 512, 1};
@@ -265,6 +265,16 @@ static SlabShape slab_shape(int p) {
 }
 
 int logit_slab_rows(int p) { return slab_shape(p).rt; }      // rows per slab; 0 = the slab route does not apply
+
+// Which data-pass route a logistic fit takes by default.  From p = 128 on the slab kernel runs at the HBM copy rate.  Below,
+// most of its 256 threads own no column and a pass costs ~1 us per 8-row slab and CTA, whatever p is -- but it is 2 launches
+// against the 5 of the two column sweeps, which decides problems small enough to be launch-bound.  Measured on a B200
+// (40 lambdas, ms per fit, slab / sweeps): n = 5e4: p = 8 14.1 / 16.0, p = 16 12.9 / 16.1, p = 64 16.3 / 17.5, p = 100 (the
+// vignette's example) 26.6 / 34.1;  n = 1e6: p = 16 48.5 / 18.4, p = 64 57.6 / 34.5 (tools/bench_logit_route_small_p.py).
+bool logit_slab_preferred(int64_t n, int p) {
+    if (!slab_shape(p).rt) return false;
+    return p >= 128 || n <= 100000;
+}
 
 size_t logit_slab_doubles(int64_t n, int p) {
     const int rt = logit_slab_rows(p);

@@ -273,7 +273,8 @@ void scale_sym_launch(Ctx &cx, int p, const double *sinv, const double *XXin, co
 void symv_add_launch(Ctx &cx, int q, const double *M, const double *x, const double *add, double *y);
 
 // ---------------- logit_slab.cu ----------------
-int logit_slab_rows(int p);                       // rows per slab (0: the slab route does not apply to this p)
+int logit_slab_rows(int p);                       // rows per slab (0: the slab route does not apply to this p; it does for 8 <= p <= 2048)
+bool logit_slab_preferred(int64_t n, int p);      // the default route: slab for p >= 128, and for smaller p when n <= 1e5 (launch-bound)
 size_t logit_slab_doubles(int64_t n, int p);      // size of the re-laid-out copy
 void logit_slab_relayout(Ctx &cx, const double *X, int64_t n, int p, int64_t ld, double *slabs);
 // one pass over the slabs: prob, w (may be NULL), grad_out[0] = sum (y - prob), grad_out[1 + j] = sum_i x_ij (y_i - prob_i)

@@ -128,12 +128,15 @@ def test_logistic(lib, oracle, hessian):
     (4001, 530, False, True, None),        # 8-row slabs, three columns per thread
     (3000, 1030, True, True, None),        # 4-row slabs
     (5003, 300, True, True, "sweeps"),     # same problem through the two-sweep route
-    (3001, 17, False, True, None),         # small p: two sweeps
+    (3001, 17, False, True, None),         # small p, small n: launch-bound, the slab route (2 launches per pass) wins
+    (3001, 17, False, True, "sweeps"),     # the same through the two sweeps
+    (100003, 9, True, True, None),         # small p, n > 1e5: two sweeps by default
+    (3001, 5, True, False, None),          # p < 8: two sweeps
 ])
 def test_logistic_data_pass_routes(lib, oracle, monkeypatch, n, p, intercept, standardize, route):
-    # the IRLS data pass either reads a row-slab copy of X once (logit_slab.cu, 128 <= p <= 2048) or sweeps the
-    # column-major X twice (xb_kernel + colstats_kernel); OEMB200_LOGIT_ROUTE=sweeps forces the latter.  Both must
-    # reproduce the oracle's path.
+    # the IRLS data pass either reads a row-slab copy of X once (logit_slab.cu: 128 <= p <= 2048, and 8 <= p < 128 when
+    # n <= 1e5) or sweeps the column-major X twice (xb_kernel + colstats_kernel); OEMB200_LOGIT_ROUTE=sweeps forces the
+    # latter.  Both must reproduce the oracle's path.
     if route:
         monkeypatch.setenv("OEMB200_LOGIT_ROUTE", route)
     X, y = binomial_problem(300 + p, n, p)
@@ -144,7 +147,7 @@ def test_logistic_data_pass_routes(lib, oracle, monkeypatch, n, p, intercept, st
     for lg, lr in zip(got["loss"], ref["loss"]):
         assert np.allclose(lg, lr, rtol=1e-9)
     st = got["stats"]
-    expect_slab = route is None and 128 <= p <= 2048
+    expect_slab = route is None and (128 <= p <= 2048 or (8 <= p < 128 and n <= 100000))
     assert st["data_passes"] > 0 and (st["ms_relayout"] > 0) == expect_slab
     assert st["host_syncs"] <= int(sum(np.sum(v) for v in got["niter"])) + 8 * len(got["niter"][0]) + 16
 
